@@ -1,0 +1,181 @@
+/*
+ * mbgdml_b200 -- C ABI of the B200-native many-body GDML prediction path.
+ *
+ * The reference (keithgroup/mbGDML) has no FFI: its plugin surface is the Python
+ * callable handed to mbePredict (reference mbgdml/mbe.py:521-532, call sites
+ * mbe.py:809-811 and 949-951).  This header is the boundary a binding for that
+ * callable targets: plain pointers and sizes, no torch / numpy types.
+ * INTEGRATION.md shows the ctypes stub that mbgdml/predictors/gdml_predict.py
+ * would use.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns MBG_OK (0) or a negative error code; the message
+ *     of the last error on the calling thread is mbg_last_error();
+ *   - all floating point is IEEE double; all index arrays are int32 unless noted;
+ *   - the caller owns every buffer it passes; nothing is retained after a call
+ *     returns except by mbg_model_create (which copies to device memory);
+ *   - one in-flight call per context; calls are stream-ordered on the context's
+ *     CUDA stream and return after the result buffers are valid (host buffers)
+ *     or after the work is enqueued (device buffers, MBG_FLAG_*_ON_DEVICE).
+ */
+#ifndef MBGDML_B200_H
+#define MBGDML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBG_ABI_VERSION 1
+
+#define MBG_OK 0
+#define MBG_ERR_ARG (-1)         /* invalid argument (the Python mirror raises ValueError/AssertionError) */
+#define MBG_ERR_CUDA (-2)        /* CUDA runtime failure */
+#define MBG_ERR_UNSUPPORTED (-3) /* valid request this build has no kernel for (no CPU fallback exists) */
+#define MBG_ERR_NOMEM (-4)
+
+#define MBG_MAX_ORDER 8       /* entities per fragment */
+#define MBG_MAX_FRAG_ATOMS 24 /* atoms per fragment */
+#define MBG_MAX_ALCHEMY 16    /* alchemical scalers per job */
+
+typedef struct mbg_context_s *mbg_context_t;
+typedef struct mbg_model_s *mbg_model_t;
+
+/* Acceptance criteria evaluated on device (reference mbgdml/descriptors.py:32-201). */
+enum {
+  MBG_CRIT_NONE = 0,              /* Criteria is None or cutoff is None: accept everything      */
+  MBG_CRIT_COM_DISTANCE_SUM = 1,  /* descriptors.com_distance_sum  (descriptors.py:159-201)       */
+  MBG_CRIT_MAX_ATOM_PAIR_DIST = 2 /* descriptors.max_atom_pair_dist (descriptors.py:131-156)      */
+};
+enum {
+  MBG_BOUND_UPPER = 0, /* accept iff v <  hi            (descriptors.py:96-97) */
+  MBG_BOUND_LOWER = 1, /* accept iff v >  lo            (descriptors.py:98-99) */
+  MBG_BOUND_RANGE = 2  /* accept iff lo < v && v < hi   (descriptors.py:93-94) */
+};
+
+/* A GDML model as stored in the reference's .npz (gdml_model.py:60-125). */
+typedef struct mbg_model_desc {
+  int32_t n_atoms;               /* atoms per fragment = len(model["z"])                               */
+  int32_t order;                 /* n-body order = len(comp_ids)                                        */
+  int32_t n_train;               /* T = R_desc.shape[1]                                                 */
+  int32_t n_perms;               /* P = perms.shape[0]                                                  */
+  double sig;                    /* model["sig"]                                                        */
+  double c;                      /* model["c"]   (integ_c)                                              */
+  double std;                    /* model["std"] (1.0 when absent)                                      */
+  const double *R_desc;          /* [D][T] row-major, D = n_atoms(n_atoms-1)/2  (model["R_desc"])      */
+  const double *R_d_desc_alpha;  /* [T][D] row-major                         (model["R_d_desc_alpha"]) */
+  const int64_t *tril_perms_lin; /* [P*D]                                    (model["tril_perms_lin"]) */
+  const double *alphas_E;        /* [T] or NULL                              (model["alphas_E"])       */
+  /* Criteria attached to the model by the caller (gdmlModel(model, criteria=...)). */
+  int32_t criteria_kind;         /* MBG_CRIT_*                                                          */
+  int32_t criteria_bound;        /* MBG_BOUND_*                                                         */
+  double criteria_lo, criteria_hi;
+  const int32_t *criteria_entity_ids; /* [n_atoms] desc_kwargs["entity_ids"] for com_distance_sum, else NULL */
+} mbg_model_desc;
+
+/* The supersystem: which atoms form which entity, masses, optional periodic cell
+ * (reference mbgdml/periodic.py:32-140).  Coordinates are passed per call. */
+typedef struct mbg_system_desc {
+  int32_t n_atoms;
+  int32_t n_entities;
+  const int32_t *entity_offsets; /* [n_entities+1] CSR offsets into entity_atoms                           */
+  const int32_t *entity_atoms;   /* atom indices of each entity, ascending (np.where(entity_ids == e)[0])  */
+  const double *masses;          /* [n_atoms] qcelemental.periodictable.to_mass(Z[i]) (descriptors.py:125) */
+  const double *cell;            /* [9] row-major cell vectors (Cell.cell_v) or NULL for no periodicity    */
+  double cell_cutoff;            /* Cell.cutoff (periodic.py:82); ignored when cell == NULL                */
+} mbg_system_desc;
+
+/* One model applied to the system: the fragments it predicts and its alchemical scalers. */
+typedef struct mbg_job {
+  mbg_model_t model;
+  /* Fragment source A (combs == NULL): utils.gen_combs(avail_entity_ids) (utils.py:449-489,
+   * mbe.py:785-787): tuples of the Cartesian product of the per-slot entity sets that are
+   * strictly ascending, in itertools.product order.  Enumerated on device. */
+  const int32_t *set_offsets;  /* [order+1] */
+  const int32_t *set_entities; /* concatenated per-slot entity ids */
+  /* Fragment source B (combs != NULL): explicit entity tuples, e.g. a ray chunk (mbe.py:823-828). */
+  const int32_t *combs; /* [n_combs][order] */
+  int64_t n_combs;
+  /* mbeAlchemyScale with linear_switching, already filtered to this model's order
+   * (alchemy.py:30-62, switching.py:30-48, mbe.py:789-796). */
+  int32_t n_alchemy;
+  const int32_t *alchemy_entity; /* [n_alchemy] */
+  const double *alchemy_factor;  /* [n_alchemy] */
+} mbg_job;
+
+#define MBG_FLAG_R_ON_DEVICE (1u << 0)   /* R is a device pointer                                       */
+#define MBG_FLAG_OUT_ON_DEVICE (1u << 1) /* E, F, virial are device pointers (left enqueued on stream)  */
+#define MBG_FLAG_VIRIAL (1u << 2)        /* accumulate sum_k r_k (x) f_k per fragment (stress.py:34-56) */
+#define MBG_FLAG_ACCUMULATE (1u << 3)    /* add into E/F/virial instead of overwriting                  */
+
+/* Counters returned per job. */
+typedef struct mbg_job_stats {
+  int64_t n_candidates; /* tuples examined (product space; this shard only) */
+  int64_t n_enumerated; /* strictly ascending tuples = what gen_combs yields (this shard only) */
+  int64_t n_accepted;   /* fragments that passed MIC cutoff and criteria and were evaluated    */
+} mbg_job_stats;
+
+const char *mbg_last_error(void);
+int mbg_abi_version(void);
+int mbg_device_count(int *count);
+
+int mbg_context_create(int device, mbg_context_t *ctx);
+int mbg_context_destroy(mbg_context_t ctx);
+/* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = context's own. */
+int mbg_context_set_stream(mbg_context_t ctx, void *cuda_stream);
+int mbg_context_synchronize(mbg_context_t ctx);
+/* Launch counters since context creation: number of kernels this library launched. */
+int mbg_context_launch_count(mbg_context_t ctx, int64_t *n_launches);
+/* Device time (ms, CUDA events on the context's stream) of the Matern contraction launches and of
+ * all other launches during the most recent mbg_predict / mbg_predict_decomp call. */
+int mbg_context_last_timing(mbg_context_t ctx, double *ms_contract, double *ms_other, int64_t *n_contract_launches);
+/* Per-launch records of the Matern contraction kernel in the most recent call: fragment size,
+ * fragments processed, padded training rows, permutations and device time (ms).  Arrays hold
+ * max_records entries; *n_records receives the number of launches (may exceed max_records). */
+int mbg_context_last_launches(mbg_context_t ctx, int32_t max_records, int32_t *n_records, int32_t *n_frag_atoms,
+                              int64_t *n_fragments, int32_t *n_train_padded, int32_t *n_perms, double *ms);
+
+/* gdmlModel(model, criteria=...)._unpack (gdml_model.py:90-125): upload + permutation tables. */
+int mbg_model_create(mbg_context_t ctx, const mbg_model_desc *desc, mbg_model_t *model);
+int mbg_model_destroy(mbg_model_t model);
+
+/* mbePredict.predict (mbe.py:1009-1104) for all frames and all jobs in one call:
+ *   for frame, for job: predict_gdml(Z, R[frame], entity_ids, combs, model, periodic_cell, ...)
+ *   (gdml_predict.py:170-272) accumulated into E[n_frames], F[n_frames][n_atoms][3] and,
+ *   with MBG_FLAG_VIRIAL, virial[n_frames][9] (un-normalised; the caller divides by the volume,
+ *   mbe.py:1079).  Fragments are partitioned block-cyclically over `shard_count` callers
+ *   (one per GPU); each returns its partial sums, to be all-reduced by the caller.
+ *   stats may be NULL, else [n_jobs]. */
+int mbg_predict(mbg_context_t ctx, const mbg_system_desc *sys, const double *R, int32_t n_frames,
+                const mbg_job *jobs, int32_t n_jobs, uint32_t flags, int32_t shard_rank,
+                int32_t shard_count, double *E, double *F, double *virial, mbg_job_stats *stats);
+
+/* predict_gdml_decomp (gdml_predict.py:275-364) for one frame and one job with explicit
+ * combs: E[n_combs], F[n_combs][model n_atoms][3]; rows of rejected fragments are NaN. */
+int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc *sys, const double *R,
+                       const mbg_job *job, uint32_t flags, double *E, double *F, mbg_job_stats *stats);
+
+/* utils.gen_combs (utils.py:449-489) on device.  Call with combs == NULL to get the count,
+ * then with a buffer of [*n_combs][order] int32. */
+int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t *set_offsets,
+                  const int32_t *set_entities, int32_t *combs, int64_t *n_combs);
+
+/* Criteria.desc on device for a batch of same-size structures (descriptors.py:131-201):
+ * R[n_R][n_atoms][3] -> values[n_R].  entity_ids is used by MBG_CRIT_COM_DISTANCE_SUM only. */
+int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const double *masses,
+                      const int32_t *entity_ids, const double *R, int64_t n_R, double *values);
+
+/* Cell.r_mic (periodic.py:86-107) on device for one fragment: r[n][3] -> out[n][3];
+ * *accepted = 0 when any pair distance >= cutoff (the reference returns None). */
+int mbg_r_mic(mbg_context_t ctx, const double *cell, double cutoff, const double *r, int32_t n,
+              double *out, int32_t *accepted);
+
+/* Measured FP64 FMA-pipe peak of this GPU (dependent-chain-free DFMA loop, CUDA-event timed),
+ * in TFLOP/s: the roofline denominator bench.py reports against. */
+int mbg_measure_fp64_peak(mbg_context_t ctx, double *tflops, double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBGDML_B200_H */

@@ -1,0 +1,152 @@
+"""Host glue between the reference-shaped Python surface and the C ABI: turns
+(Z, entity_ids, models, combs, cell, scalers) into mbg_system_desc / mbg_job arrays."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .descriptors import masses_of
+from .utils import CombGenerator
+
+
+class System:
+    """mbg_system_desc plus the arrays that back its pointers."""
+
+    def __init__(self, Z, entity_ids, periodic_cell=None, need_masses=True):
+        Z = np.asarray(Z)
+        entity_ids = np.asarray(entity_ids)
+        if entity_ids.shape != Z.shape:
+            raise ValueError("entity_ids must have one entry per atom")
+        if entity_ids.size and entity_ids.min() < 0:
+            raise ValueError("entity_ids must be non-negative")
+        self.n_atoms = int(Z.shape[0])
+        self.n_entities = int(entity_ids.max()) + 1 if entity_ids.size else 0
+        # np.where(entity_ids == e)[0] for every e: a stable sort keeps atoms ascending within an entity
+        self.entity_atoms = _native.as_i32(np.argsort(entity_ids, kind="stable"))
+        counts = np.bincount(entity_ids.astype(np.int64), minlength=self.n_entities)
+        self.entity_offsets = np.zeros(self.n_entities + 1, dtype=np.int32)
+        self.entity_offsets[1:] = np.cumsum(counts)
+        self.masses = _native.as_f64(masses_of(Z, strict=need_masses))
+        self.cell = None
+        cutoff = 0.0
+        if periodic_cell is not None:
+            self.cell, cutoff = periodic_cell.native_cell()
+        self.desc = _native.SystemDesc(
+            n_atoms=self.n_atoms, n_entities=self.n_entities,
+            entity_offsets=_native.ptr(self.entity_offsets, _native._ip),
+            entity_atoms=_native.ptr(self.entity_atoms, _native._ip),
+            masses=_native.ptr(self.masses, _native._dp),
+            cell=_native.ptr(self.cell, _native._dp), cell_cutoff=cutoff,
+        )
+
+
+def _needs_masses(models):
+    from .descriptors import com_distance_sum
+
+    return any(m.criteria is not None and m.criteria.cutoff is not None and m.criteria.desc is com_distance_sum
+               for m in models)
+
+
+def make_job(ctx, model, entity_combs, alchemy_scalers, keep):
+    """One mbg_job.  ``entity_combs`` is a CombGenerator (device enumeration from its sets) or any
+    iterable / array of entity tuples (explicit)."""
+    job = _native.Job()
+    job.model = model.native_handle(ctx)
+    order = int(model.nbody_order)
+    if isinstance(entity_combs, CombGenerator) and entity_combs._iter is None:
+        sets = entity_combs.sets
+        if len(sets) != order:
+            raise ValueError("number of entity sets differs from the model's n-body order")
+        offs = np.zeros(order + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(s) for s in sets])
+        vals = _native.as_i32(np.concatenate(sets) if offs[-1] else np.zeros(0))
+        keep += [offs, vals]
+        job.set_offsets = _native.ptr(offs, _native._ip)
+        job.set_entities = _native.ptr(vals, _native._ip)
+        job.n_combs = 0
+    else:
+        if isinstance(entity_combs, np.ndarray):
+            combs = entity_combs
+        else:
+            combs = np.array([tuple(c) for c in entity_combs], dtype=np.int64)
+        combs = _native.as_i32(combs.reshape(-1, order))
+        keep.append(combs)
+        # a non-NULL pointer marks the explicit source even when it is empty
+        job.combs = _native.ptr(combs if combs.size else np.zeros(1, dtype=np.int32), _native._ip)
+        if not combs.size:
+            keep.append(np.zeros(1, dtype=np.int32))
+            job.combs = _native.ptr(keep[-1], _native._ip)
+        job.n_combs = combs.shape[0]
+    scalers = list(alchemy_scalers or [])
+    if scalers:
+        ents = _native.as_i32([s.entity_id for s in scalers])
+        facs = _native.as_f64([s.native_factor() for s in scalers])
+        keep += [ents, facs]
+        job.n_alchemy = len(scalers)
+        job.alchemy_entity = _native.ptr(ents, _native._ip)
+        job.alchemy_factor = _native.ptr(facs, _native._dp)
+    return job
+
+
+def predict_total(ctx, Z, R, entity_ids, models, comb_sources, scalers_per_model, periodic_cell,
+                  compute_virial=False, shard=(0, 1), device_out=None):
+    """All frames x all jobs in one native call.  Returns (E, F, virial-or-None, stats).
+
+    ``R`` is a host array, or a contiguous float64 torch CUDA tensor (n_frames, n_atoms, 3) that
+    is already resident in HBM (MBG_FLAG_R_ON_DEVICE)."""
+    r_on_device = hasattr(R, "data_ptr")
+    if r_on_device:
+        assert R.is_cuda and R.is_contiguous() and R.dim() == 3 and R.element_size() == 8
+        n_frames, n_atoms = int(R.shape[0]), int(R.shape[1])
+        r_ptr = R.data_ptr()
+    else:
+        R = _native.as_f64(R)
+        if R.ndim == 2:
+            R = R[None]
+        n_frames, n_atoms = R.shape[0], R.shape[1]
+        r_ptr = R.ctypes.data
+    system = System(Z, entity_ids, periodic_cell, need_masses=_needs_masses(models))
+    if system.n_atoms != n_atoms:
+        raise ValueError("R and Z disagree on the number of atoms")
+    keep = []
+    jobs = (_native.Job * len(models))()
+    for k, (m, src, sc) in enumerate(zip(models, comb_sources, scalers_per_model)):
+        jobs[k] = make_job(ctx, m, src, sc, keep)
+    stats = (_native.JobStats * len(models))()
+    flags = _native.FLAG_VIRIAL if compute_virial else 0
+    if r_on_device:
+        flags |= _native.FLAG_R_ON_DEVICE
+    if device_out is not None:  # torch CUDA tensors (E, F, virial) for the multi-GPU path
+        E_t, F_t, V_t = device_out
+        flags |= _native.FLAG_OUT_ON_DEVICE
+        _native.check(ctx.lib.mbg_predict(
+            ctx.handle, C.byref(system.desc), r_ptr, n_frames, jobs, len(models), flags, shard[0], shard[1],
+            E_t.data_ptr(), F_t.data_ptr(), V_t.data_ptr() if V_t is not None else None, stats))
+        return None, None, None, [(_s.n_candidates, _s.n_enumerated, _s.n_accepted) for _s in stats]
+    E = np.zeros(n_frames)
+    F = np.zeros((n_frames, n_atoms, 3))
+    V = np.zeros((n_frames, 3, 3)) if compute_virial else None
+    _native.check(ctx.lib.mbg_predict(
+        ctx.handle, C.byref(system.desc), r_ptr, n_frames, jobs, len(models), flags, shard[0], shard[1],
+        E.ctypes.data, F.ctypes.data, V.ctypes.data if V is not None else None, stats))
+    return E, F, V, [(_s.n_candidates, _s.n_enumerated, _s.n_accepted) for _s in stats]
+
+
+def predict_decomp(ctx, Z, R, entity_ids, model, entity_combs, alchemy_scalers=None):
+    """One frame, one model, explicit combs -> per-fragment rows (NaN when rejected)."""
+    R = _native.as_f64(R)
+    system = System(Z, entity_ids, None, need_masses=_needs_masses([model]))
+    keep = []
+    combs = np.asarray(entity_combs)
+    job = make_job(ctx, model, combs.reshape(-1, int(model.nbody_order)), alchemy_scalers, keep)
+    n = int(job.n_combs)
+    n_frag_atoms = int(model.Z.shape[0])
+    E = np.full(n, np.nan)
+    F = np.full((n, n_frag_atoms, 3), np.nan)
+    st = _native.JobStats()
+    if n:
+        _native.check(ctx.lib.mbg_predict_decomp(ctx.handle, C.byref(system.desc), R.ctypes.data, C.byref(job), 0,
+                                                 E.ctypes.data, F.ctypes.data, C.byref(st)))
+    return E, F

@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in include/mbgdml_b200.h.
+
+The shared library is built in-tree (``mbgdml_b200/libmbgdml_b200.so``) by
+``python -m mbgdml_b200.build`` / ``__graft_entry__.build()``.  There is no CPU
+fallback: if the library is missing, or no B200 is visible, the product path
+raises :class:`NativeUnavailable`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+LIB_NAME = "libmbgdml_b200.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+MBG_OK, MBG_ERR_ARG, MBG_ERR_CUDA, MBG_ERR_UNSUPPORTED, MBG_ERR_NOMEM = 0, -1, -2, -3, -4
+CRIT_NONE, CRIT_COM_DISTANCE_SUM, CRIT_MAX_ATOM_PAIR_DIST = 0, 1, 2
+BOUND_UPPER, BOUND_LOWER, BOUND_RANGE = 0, 1, 2
+FLAG_R_ON_DEVICE, FLAG_OUT_ON_DEVICE, FLAG_VIRIAL, FLAG_ACCUMULATE = 1, 2, 4, 8
+
+# every symbol include/mbgdml_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "mbg_last_error", "mbg_abi_version", "mbg_device_count", "mbg_context_create", "mbg_context_destroy",
+    "mbg_context_set_stream", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
+    "mbg_context_last_launches",
+    "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_enumerate",
+    "mbg_criteria_eval", "mbg_r_mic", "mbg_measure_fp64_peak",
+]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class NativeUnavailable(RuntimeError):
+    """The CUDA library (or a B200) is not available; there is no CPU fallback."""
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("n_atoms", C.c_int32), ("order", C.c_int32), ("n_train", C.c_int32), ("n_perms", C.c_int32),
+        ("sig", C.c_double), ("c", C.c_double), ("std", C.c_double),
+        ("R_desc", _dp), ("R_d_desc_alpha", _dp), ("tril_perms_lin", _lp), ("alphas_E", _dp),
+        ("criteria_kind", C.c_int32), ("criteria_bound", C.c_int32),
+        ("criteria_lo", C.c_double), ("criteria_hi", C.c_double), ("criteria_entity_ids", _ip),
+    ]
+
+
+class SystemDesc(C.Structure):
+    _fields_ = [
+        ("n_atoms", C.c_int32), ("n_entities", C.c_int32), ("entity_offsets", _ip), ("entity_atoms", _ip),
+        ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double),
+    ]
+
+
+class Job(C.Structure):
+    _fields_ = [
+        ("model", C.c_void_p), ("set_offsets", _ip), ("set_entities", _ip), ("combs", _ip), ("n_combs", C.c_int64),
+        ("n_alchemy", C.c_int32), ("alchemy_entity", _ip), ("alchemy_factor", _dp),
+    ]
+
+
+class JobStats(C.Structure):
+    _fields_ = [("n_candidates", C.c_int64), ("n_enumerated", C.c_int64), ("n_accepted", C.c_int64)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree library and declare the prototypes."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeUnavailable(
+                f"{LIB_PATH} is missing: build it with `python -m mbgdml_b200.build` "
+                "(there is no CPU fallback for the prediction path)"
+            )
+        lib = C.CDLL(LIB_PATH)
+        lib.mbg_last_error.restype = C.c_char_p
+        lib.mbg_abi_version.restype = C.c_int
+        lib.mbg_device_count.argtypes = [C.POINTER(C.c_int)]
+        lib.mbg_context_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.mbg_context_destroy.argtypes = [C.c_void_p]
+        lib.mbg_context_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mbg_context_synchronize.argtypes = [C.c_void_p]
+        lib.mbg_context_launch_count.argtypes = [C.c_void_p, _lp]
+        lib.mbg_context_last_timing.argtypes = [C.c_void_p, _dp, _dp, _lp]
+        lib.mbg_context_last_launches.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _lp, _ip, _ip, _dp]
+        lib.mbg_model_create.argtypes = [C.c_void_p, C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]
+        lib.mbg_model_destroy.argtypes = [C.c_void_p]
+        lib.mbg_predict.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.c_int32, C.POINTER(Job), C.c_int32,
+                                    C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(JobStats)]
+        lib.mbg_predict_decomp.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.POINTER(Job), C.c_uint32,
+                                           C.c_void_p, C.c_void_p, C.POINTER(JobStats)]
+        lib.mbg_enumerate.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, _lp]
+        lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
+        lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
+        lib.mbg_measure_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+        for name in EXPORTED_SYMBOLS:
+            fn = getattr(lib, name)
+            if name != "mbg_last_error":
+                fn.restype = C.c_int
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    """Map a C-ABI return code onto the exception types of the reference's Python surface."""
+    if rc == MBG_OK:
+        return
+    msg = load_library().mbg_last_error().decode("utf-8", "replace")
+    if rc == MBG_ERR_ARG:
+        raise ValueError(msg)
+    if rc == MBG_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == MBG_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else typ()
+
+
+class Context:
+    """One native context = one GPU + one stream + scratch buffers."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        n = C.c_int(0)
+        rc = self.lib.mbg_device_count(C.byref(n))
+        if rc != MBG_OK or n.value == 0:
+            raise NativeUnavailable("no CUDA device visible: the mbgdml_b200 prediction path needs a B200 "
+                                    "(there is no CPU fallback)")
+        self.device = int(device)
+        h = C.c_void_p()
+        check(self.lib.mbg_context_create(self.device, C.byref(h)))
+        self.handle = h
+        self._models = {}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            for m in list(self._models.values()):
+                self.lib.mbg_model_destroy(m)
+            self._models.clear()
+            self.lib.mbg_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(self.lib.mbg_context_set_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(self.lib.mbg_context_synchronize(self.handle))
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(self.lib.mbg_context_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    def last_timing(self):
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        check(self.lib.mbg_context_last_timing(self.handle, C.byref(a), C.byref(b), C.byref(n)))
+        return {"ms_contract": a.value, "ms_other": b.value, "n_contract_launches": n.value}
+
+    def last_launches(self, max_records=4096):
+        """Per-launch records of the contraction kernel in the last call (list of dicts)."""
+        n = C.c_int32(0)
+        na = np.zeros(max_records, dtype=np.int32)
+        nf = np.zeros(max_records, dtype=np.int64)
+        nt = np.zeros(max_records, dtype=np.int32)
+        npm = np.zeros(max_records, dtype=np.int32)
+        ms = np.zeros(max_records)
+        check(self.lib.mbg_context_last_launches(self.handle, max_records, C.byref(n), ptr(na, _ip), ptr(nf, _lp),
+                                                 ptr(nt, _ip), ptr(npm, _ip), ptr(ms, _dp)))
+        k = min(n.value, max_records)
+        return [dict(n_frag_atoms=int(na[i]), n_fragments=int(nf[i]), n_train_padded=int(nt[i]), n_perms=int(npm[i]),
+                     ms=float(ms[i])) for i in range(k)]
+
+    def measure_fp64_peak(self):
+        t, f = C.c_double(0), C.c_double(0)
+        check(self.lib.mbg_measure_fp64_peak(self.handle, C.byref(t), C.byref(f)))
+        return t.value, f.value
+
+    # -- models ---------------------------------------------------------------------
+    def model_handle(self, key, build_desc):
+        """Device model cached by ``key``; ``build_desc()`` returns (ModelDesc, keepalive)."""
+        h = self._models.get(key)
+        if h is None:
+            desc, _keep = build_desc()
+            h = C.c_void_p()
+            check(self.lib.mbg_model_create(self.handle, C.byref(desc), C.byref(h)))
+            self._models[key] = h
+        return h
+
+    def drop_model(self, key):
+        h = self._models.pop(key, None)
+        if h is not None:
+            self.lib.mbg_model_destroy(h)
+
+    # -- small operators ------------------------------------------------------------
+    def enumerate(self, sets):
+        order = len(sets)
+        offs = np.zeros(order + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(s) for s in sets])
+        vals = as_i32(np.concatenate([np.asarray(s, dtype=np.int64).ravel() for s in sets])
+                      if offs[-1] else np.zeros(0))
+        n = C.c_int64(0)
+        check(self.lib.mbg_enumerate(self.handle, order, ptr(offs, _ip), ptr(vals, _ip), _ip(), C.byref(n)))
+        combs = np.zeros((n.value, order), dtype=np.int32)
+        if n.value:
+            check(self.lib.mbg_enumerate(self.handle, order, ptr(offs, _ip), ptr(vals, _ip), ptr(combs, _ip),
+                                         C.byref(n)))
+        return combs
+
+    def criteria_eval(self, kind, masses, entity_ids, R):
+        R = as_f64(R)
+        n_R, n_atoms = R.shape[0], R.shape[1]
+        out = np.zeros(n_R)
+        m = as_f64(masses) if masses is not None else None
+        e = as_i32(entity_ids) if entity_ids is not None else None
+        check(self.lib.mbg_criteria_eval(self.handle, kind, n_atoms, ptr(m, _dp), ptr(e, _ip), ptr(R, _dp), n_R,
+                                         ptr(out, _dp)))
+        return out
+
+    def r_mic(self, cell, cutoff, r):
+        r = as_f64(r)
+        cell = as_f64(cell).reshape(9)
+        out = np.zeros_like(r)
+        acc = C.c_int32(0)
+        check(self.lib.mbg_r_mic(self.handle, ptr(cell, _dp), float(cutoff), ptr(r, _dp), r.shape[0], ptr(out, _dp),
+                                 C.byref(acc)))
+        return out, bool(acc.value)
+
+
+_contexts = {}
+
+
+def get_context(device=None):
+    """Process-wide context of a device (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        try:
+            import torch
+
+            if torch.cuda.is_available() and torch.cuda.is_initialized():
+                device = torch.cuda.current_device()
+        except Exception:  # pragma: no cover
+            pass
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx

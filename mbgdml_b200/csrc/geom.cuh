@@ -1,0 +1,211 @@
+// Per-fragment geometry on device: gather, minimum image, pair cut-off, acceptance
+// criteria, inverse-distance descriptor.  Every discrete decision (cut-offs) is
+// evaluated with explicitly rounded, un-fused FP64 operations in the reference's
+// operation order so that accept masks reproduce the NumPy path bit for bit.
+//
+// Reference: mbgdml/periodic.py:61-107 (Cell.r_mic/d_mic -> ase.geometry.find_mic),
+//            mbgdml/descriptors.py:65-201 (Criteria.accept, com_distance_sum,
+//            max_atom_pair_dist), mbgdml/_gdml/desc.py:79-233 (_from_r),
+//            mbgdml/predictors/gdml_predict.py:214-235 (slice -> MIC -> criteria).
+#pragma once
+#include "common.cuh"
+
+namespace mbg {
+
+__device__ __forceinline__ double norm3_rn(double x, double y, double z) {
+  // sqrt((x*x + y*y) + z*z) with each operation rounded (scipy pdist / np.linalg.norm over 3 components)
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+
+// out = v @ M (M row-major 3x3), sequential un-fused accumulation.
+__device__ __forceinline__ void vec_mat_rn(const double v[3], const double* M, double out[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    out[i] = __dadd_rn(__dadd_rn(__dmul_rn(v[0], M[i]), __dmul_rn(v[1], M[3 + i])), __dmul_rn(v[2], M[6 + i]));
+}
+
+// ase.geometry.naive_find_mic: f = v cell^-1 ; f -= floor(f + 0.5) ; v' = f cell.  Returns |v'|.
+__device__ __forceinline__ double mic_naive(const SysDev& s, const double v[3], double out[3]) {
+  double f[3];
+  vec_mat_rn(v, s.cell_inv, f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) f[i] = __dsub_rn(f[i], floor(__dadd_rn(f[i], 0.5)));
+  vec_mat_rn(f, s.cell, out);
+  return norm3_rn(out[0], out[1], out[2]);
+}
+
+// ase.geometry.general_find_mic on the Minkowski-reduced cell: wrap into [0,1)^3, then the
+// shortest of (0,0,0) followed by itertools.product([-1,0,1], repeat=3); first minimum wins.
+__device__ __noinline__ void mic_general(const SysDev& s, const double v[3], double out[3]) {
+  double f[3], pos[3];
+  vec_mat_rn(v, s.rcell_inv, f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) f[i] = __dsub_rn(f[i], floor(f[i]));
+  vec_mat_rn(f, s.rcell, pos);
+  double best = norm3_rn(pos[0], pos[1], pos[2]);
+  out[0] = pos[0], out[1] = pos[1], out[2] = pos[2];
+  for (int h = -1; h <= 1; ++h)
+    for (int k = -1; k <= 1; ++k)
+      for (int l = -1; l <= 1; ++l) {
+        const double hkl[3] = {(double)h, (double)k, (double)l};
+        double sh[3], x[3];
+        vec_mat_rn(hkl, s.rcell, sh);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[i] = __dadd_rn(pos[i], sh[i]);
+        const double len = norm3_rn(x[0], x[1], x[2]);
+        if (len < best) {
+          best = len;
+          out[0] = x[0], out[1] = x[1], out[2] = x[2];
+        }
+      }
+}
+
+// Decode candidate -> entity tuple.  Returns false when the tuple is not strictly ascending
+// (utils.gen_combs drops it, utils.py:479-488).  Explicit tuples are taken as given.
+__device__ __forceinline__ bool decode_tuple(const JobDev& j, long long cand, int ent[kMaxOrder]) {
+  if (j.explicit_combs) {
+    for (int s = 0; s < j.order; ++s) ent[s] = j.combs[cand * j.order + s];
+    return true;
+  }
+  long long idx = cand;
+  for (int s = j.order - 1; s >= 0; --s) {
+    const int n_s = j.set_off[s + 1] - j.set_off[s];
+    const int dig = (int)(idx % n_s);
+    idx /= n_s;
+    ent[s] = j.set_ent[j.set_off[s] + dig];
+  }
+  bool asc = true;
+  for (int s = 0; s + 1 < j.order; ++s) asc = asc && (ent[s] < ent[s + 1]);
+  return asc;
+}
+
+// gdml_predict.py:214-216: atoms of the fragment, entity by entity, ascending within an entity.
+__device__ __forceinline__ int gather_atoms(const SysDev& s, const JobDev& j, const int ent[kMaxOrder],
+                                            int atoms[kMaxFragAtoms]) {
+  int a = 0;
+  for (int k = 0; k < j.order; ++k) {
+    const int lo = s.ent_off[ent[k]], hi = s.ent_off[ent[k] + 1];
+    for (int i = lo; i < hi && a < kMaxFragAtoms; ++i) atoms[a++] = s.ent_atoms[i];
+  }
+  return a;
+}
+
+// mbeAlchemyScale.scale with linear_switching for every scaler whose entity is in the tuple
+// (gdml_predict.py:256-260): the product of the factors.
+__device__ __forceinline__ double alchemy_lambda(const JobDev& j, const int ent[kMaxOrder]) {
+  double lam = 1.0;
+  for (int a = 0; a < j.n_alch; ++a) {
+    bool hit = false;
+    for (int s = 0; s < j.order; ++s) hit = hit || (ent[s] == j.alch_ent[a]);
+    if (hit) lam *= j.alch_fac[a];
+  }
+  return lam;
+}
+
+// Load the fragment's coordinates; under periodicity re-express them relative to the first atom
+// in the minimum image and apply the pair cut-off (periodic.py:61-107).  Returns false if rejected.
+template <int NA>
+__device__ __forceinline__ bool fragment_coords(const SysDev& s, const double* __restrict__ Rf,
+                                                const int* atoms, double (*r)[3]) {
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const double* p = Rf + 3 * (long long)atoms[a];
+    r[a][0] = p[0], r[a][1] = p[1], r[a][2] = p[2];
+  }
+  if (!s.periodic) return true;
+  const double r0[3] = {r[0][0], r[0][1], r[0][2]};
+  bool naive_ok = true;
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const double d[3] = {__dsub_rn(r[a][0], r0[0]), __dsub_rn(r[a][1], r0[1]), __dsub_rn(r[a][2], r0[2])};
+    double v[3];
+    const double len = mic_naive(s, d, v);
+    naive_ok = naive_ok && (len < s.half_min_len);
+    r[a][0] = v[0], r[a][1] = v[1], r[a][2] = v[2];
+  }
+  if (!naive_ok) {
+    // find_mic falls back to the general algorithm for the whole set of vectors.
+    if (s.fast_reject) return false;  // some |d_0k| >= L_min/2 >= cutoff: pdist test below must fail
+    for (int a = 0; a < NA; ++a) {
+      const double* p = Rf + 3 * (long long)atoms[a];
+      const double d[3] = {__dsub_rn(p[0], r0[0]), __dsub_rn(p[1], r0[1]), __dsub_rn(p[2], r0[2])};
+      double v[3];
+      mic_general(s, d, v);
+      r[a][0] = v[0], r[a][1] = v[1], r[a][2] = v[2];
+    }
+  }
+  // periodic.py:80-83: reject if any pair distance >= cutoff
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NA; ++i)
+#pragma unroll
+    for (int k = i + 1; k < NA; ++k) {
+      const double dist = norm3_rn(__dsub_rn(r[i][0], r[k][0]), __dsub_rn(r[i][1], r[k][1]),
+                                   __dsub_rn(r[i][2], r[k][2]));
+      ok = ok && !(dist >= s.cutoff);
+    }
+  return ok;
+}
+
+// Criteria.accept (descriptors.py:65-103) with com_distance_sum / max_atom_pair_dist.
+template <int NA>
+__device__ __forceinline__ double criteria_value(const SysDev& s, const CritDev& c, const int* atoms,
+                                                 const double (*r)[3]) {
+  if (c.kind == MBG_CRIT_MAX_ATOM_PAIR_DIST) {
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+#pragma unroll
+      for (int k = i + 1; k < NA; ++k) {
+        const double dist = norm3_rn(__dsub_rn(r[i][0], r[k][0]), __dsub_rn(r[i][1], r[k][1]),
+                                     __dsub_rn(r[i][2], r[k][2]));
+        mx = dist > mx ? dist : mx;
+      }
+    return mx;
+  }
+  // com_distance_sum: sum over entity groups of |CM_total - CM_group| (descriptors.py:159-201),
+  // centres of mass as np.average(R, weights=masses) = sum(R*m)/sum(m) in atom order (106-128).
+  double m[NA];
+  double num[3] = {0.0, 0.0, 0.0}, den = 0.0;
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    m[a] = s.masses[atoms[a]];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) num[k] = __dadd_rn(num[k], __dmul_rn(r[a][k], m[a]));
+    den = __dadd_rn(den, m[a]);
+  }
+  const double cm[3] = {__ddiv_rn(num[0], den), __ddiv_rn(num[1], den), __ddiv_rn(num[2], den)};
+  double dsum = 0.0;
+  for (int g = 0; g < c.n_groups; ++g) {
+    double gn[3] = {0.0, 0.0, 0.0}, gd = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+      if (c.group[a] == g) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gn[k] = __dadd_rn(gn[k], __dmul_rn(r[a][k], m[a]));
+        gd = __dadd_rn(gd, m[a]);
+      }
+    const double dx = __dsub_rn(cm[0], __ddiv_rn(gn[0], gd));
+    const double dy = __dsub_rn(cm[1], __ddiv_rn(gn[1], gd));
+    const double dz = __dsub_rn(cm[2], __ddiv_rn(gn[2], gd));
+    dsum = __dadd_rn(dsum, norm3_rn(dx, dy, dz));
+  }
+  return dsum;
+}
+
+__device__ __forceinline__ bool criteria_accept(const CritDev& c, double v) {
+  if (c.bound == MBG_BOUND_RANGE) return (c.lo < v) && (v < c.hi);
+  if (c.bound == MBG_BOUND_UPPER) return v < c.hi;
+  return v > c.lo;
+}
+
+// Full accept decision for one fragment; r receives the coordinates the descriptor is built from.
+template <int NA>
+__device__ __forceinline__ bool fragment_accept(const SysDev& s, const CritDev& c, const double* __restrict__ Rf,
+                                                const int* atoms, double (*r)[3]) {
+  if (!fragment_coords<NA>(s, Rf, atoms, r)) return false;
+  if (c.kind == MBG_CRIT_NONE) return true;
+  return criteria_accept(c, criteria_value<NA>(s, c, atoms, r));
+}
+
+}  // namespace mbg

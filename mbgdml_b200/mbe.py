@@ -1,0 +1,229 @@
+"""Many-body expansion driver (reference mbgdml/mbe.py:511-1181).
+
+``mbePredict(models, predict_model, ...)`` keeps the reference's constructor, public
+attributes and methods.  When ``predict_model`` is this package's ``predict_gdml`` the
+whole ``R`` batch x all models goes to the GPU in ONE native call (fragment
+enumeration, culling, contraction and scatter all on device); any other callable is
+driven per frame x model exactly as the reference does (mbe.py:1048-1058).
+
+Multi-GPU: one process per GPU.  With ``torch.distributed`` initialised (NCCL), every
+rank evaluates its block-cyclic share of the fragments and the per-atom forces,
+energies and virials are summed with a single all-reduce.
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from . import _engine, _native
+from .predictors import predict_gdml, predict_gdml_decomp
+from .stress import to_voigt, virial_finite_diff
+from .utils import gen_combs
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except Exception:  # pragma: no cover
+        pass
+    return None
+
+
+class mbePredict:  # pylint: disable=invalid-name
+    """Predict energies and forces of structures with many-body GDML models on B200 GPUs."""
+
+    def __init__(
+        self,
+        models,
+        predict_model,
+        use_ray=False,
+        n_workers=1,
+        ray_address="auto",
+        wkr_chunk_size=None,
+        alchemy_scalers=None,
+        periodic_cell=None,
+        compute_stress=False,
+    ):
+        if use_ray:
+            raise NotImplementedError(
+                "use_ray=True: the ray CPU fan-out (mbe.py:814-868) is replaced by GPU kernels; "
+                "launch one process per GPU (torchrun) for multi-GPU runs"
+            )
+        self.models = models
+        self.predict_model = predict_model
+        self.use_ray = False
+        self.n_workers = n_workers
+        self.ray_address = ray_address
+        self.wkr_chunk_size = wkr_chunk_size
+        self.alchemy_scalers = [] if alchemy_scalers is None else alchemy_scalers
+        self.periodic_cell = periodic_cell
+        self.compute_stress = compute_stress
+        self.virial_form = "group"
+        self.finite_diff_dh = 1e-4
+        self.use_voigt = False
+        self.only_normal_stress = False
+        self.box_scaling_type = "anisotropic"
+        self.last_stats = None
+
+    @property
+    def periodic_cell(self):
+        return getattr(self, "_periodic_cell", None)
+
+    @periodic_cell.setter
+    def periodic_cell(self, var):
+        self._periodic_cell = var
+
+    def get_avail_entities(self, comp_ids_r, comp_ids_model):
+        """mbe.py:713-736: entity ids of the structure that carry each model component id."""
+        comp_ids_r = np.asarray(comp_ids_r)
+        return [np.where(comp_id == comp_ids_r)[0] for comp_id in comp_ids_model]
+
+    def _scalers_for(self, model):
+        order = len(model.comp_ids)
+        return [s for s in (self.alchemy_scalers or []) if s.order == order]  # mbe.py:789-796
+
+    # ------------------------------------------------------------------------------
+    def compute_nbody(self, Z, R, entity_ids, comp_ids, model):
+        """All n-body contributions of one structure with one model (mbe.py:739-875)."""
+        R = np.asarray(R)
+        if R.ndim == 3:
+            if R.shape[0] == 1:
+                R = R[0]
+            else:
+                raise ValueError("R.ndim is not 2 (only one structure is allowed)")
+        avail_entity_ids = self.get_avail_entities(comp_ids, model.comp_ids)
+        nbody_gen = gen_combs(avail_entity_ids)
+        kwargs_pred = {"alchemy_scalers": self._scalers_for(model)}
+        periodic_cell = self.periodic_cell
+        compute_stress = self.compute_stress and bool(periodic_cell) and self.virial_form == "group"
+        if compute_stress:
+            kwargs_pred["compute_virial"] = True
+        E, F, *virial_model = self.predict_model(Z, R, entity_ids, nbody_gen, model, periodic_cell, **kwargs_pred)
+        if compute_stress:
+            return E, F, virial_model[0]
+        return E, F
+
+    def compute_nbody_decomp(self, Z, R, entity_ids, comp_ids, model):
+        """Per-fragment n-body energies and forces of one structure (mbe.py:878-1007)."""
+        R = np.asarray(R)
+        if R.ndim == 3:
+            if R.shape[0] == 1:
+                R = R[0]
+            else:
+                raise ValueError("R.ndim is not 2 (only one structure is allowed)")
+        avail_entity_ids = self.get_avail_entities(comp_ids, model.comp_ids)
+        entity_combs = gen_combs(avail_entity_ids).to_array()  # enumerated on device, reference order
+        E, F, entity_combs = self.predict_model(Z, R, entity_ids, entity_combs, model)
+        return E, F, entity_combs
+
+    # ------------------------------------------------------------------------------
+    def _predict_batched(self, Z, R, entity_ids, comp_ids, want_virial):
+        """Fast path: every frame and every model in one native call (+ one all-reduce)."""
+        ctx = _native.get_context()
+        sources = [gen_combs(self.get_avail_entities(comp_ids, m.comp_ids)) for m in self.models]
+        scalers = [self._scalers_for(m) for m in self.models]
+        dist = _dist()
+        if dist is None:
+            E, F, V, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
+                                                   self.periodic_cell, compute_virial=want_virial)
+            self.last_stats = stats
+            return E, F, V
+        import torch
+
+        dev = torch.device("cuda", ctx.device)
+        n_frames, n_atoms = R.shape[0], R.shape[1]
+        # one flat buffer [E | F | virial] so that a single all-reduce carries everything
+        n_E, n_F, n_V = n_frames, n_frames * n_atoms * 3, n_frames * 9 if want_virial else 0
+        buf = torch.zeros(n_E + n_F + n_V, dtype=torch.float64, device=dev)
+        E_t, F_t = buf[:n_E], buf[n_E:n_E + n_F]
+        V_t = buf[n_E + n_F:] if want_virial else None
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
+                                               self.periodic_cell, compute_virial=want_virial,
+                                               shard=(dist.get_rank(), dist.get_world_size()),
+                                               device_out=(E_t, F_t, V_t))
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        host = buf.cpu().numpy()
+        self.last_stats = stats
+        E = host[:n_E].copy()
+        F = host[n_E:n_E + n_F].reshape(n_frames, n_atoms, 3).copy()
+        V = host[n_E + n_F:].reshape(n_frames, 3, 3).copy() if want_virial else None
+        return E, F, V
+
+    def predict(self, Z, R, entity_ids, comp_ids):
+        """Energies and forces (and stress) of one or several structures (mbe.py:1009-1104)."""
+        R = np.asarray(R, dtype=np.float64)
+        if R.ndim == 2:
+            R = np.array([R])
+        n_R = R.shape[0]
+        compute_stress = self.compute_stress and bool(self.periodic_cell)
+        if compute_stress:
+            assert self.virial_form in ("group", "finite_diff")
+        group_virial = compute_stress and self.virial_form == "group"
+
+        if self.predict_model is predict_gdml:
+            E, F, V = self._predict_batched(Z, R, entity_ids, comp_ids, group_virial)
+            stress = V if group_virial else (np.zeros((n_R, 3, 3)) if compute_stress else None)
+        else:
+            E = np.zeros((n_R,), dtype=np.float64)
+            F = np.zeros(R.shape, dtype=np.float64)
+            stress = np.zeros((n_R, 3, 3), dtype=np.float64) if compute_stress else None
+            for i, r in enumerate(R):
+                for model in self.models:
+                    E_nbody, F_nbody, *virial_nbody = self.compute_nbody(Z, r, entity_ids, comp_ids, model)
+                    E[i] += E_nbody
+                    F[i] += F_nbody
+                    if group_virial:
+                        stress[i] += virial_nbody[0]
+
+        if compute_stress and self.virial_form == "finite_diff":
+            cell_v = self.periodic_cell.cell_v
+            for i, r in enumerate(R):
+                stress[i] = virial_finite_diff(Z, r, entity_ids, comp_ids, cell_v, self,
+                                               only_normal_stress=self.only_normal_stress)
+
+        if compute_stress:
+            stress = stress / self.periodic_cell.volume  # mbe.py:1079
+            if self.only_normal_stress:  # mbe.py:1081-1091
+                for n in range(stress.shape[0]):
+                    for i in range(3):
+                        for j in range(3):
+                            if i != j:
+                                stress[n][i][j] = 0.0
+                    if self.box_scaling_type == "isotropic":
+                        stress_average = np.trace(stress[n]) / 3
+                        for i in range(3):
+                            stress[n][i][i] = stress_average
+            if self.use_voigt:
+                stress = np.array([to_voigt(r_stress) for r_stress in stress])
+            return E, F, stress
+        return E, F
+
+    def predict_decomp(self, Z, R, entity_ids, comp_ids):
+        """Per-fragment predictions grouped by n-body order (mbe.py:1106-1181)."""
+        R = np.asarray(R, dtype=np.float64)
+        if R.ndim == 2:
+            R = np.array([R])
+        E_data, F_data, entity_comb_data = [], [], []
+        model_nbody_orders = [model.nbody_order for model in self.models]
+        nbody_orders = sorted(set(model_nbody_orders))
+        for nbody_order in nbody_orders:
+            E_nbody, F_nbody, entity_comb_nbody = [], [], []
+            for model in (m for m in self.models if m.nbody_order == nbody_order):
+                for i, r in enumerate(R):
+                    E, F, entity_combs = self.compute_nbody_decomp(Z, r, entity_ids, comp_ids, model)
+                    entity_combs = np.hstack((np.full((len(entity_combs), 1), i, dtype=np.int64), entity_combs))
+                    E_nbody.extend(E)
+                    F_nbody.extend(F)
+                    entity_comb_nbody.extend(entity_combs)
+            E_data.append(np.array(E_nbody))
+            F_data.append(np.array(F_nbody))
+            entity_comb_data.append(np.array(entity_comb_nbody))
+        return E_data, F_data, entity_comb_data, nbody_orders
+
+
+__all__ = ["mbePredict", "predict_gdml", "predict_gdml_decomp", "gen_combs", "itertools"]

@@ -1,0 +1,105 @@
+"""CPU: the C-ABI library loads, exports every symbol include/mbgdml_b200.h declares, and the
+host-side mirror fails loudly (no CPU fallback) and validates like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mbgdml_b200 as mb
+from mbgdml_b200 import _engine, _native, build, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "mbgdml_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    declared = header_functions()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mbgdml_b200.h but not exported"
+    assert sorted(_native.EXPORTED_SYMBOLS) == declared
+    assert _native.load_library().mbg_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes implied by the header on LP64
+    assert ctypes.sizeof(_native.ModelDesc) == 16 + 24 + 32 + 8 + 16 + 8
+    assert ctypes.sizeof(_native.SystemDesc) == 8 + 32 + 8
+    assert ctypes.sizeof(_native.Job) == 8 + 24 + 8 + 8 + 16
+    assert ctypes.sizeof(_native.JobStats) == 24
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.NativeUnavailable):
+        _native.get_context()
+    md = synthetic.make_model(["h2o"], n_train=8)
+    Z, R, eids, cids = synthetic.make_cluster(2)
+    pred = mb.mbePredict([mb.gdmlModel(md)], mb.predict_gdml)
+    with pytest.raises(_native.NativeUnavailable):
+        pred.predict(Z, R, eids, cids)
+
+
+def test_system_csr_matches_np_where():
+    Z = np.array([8, 1, 1, 6, 8, 1, 1, 1, 1, 8, 1, 1])
+    eids = np.array([0, 0, 0, 2, 2, 1, 2, 2, 2, 1, 1, 2])  # non-contiguous entities
+    s = _engine.System(Z, eids)
+    for e in range(3):
+        lo, hi = s.entity_offsets[e], s.entity_offsets[e + 1]
+        assert np.array_equal(s.entity_atoms[lo:hi], np.where(eids == e)[0])
+    assert s.masses[0] == 15.99491461957 and s.masses[1] == 1.00782503223 and s.masses[3] == 12.0
+
+
+def test_criteria_native_spec_and_unsupported_callables():
+    c = mb.Criteria(mb.com_distance_sum, {"entity_ids": np.array([0, 0, 0, 1, 1, 1])}, 6.0)
+    kind, bound, lo, hi, eids = c.native_spec(6)
+    assert (kind, bound, hi) == (_native.CRIT_COM_DISTANCE_SUM, _native.BOUND_UPPER, 6.0) and eids.dtype == np.int32
+    c = mb.Criteria(mb.max_atom_pair_dist, {}, (7.0, 2.0))
+    assert c.cutoff == [2.0, 7.0]
+    assert c.native_spec(6)[:4] == (_native.CRIT_MAX_ATOM_PAIR_DIST, _native.BOUND_RANGE, 2.0, 7.0)
+    c = mb.Criteria(mb.max_atom_pair_dist, {}, 3.0, bound="LOWER")
+    assert c.native_spec(6)[:3] == (_native.CRIT_MAX_ATOM_PAIR_DIST, _native.BOUND_LOWER, 3.0)
+    assert mb.Criteria(lambda Z, R: R, {}, None).native_spec(3)[0] == _native.CRIT_NONE
+    with pytest.raises(NotImplementedError):
+        mb.Criteria(lambda Z, R: R, {}, 1.0).native_spec(3)
+    acc, val = mb.Criteria(mb.com_distance_sum, {}, None).accept(np.array([8, 1, 1]), np.zeros((3, 3)))
+    assert acc.all() and val is None
+
+
+def test_alchemy_and_reference_error_behaviour():
+    s = mb.mbeAlchemyScale(3, 2, mb.linear_switching, {"factor": 0.25})
+    assert s.native_factor() == 0.25 and s.scale(4.0) == 1.0
+    with pytest.raises(AssertionError):  # switching.py:47
+        mb.linear_switching(1.0, 1.5)
+    with pytest.raises(NotImplementedError):
+        mb.mbeAlchemyScale(3, 2, lambda d, k: d * k, {"k": 0.5}).native_factor()
+    with pytest.raises(TypeError):  # gdml_model.py:67
+        mb.gdmlModel(3.0)
+    with pytest.raises(KeyError):  # gdml_model.py:76
+        mb.gdmlModel({"r_unit": np.array("Angstrom")})
+    with pytest.raises(NotImplementedError):
+        mb.mbePredict([], mb.predict_gdml, use_ray=True)
+    cell = mb.Cell(np.eye(3) * 10.0, cutoff=3.0)
+    assert cell.cutoff == 3.0 and cell.volume == 1000.0
+    cell.cell_v = np.eye(3) * 8.0  # the setter silently resets the cutoff (periodic.py:121-126)
+    assert cell.cutoff == 4.0
+
+
+def test_model_container_attributes():
+    md = synthetic.make_model(["h2o", "h2o"], n_train=12, sig=55.0, c=1.5, std=2.0)
+    m = mb.gdmlModel(md, criteria=mb.Criteria(mb.com_distance_sum, {"entity_ids": md["entity_ids"]}, 6.0))
+    assert m.type == "gdml" and m.nbody_order == 2 and m.n_atoms == 6 and m.n_train == 12 and m.n_perms == 8
+    assert m.sig == 55.0 and m.integ_c == 1.5 and m.stdev == 2.0 and list(m.comp_ids) == ["h2o", "h2o"]
+    assert mb.gdmlModel(md, comp_ids=["a", "b"]).comp_ids == ["a", "b"]

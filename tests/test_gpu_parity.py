@@ -1,0 +1,302 @@
+"""GPU parity: the CUDA path (through the C ABI / reference-shaped Python surface) against the
+reference outputs committed in tests/golden/ and against the NumPy oracle on the same seeded inputs.
+
+Tolerance (north_star): energies/forces within 1e-9 relative on random-init models, measured as
+max|delta| / max|reference|; fragment index sets and accept masks bit-exact.  The reference's trained
+models are ill-conditioned, so for them the reference's own tolerance applies.
+"""
+import numpy as np
+import pytest
+
+import mbgdml_b200 as mb
+from helpers import b200_models, cutoffs_from, load, oracle_models, relerr, unpack_models
+from mbgdml_b200 import _native, synthetic
+from oracle import mbgdml_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9  # north_star bar; observed errors are ~1e-13
+
+
+def alch(rows):
+    return [mb.mbeAlchemyScale(int(e), int(o), mb.linear_switching, {"factor": float(f)}) for e, o, f in rows]
+
+
+# ------------------------------------------------------------------------------------------
+def test_enumerate_bit_exact(gpu_ctx):
+    g = load("gen_combs.npz")
+    for k in range(int(g["n"])):
+        order = int(g[f"s{k}_order"])
+        sets = [g[f"s{k}_set{j}"] for j in range(order)]
+        got = gpu_ctx.enumerate(sets)
+        assert got.shape == g[f"s{k}_combs"].shape
+        assert np.array_equal(got, g[f"s{k}_combs"])
+    # python-facing generator yields the same tuples lazily
+    assert list(mb.gen_combs([[0, 2], [1, 3]])) == [(0, 1), (0, 3), (2, 3)]
+    assert list(mb.gen_combs([[2, 3], [0, 1]])) == []
+
+
+def test_enumerate_large_matches_oracle(gpu_ctx):
+    sets = [np.arange(140)] * 3  # BASELINE config 4: C(140,3) = 447,580 trimers out of 2,744,000 tuples
+    got = gpu_ctx.enumerate(sets)
+    assert got.shape == (447580, 3)
+    assert np.array_equal(got, orc.gen_combs_array(sets))
+    sets = [np.arange(0, 100), np.arange(50, 100), np.arange(100, 140)]  # heterogeneous, overlapping
+    assert np.array_equal(gpu_ctx.enumerate(sets), orc.gen_combs_array(sets))
+
+
+@pytest.mark.parametrize("tag", ["1b", "2b", "3b"])
+def test_single_fragment_kernel(tag):
+    """_predict_gdml_wkr on single fragments (reference outputs), through predict_gdml."""
+    g = load("fragment_kernel.npz")
+    md = unpack_models(g, f"{tag}_m")[0]
+    model = mb.gdmlModel(dict(md))
+    n = len(md["z"])
+    eids = np.asarray(md["entity_ids"])
+    for r, out_ref in zip(g[f"{tag}_r"], g[f"{tag}_out"]):
+        E, F = mb.predict_gdml(md["z"], r, eids, [tuple(range(model.nbody_order))], model)
+        e_ref = out_ref[0] * md["std"] + md["c"]
+        f_ref = out_ref[1:].reshape(n, 3) * md["std"]
+        assert abs(E - e_ref) <= TOL * max(abs(e_ref), 1.0)
+        assert relerr(F, f_ref) <= TOL
+
+
+def test_cluster_variants():
+    g = load("cluster_6h2o.npz")
+    mds = unpack_models(g)
+    Z, R, eids, cids = g["Z"], g["R"], g["entity_ids"], g["comp_ids"]
+    E, F = mb.mbePredict(b200_models(mds, [None] * 3), mb.predict_gdml).predict(Z, R, eids, cids)
+    assert relerr(E, g["plain_E"]) <= TOL and relerr(F, g["plain_F"]) <= TOL
+    cuts = cutoffs_from(g["crit_cutoffs"])
+    pred = mb.mbePredict(b200_models(mds, cuts), mb.predict_gdml)
+    E, F = pred.predict(Z, R, eids, cids)
+    assert relerr(E, g["crit_E"]) <= TOL and relerr(F, g["crit_F"]) <= TOL
+    # accept masks: accepted counts equal the number of non-NaN rows of the reference's decomposition
+    for k in range(3):
+        assert pred.last_stats[k][2] == np.count_nonzero(~np.isnan(g[f"decomp_E{k}"]))
+        assert pred.last_stats[k][1] == len(g[f"decomp_E{k}"])
+    E, F = mb.mbePredict(b200_models(mds, cuts), mb.predict_gdml, alchemy_scalers=alch(g["alch"])).predict(
+        Z, R, eids, cids)
+    assert relerr(E, g["alch_E"]) <= TOL and relerr(F, g["alch_F"]) <= TOL
+    E, F = mb.mbePredict(
+        b200_models(mds, [None, (3.0, 6.0), 5.5], desc="pair", bounds=["upper", "upper", "lower"]),
+        mb.predict_gdml).predict(Z, R, eids, cids)
+    assert relerr(E, g["pair_E"]) <= TOL and relerr(F, g["pair_F"]) <= TOL
+    mdsE = [dict(m) for m in mds]
+    mdsE[1]["alphas_E"] = g["useE_alphas_E"]
+    E, F = mb.mbePredict(b200_models(mdsE, cuts), mb.predict_gdml).predict(Z, R, eids, cids)
+    assert relerr(E, g["useE_E"]) <= TOL and relerr(F, g["useE_F"]) <= TOL
+
+
+def test_single_frame_2d_input_and_per_model_plugin_path():
+    """R.ndim == 2 is accepted (mbe.py:1035-1036); compute_nbody drives the plugin per model like the
+    reference (mbe.py:809-811) and sums to the batched result."""
+    g = load("cluster_6h2o.npz")
+    mds = unpack_models(g)
+    Z, R, eids, cids = g["Z"], g["R"], g["entity_ids"], g["comp_ids"]
+    models = b200_models(mds, cutoffs_from(g["crit_cutoffs"]))
+    pred = mb.mbePredict(models, mb.predict_gdml)
+    E, F = pred.predict(Z, R[1], eids, cids)
+    assert E.shape == (1,) and F.shape == (1,) + R[1].shape
+    assert relerr(E, g["crit_E"][1:2]) <= TOL and relerr(F, g["crit_F"][1:2]) <= TOL
+    e_sum, f_sum = 0.0, np.zeros(R[1].shape)
+    for m in models:
+        e, f = pred.compute_nbody(Z, R[1], eids, cids, m)
+        e_sum += e
+        f_sum += f
+    assert abs(e_sum - g["crit_E"][1]) <= TOL * abs(g["crit_E"][1]) and relerr(f_sum, g["crit_F"][1]) <= TOL
+    with pytest.raises(ValueError):  # mbe.py:777
+        pred.compute_nbody(Z, R, eids, cids, models[0])
+    # explicit tuple chunk, as the reference's ray branch passes (mbe.py:823-828)
+    e, f = mb.predict_gdml(Z, R[1], eids, ((0, 1), (2, 5), (3, 4)), models[1], None)
+    eo, fo = orc.predict_gdml(Z, R[1], eids, ((0, 1), (2, 5), (3, 4)), oracle_models(mds, cutoffs_from(g["crit_cutoffs"]))[1])
+    assert abs(e - eo) <= TOL * max(abs(eo), 1) and relerr(f, fo) <= TOL
+
+
+def test_cluster_decomp():
+    g = load("cluster_6h2o.npz")
+    mds = unpack_models(g)
+    Z, R, eids, cids = g["Z"], g["R"], g["entity_ids"], g["comp_ids"]
+    pred = mb.mbePredict(b200_models(mds, cutoffs_from(g["crit_cutoffs"])), mb.predict_gdml_decomp)
+    Ed, Fd, Cd, orders = pred.predict_decomp(Z, R, eids, cids)
+    assert orders == [1, 2, 3]
+    for k in range(3):
+        assert np.array_equal(Cd[k], g[f"decomp_C{k}"])  # bit-exact fragment index sequence
+        assert np.array_equal(np.isnan(Ed[k]), np.isnan(g[f"decomp_E{k}"]))  # bit-exact accept mask
+        assert np.array_equal(np.isnan(Fd[k]), np.isnan(g[f"decomp_F{k}"]))
+        assert relerr(np.nan_to_num(Ed[k]), np.nan_to_num(g[f"decomp_E{k}"])) <= TOL
+        assert relerr(np.nan_to_num(Fd[k]), np.nan_to_num(g[f"decomp_F{k}"])) <= TOL
+
+
+def test_periodic_boxes():
+    g = load("periodic_40h2o.npz")
+    mds = unpack_models(g)
+    cuts = cutoffs_from(g["crit_cutoffs"])
+    Z, eids, cids = g["cub_Z"], g["cub_eids"], g["cub_cids"]
+    models = b200_models(mds, cuts)
+    # cubic, default cutoff L/2, alchemy, group virial -> stress
+    pred = mb.mbePredict(models, mb.predict_gdml, alchemy_scalers=alch(g["alch"]),
+                         periodic_cell=mb.Cell(g["cub_cell"], pbc=True), compute_stress=True)
+    E, F, S = pred.predict(Z, g["cub_R"], eids, cids)
+    assert relerr(E, g["cub_E"]) <= TOL and relerr(F, g["cub_F"]) <= TOL and relerr(S, g["cub_stress"]) <= TOL
+    # accept mask: same number of surviving fragments as the reference path for frame 0
+    pred1 = mb.mbePredict(models, mb.predict_gdml, periodic_cell=mb.Cell(g["cub_cell"], pbc=True))
+    pred1.predict(Z, g["cub_R"][0], eids, cids)
+    for k in range(3):
+        assert pred1.last_stats[k][2] == int(g[f"cub_naccept{k}"])
+    # user cutoff, Voigt + isotropic normal stress post-processing (mbe.py:1081-1094)
+    pred = mb.mbePredict(models, mb.predict_gdml, periodic_cell=mb.Cell(g["cub_cell"], cutoff=5.0, pbc=True),
+                         compute_stress=True)
+    pred.use_voigt, pred.only_normal_stress, pred.box_scaling_type = True, True, "isotropic"
+    E, F, S = pred.predict(Z, g["cub_R"], eids, cids)
+    assert S.shape == g["cut5_stress"].shape
+    assert relerr(E, g["cut5_E"]) <= TOL and relerr(F, g["cut5_F"]) <= TOL and relerr(S, g["cut5_stress"]) <= TOL
+    # triclinic cell
+    pred = mb.mbePredict(models, mb.predict_gdml, alchemy_scalers=alch(g["alch"]),
+                         periodic_cell=mb.Cell(g["tri_cell"], pbc=True), compute_stress=True)
+    E, F, S = pred.predict(Z, g["tri_R"], eids, cids)
+    assert relerr(E, g["tri_E"]) <= TOL and relerr(F, g["tri_F"]) <= TOL and relerr(S, g["tri_stress"]) <= TOL
+    # cutoff above half the shortest cell vector: the general (Minkowski) minimum-image branch decides
+    pred = mb.mbePredict(models, mb.predict_gdml,
+                         periodic_cell=mb.Cell(g["tri_cell"], cutoff=float(g["tribig_cutoff"]), pbc=True))
+    E, F = pred.predict(Z, g["tri_R"], eids, cids)
+    assert relerr(E, g["tribig_E"]) <= TOL and relerr(F, g["tribig_F"]) <= TOL
+
+
+def test_r_mic_operator():
+    g = load("periodic_40h2o.npz")
+    rng = np.random.default_rng(0)
+    for cell_v, cutoff in ((g["cub_cell"], None), (g["tri_cell"], None), (g["tri_cell"], float(g["tribig_cutoff"]))):
+        ocell, bcell = orc.Cell(cell_v, cutoff=cutoff), mb.Cell(cell_v, cutoff=cutoff)
+        n_none = 0
+        for _ in range(40):
+            start = rng.integers(0, 38) * 3
+            r = g["cub_R"][0][start:start + 9] if cell_v is g["cub_cell"] else g["tri_R"][0][start:start + 9]
+            want, got = ocell.r_mic(r), bcell.r_mic(r)
+            assert (want is None) == (got is None)
+            if want is None:
+                n_none += 1
+            else:
+                assert np.allclose(got, want, rtol=0, atol=1e-12)
+        assert 0 < n_none < 40
+
+
+def test_mixed_water_methanol_small_fragments():
+    """Heterogeneous comp_ids; models of up to 9 atoms (larger fragments: see test_wide_fragments)."""
+    g = load("mixed_h2o_meoh.npz")
+    mds = [m for m in unpack_models(g) if len(m["z"]) <= 9]
+    assert len(mds) == 5
+    for tag in ("", "2"):
+        Z, R, eids, cids = g["Z" + tag], g["R" + tag], g["entity_ids" + tag], g["comp_ids" + tag]
+        al_rows = g["alch"] if tag == "" else []
+        E, F = mb.mbePredict(b200_models(mds, [None] * 5), mb.predict_gdml, alchemy_scalers=alch(al_rows)).predict(
+            Z, R, eids, cids)
+        Eo, Fo = orc.mbe_predict(oracle_models(mds, [None] * 5), Z, R, eids, cids,
+                                 alchemy_scalers=[orc.AlchemyScale(int(e), int(o), float(f)) for e, o, f in al_rows])
+        assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+
+
+def test_reference_known_answers_on_device():
+    """reference tests/test_descriptors.py:40-49 (bit-exact) and tests/test_predictsets.py:80-142."""
+    g = load("ref_2h2o_criteria.npz")
+    v = mb.com_distance_sum(g["z"], g["R"], g["entity_ids"])
+    assert np.array_equal(v, g["desc_v"])  # 120 dimers, bit for bit
+    crit = mb.Criteria(mb.com_distance_sum, {"entity_ids": g["entity_ids"]}, cutoff=5.3809148637976385)
+    acc, val = crit.accept(g["z"], g["R"][42])
+    assert not acc and val == 5.3809148637976385
+    # NaN index set: each dimer is its own 2-entity structure predicted with the trained 2-body model
+    md = unpack_models(load("ref_models_t500.npz"))[1]
+    model = mb.gdmlModel(dict(md), criteria=mb.Criteria(mb.com_distance_sum, {"entity_ids": g["entity_ids"]}, 6.0))
+    pred = mb.mbePredict([model], mb.predict_gdml_decomp)
+    Ed, _, _, _ = pred.predict_decomp(g["z"], g["R"], g["entity_ids"], np.array(["h2o", "h2o"]))
+    assert np.array_equal(np.where(np.isnan(Ed[0]))[0], g["nan_idx"])
+
+
+def test_reference_16mer_and_6mer_with_trained_models():
+    """reference tests/test_predict.py:40-128: pinned E and forces at the reference's own tolerance
+    (the trained models are ill-conditioned: cond ~1e15)."""
+    mds = unpack_models(load("ref_models_t500.npz"))
+    models = b200_models(mds, [None, 6.0, 10.0])
+    g = load("ref_16mer.npz")
+    E, F = mb.mbePredict(models, mb.predict_gdml).predict(g["Z"], g["R"], g["entity_ids"], g["comp_ids"])
+    assert np.allclose(E, g["E_pinned"])
+    assert np.allclose(E, g["E_live"]) and np.allclose(F, g["F_live"], rtol=1e-4, atol=1e-2)
+    g = load("ref_6h2o.npz")
+    pred = mb.mbePredict(models, mb.predict_gdml)
+    E, F = pred.predict(g["Z"], g["R"], g["entity_ids"], g["comp_ids"])
+    assert np.allclose(E, g["E_live"]) and np.allclose(F, g["F_live"], rtol=1e-4, atol=1e-2)
+    # tests/test_predictsets.py:40-77: decomposed predictions add up to the totals
+    Ed, Fd, Cd, _ = mb.mbePredict(models, mb.predict_gdml_decomp).predict_decomp(
+        g["Z"], g["R"], g["entity_ids"], g["comp_ids"])
+    E_tot, F_tot = np.zeros_like(E), np.zeros_like(F)
+    for k in range(3):
+        for e, f, c in zip(Ed[k], Fd[k], Cd[k]):
+            if not np.isnan(e):
+                E_tot[c[0]] += e
+                F_tot[c[0], orc.r_slice(g["entity_ids"], c[1:])] += f
+    assert np.allclose(E_tot, E) and np.allclose(F_tot, F, rtol=1e-4, atol=1e-2)
+
+
+def test_sharded_partial_sums_add_up(gpu_ctx):
+    """Three shards evaluated one after the other on one GPU sum to the unsharded result, and
+    every fragment is evaluated exactly once."""
+    from mbgdml_b200 import _engine
+
+    g = load("periodic_40h2o.npz")
+    mds = unpack_models(g)
+    models = b200_models(mds, cutoffs_from(g["crit_cutoffs"]))
+    Z, R, eids, cids = g["cub_Z"], g["cub_R"], g["cub_eids"], g["cub_cids"]
+    cell = mb.Cell(g["cub_cell"], pbc=True)
+    pred = mb.mbePredict(models, mb.predict_gdml, periodic_cell=cell)
+    sources = lambda: [mb.gen_combs(pred.get_avail_entities(cids, m.comp_ids)) for m in models]
+    E1, F1, _, st1 = _engine.predict_total(gpu_ctx, Z, R, eids, models, sources(), [[]] * 3, cell)
+    E_sum, F_sum, acc = 0, 0, np.zeros(3, dtype=int)
+    for r in range(3):
+        E, F, _, st = _engine.predict_total(gpu_ctx, Z, R, eids, models, sources(), [[]] * 3, cell, shard=(r, 3))
+        E_sum, F_sum = E_sum + E, F_sum + F
+        acc += np.array([s[2] for s in st])
+    assert np.array_equal(acc, [s[2] for s in st1])
+    assert relerr(E_sum, E1) <= 1e-12 and relerr(F_sum, F1) <= 1e-12
+    assert relerr(E1, g["cub_E"] * 0 + E1) == 0  # sanity: finite
+
+
+def test_full_size_properties_64_h2o_trimers():
+    """BASELINE config 3 at full size (64 H2O, T = 1000, 41,664 trimers): size-independent checks.
+    (a) internal forces sum to zero; (b) invariance under a rigid translation + rotation of the cluster
+    (energies equal, forces co-rotate); (c) relabelling the molecules permutes the forces;
+    (d) a random sample of trimers evaluated by the oracle matches the decomposed rows."""
+    md = synthetic.make_model(["h2o"] * 3, n_train=1000, sig=100.0, seed=2)
+    Z, R, eids, cids = synthetic.make_cluster(64, seed=0)
+    model = mb.gdmlModel(dict(md))
+    pred = mb.mbePredict([model], mb.predict_gdml)
+    E, F = pred.predict(Z, R, eids, cids)
+    assert pred.last_stats[0][1] == 41664 and pred.last_stats[0][2] == 41664
+    scale = np.abs(F).max()
+    assert np.abs(F[0].sum(axis=0)).max() <= 1e-9 * scale * 64  # (a)
+    rot = synthetic.random_rotations(np.random.default_rng(1), 1)[0]
+    E2, F2 = pred.predict(Z, R @ rot.T + np.array([3.0, -2.0, 0.5]), eids, cids)  # (b)
+    assert abs(E2[0] - E[0]) <= 1e-9 * abs(E[0])
+    assert relerr(F2[0], F[0] @ rot.T) <= 1e-9
+    perm = np.random.default_rng(2).permutation(64)  # (c) molecule k of the new listing is old perm[k]
+    atom_perm = (perm[:, None] * 3 + np.arange(3)).ravel()
+    E3, F3 = pred.predict(Z[atom_perm], R[atom_perm], eids, cids)
+    assert abs(E3[0] - E[0]) <= 1e-9 * abs(E[0]) and relerr(F3[0], F[0][atom_perm]) <= 1e-9
+    rng = np.random.default_rng(5)  # (d)
+    combs = np.sort(np.array([rng.choice(64, 3, replace=False) for _ in range(12)]), axis=1)
+    Ed, Fd, _ = mb.predict_gdml_decomp(Z, R, eids, combs, model)
+    Eo, Fo, _ = orc.predict_gdml_decomp(Z, R, eids, combs, orc.Model(dict(md)))
+    assert relerr(Ed, Eo) <= TOL and relerr(Fd, Fo) <= TOL
+
+
+def test_errors_surface_as_reference_exceptions():
+    md = synthetic.make_model(["h2o", "h2o"], n_train=8)
+    Z, R, eids, cids = synthetic.make_cluster(3)
+    model = mb.gdmlModel(dict(md))
+    with pytest.raises(ValueError):  # entity with the wrong number of atoms for this model
+        mb.predict_gdml(Z, R, np.array([0, 0, 0, 0, 1, 2, 2, 2, 2]), [(0, 1)], model)
+    with pytest.raises(AssertionError):  # gdml_predict.py:197
+        mb.predict_gdml(Z, R[None], eids, [(0, 1)], model)
+    with pytest.raises(NotImplementedError):
+        bad = mb.gdmlModel(dict(md), criteria=mb.Criteria(lambda Z, R: np.zeros(1), {}, 1.0))
+        mb.predict_gdml(Z, R, eids, [(0, 1)], bad)
+    E, F = mb.predict_gdml(Z, R, eids, [], model)  # empty fragment list -> zeros (gdml_predict.py:198-199)
+    assert E == 0.0 and not F.any()
