@@ -242,7 +242,11 @@ def run_gpu_arm(args):
     n_frames = args.frames * world  # weak scaling: fixed frames per GPU
     w = make_workload(args.workload, n_frames, args.n_train)
     ctx = _native.get_context(local)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) torch stream: the library launches on it, the CUDA events that time the
+    # steps are recorded on it, and NCCL orders the all-reduce after it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     models = [mb.gdmlModel(dict(d), criteria=mb.Criteria(mb.com_distance_sum, {"entity_ids": d["entity_ids"]}, c))

@@ -141,11 +141,14 @@ class mbePredict:  # pylint: disable=invalid-name
         buf = torch.zeros(n_E + n_F + n_V, dtype=torch.float64, device=dev)
         E_t, F_t = buf[:n_E], buf[n_E:n_E + n_F]
         V_t = buf[n_E + n_F:] if want_virial else None
-        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        cur = torch.cuda.current_stream(dev).cuda_stream
+        if cur != 0:  # a NULL handle would select the context's own stream, which torch does not order against
+            ctx.set_stream(cur)
         _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
                                                self.periodic_cell, compute_virial=want_virial,
                                                shard=(dist.get_rank(), dist.get_world_size()),
                                                device_out=(E_t, F_t, V_t))
+        ctx.synchronize()  # the library's stream is idle before NCCL reads the partial sums
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         host = buf.cpu().numpy()
         self.last_stats = stats
