@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -77,6 +78,7 @@ struct mbg_context_s {
   DevBuf sys_ints, sys_masses, R, outE, outF, outV;
   DevBuf job_ints, flags, blk_acc, blk_enum, blk_off, totals;
   DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
+  DevBuf exp2_table;  // 2^(j/64), j = 0..63
   long long* h_totals = nullptr;  // pinned [2]
   // timing of the last call
   std::vector<cudaEvent_t> ev_pool;
@@ -152,7 +154,8 @@ static int launch_matern_t(mbg_context_t ctx, const MaternArgs& a) {
   if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
   CUDA_TRY(cudaFuncSetAttribute(k_matern<NA, USE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nq = a.n_frag * a.P;
-  const long long grid = (nq + nt - 1) / nt;
+  const int qc = matern_queries_per_cta<NA>(nt);
+  const long long grid = (nq + qc - 1) / qc;
   if (grid > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "too many fragments in one launch");
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
@@ -441,6 +444,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     a.sys = s;
     a.R = dR;
     a.XA = m->XA, a.alphaE = m->alphaE, a.iperm = m->iperm;
+    a.exp2_table = ctx->exp2_table.as<double>();
     a.T_pad = m->T_pad, a.P = m->P;
     a.sig = m->sig, a.c = m->c, a.std = m->std;
     a.n_frag = rec_pending;
@@ -577,6 +581,12 @@ int mbg_context_create(int device, mbg_context_t* out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   CUDA_TRY(cudaMallocHost(&ctx->h_totals, 2 * sizeof(long long)));
+  {
+    double tab[1 << kExpTableBits];
+    for (int j = 0; j < (1 << kExpTableBits); ++j) tab[j] = (double)exp2l((long double)j / (1 << kExpTableBits));
+    TRY(ctx->exp2_table.ensure(sizeof(tab)));
+    CUDA_TRY(cudaMemcpy(ctx->exp2_table.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaEventCreate(&ctx->ev_call0));
   CUDA_TRY(cudaEventCreate(&ctx->ev_call1));
   *out = ctx;
@@ -589,7 +599,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints,
                     &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
-                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot})
+                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_call0);
@@ -672,10 +682,11 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
     }
   }
   const int T_pad = (T + kTileRows - 1) / kTileRows * kTileRows;
-  std::vector<double2> xa((size_t)T_pad * D, make_double2(0.0, 0.0));
+  const int Dp = model_row_pad(d->n_atoms);  // rows padded to the kernel's lane blocking
+  std::vector<double2> xa((size_t)T_pad * Dp, make_double2(0.0, 0.0));
   for (int t = 0; t < T; ++t)
     for (int e = 0; e < D; ++e)
-      xa[(size_t)t * D + e] = make_double2(d->R_desc[(size_t)e * T + t], d->R_d_desc_alpha[(size_t)t * D + e]);
+      xa[(size_t)t * Dp + e] = make_double2(d->R_desc[(size_t)e * T + t], d->R_d_desc_alpha[(size_t)t * D + e]);
   mbg_model_t m = new mbg_model_s();
   m->ctx = ctx;
   m->n_atoms = d->n_atoms, m->order = d->order, m->D = D, m->T = T, m->T_pad = T_pad, m->P = P;

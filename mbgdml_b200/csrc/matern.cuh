@@ -28,8 +28,9 @@ namespace mbg {
 struct MaternArgs {
   SysDev sys;
   const double* R;       // [n_frames][n_atoms][3]
-  const double2* XA;     // [T_pad][D]: (X_t[e], A_t[e]); rows >= T are (0, 0)
+  const double2* XA;     // [T_pad][Dp]: (X_t[e], A_t[e]); rows >= T and entries e >= D are (0, 0)
   const double* alphaE;  // [T_pad] (zeros past T) or nullptr
+  const double* exp2_table;  // [64] 2^(j/64) correctly rounded (host-computed)
   const int* iperm;      // [P][D]: pi_p^-1
   int T_pad, P;
   double sig, c, std;
@@ -65,6 +66,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier.
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -81,45 +85,169 @@ __device__ __forceinline__ double2 lds_row(uint32_t addr) {
   return v;
 }
 
-constexpr int kMaternThreads = 256;  // max queries per CTA
+// Arithmetic wrapped in `asm volatile`: the compiler keeps volatile asm statements in program order, so
+// the stages of the scalar chain stay interleaved with the (volatile) shared-memory loads of the other
+// two streams exactly as written, instead of being re-serialised into one latency-bound run.
+__device__ __forceinline__ double vfma(double a, double b, double c) {
+  double r;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+  return r;
+}
+__device__ __forceinline__ double vmul(double a, double b) {
+  double r;
+  asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+__device__ __forceinline__ double vadd(double a, double b) {
+  double r;
+  asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+__device__ __forceinline__ double vmax(double a, double b) {
+  double r;
+  asm volatile("max.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+
+constexpr int kExpTableBits = 6;      // 2^(j/64), j = 0..63, staged in shared memory
+constexpr int kMaternThreads = 256;  // threads per CTA
 constexpr int kTileRows = 64;        // training rows per TMA tile
+
+// Register blocking of the contraction.  A "team" of L adjacent lanes owns Q queries; each lane keeps the
+// slice [h*DL, (h+1)*DL) of the descriptor dimensions of all Q queries (y and G: 2*Q*DL doubles), so one
+// 16-byte shared-memory load of (X_t[e], A_t[e]) feeds Q queries.  Partial |diff|^2 and diff.A are
+// exchanged inside the team with warp shuffles; lane h evaluates the exp/sqrt chain of query h, so no
+// transcendental is computed twice.  L = 1: no exchange.  L = 2 requires Q = 2.
+template <int NA>
+struct Blocking {
+  static constexpr int D = NA * (NA - 1) / 2;
+  static constexpr int L = (D > 21) ? 2 : 1;
+  static constexpr int Q = (D <= 6) ? 4 : 2;
+  static constexpr int DL = (D + L - 1) / L;  // dimensions per lane
+  static constexpr int Dp = DL * L;           // padded row length of the device model (pad entries are 0)
+  static constexpr int MinCtas = (D <= 6) ? 2 : 1;  // resident CTAs per SM the registers allow
+  static_assert(L == 1 || (L == 2 && Q == 2), "unsupported team shape");
+};
+
+inline int model_row_pad(int na) {  // Dp for a fragment size (host side, model upload)
+  const int D = na * (na - 1) / 2;
+  const int L = (D > 21) ? 2 : 1;
+  return (D + L - 1) / L * L;
+}
+
+// Queries per CTA for a launch with `nt` threads.
+template <int NA>
+__host__ __device__ constexpr int matern_queries_per_cta(int nt) {
+  return nt / Blocking<NA>::L * Blocking<NA>::Q;
+}
 
 // Bytes of dynamic shared memory for a launch with `nt` threads and P permutations.
 template <int NA>
 __host__ __device__ constexpr size_t matern_smem_bytes(int nt, int P) {
-  constexpr int D = NA * (NA - 1) / 2;
-  const int maxf = (nt + P - 1) / P + 1;
-  return (size_t)2 * kTileRows * D * 16 + 2 * kTileRows * 8 + (size_t)nt * D * 8 + (size_t)nt * 8 +
-         (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + 64;
+  constexpr int D = Blocking<NA>::D, Dp = Blocking<NA>::Dp;
+  const int qc = matern_queries_per_cta<NA>(nt);
+  const int maxf = (qc + P - 1) / P + 1;
+  return (size_t)2 * kTileRows * Dp * 16 + 2 * kTileRows * 8 + (size_t)qc * D * 8 + (size_t)qc * 8 +
+         (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + (8 << kExpTableBits) + 64;  // incl. 4 mbarriers
+}
+
+// ---- branch-free FP64 math for the per-pair scalar chain --------------------------------------------
+// libdevice's exp()/sqrt() carry slow-path branches that split the loop body into basic blocks and stop
+// the scheduler from overlapping the (latency-bound) scalar chain of row t with the (throughput-bound)
+// dot products of row t+1.  These versions are straight-line code, ~1 ulp.
+
+
+// sqrt(x) for x >= 0 (x is clamped to 1e-300, so sqrt(0) returns 1e-150): rsqrt seed (MUFU.RSQ64H,
+// ~2^-22) + one Goldschmidt iteration (~2^-43) + one residual correction (~1 ulp).
+__device__ __forceinline__ double fast_sqrt(double x) {
+  x = fmax(x, 1e-300);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, hh = 0.5 * y;
+  const double r = fma(-g, hh, 0.5);
+  g = fma(g, r, g);
+  hh = fma(hh, r, hh);
+  return fma(fma(-g, g, x), hh, g);
+}
+
+// exp(z) for z <= 0: z = (64 k + j) ln2/64 + r, exp(z) = 2^k 2^(j/64) (1 + expm1(r)), |r| <= ln2/128;
+// expm1 by a degree-5 polynomial (truncation 3.5e-17), 2^(j/64) from a 64-entry shared-memory table.
+__device__ __forceinline__ double fast_exp_nonpos(double z, const double* __restrict__ tab) {
+  z = fmax(z, -708.0);  // below this the result underflows; it is then ~1e-308 instead of 0
+  const double t = fma(z, 92.332482616893656, 6755399441055744.0);  // 64/ln2 ; 1.5 * 2^52 rounds to integer
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -0.01083042469326756, z);      // ln2/64 (high part)
+  r = fma(kf, -2.9815858269852933e-12, r);          // ln2/64 (low part)
+  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = p * r;
+  const double tj = tab[k & ((1 << kExpTableBits) - 1)];
+  const double res = fma(tj, p, tj);
+  // scale by 2^(k >> 6): add to the exponent field (result stays normal because z >= -708)
+  return __hiloint2double(__double2hiint(res) + ((k >> kExpTableBits) << 20), __double2loint(res));
+}
+
+// One Matern-5/2 pair: from |diff|^2 (nsq) and diff.A (adot) to the weights of the accumulation.
+struct PairWeights {
+  double w1, c2, e;
+};
+struct PairConsts {
+  double sig, neg_sig_inv, base_fact, diag_fact, third_sig_inv;
+};
+template <bool USE_E>
+__device__ __forceinline__ PairWeights matern_pair(double nsq, double adot, double aE, const PairConsts& k,
+                                                   const double* __restrict__ exp_tab) {
+  const double nrm = fast_sqrt(5.0 * nsq);  // sqrt(5) |diff|
+  const double ex = fast_exp_nonpos(nrm * k.neg_sig_inv, exp_tab);
+  const double c1 = ex * k.base_fact;
+  PairWeights r;
+  r.c2 = c1 * (nrm + k.sig);
+  r.w1 = adot * c1 * k.diag_fact;
+  r.e = adot * r.c2;
+  if (USE_E) {  // gdml_predict.py:132-140
+    r.w1 = fma(aE, r.c2, r.w1);
+    r.e = fma(aE * ex, 1.0 + (-nrm * k.neg_sig_inv) * (1.0 + nrm * k.third_sig_inv), r.e);
+  }
+  return r;
 }
 
 template <int NA, bool USE_E>
-__global__ void __launch_bounds__(kMaternThreads, 1) k_matern(const MaternArgs a) {
-  constexpr int D = NA * (NA - 1) / 2;
+__global__ void __launch_bounds__(kMaternThreads, Blocking<NA>::MinCtas) k_matern(const MaternArgs a) {
+  using B = Blocking<NA>;
+  constexpr int D = B::D, L = B::L, Q = B::Q, DL = B::DL, Dp = B::Dp;
   constexpr int TR = kTileRows;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = a.P;
-  const int maxf = (nt + P - 1) / P + 1;
+  const int qc = matern_queries_per_cta<NA>(nt);  // queries of this CTA
+  const int maxf = (qc + P - 1) / P + 1;
+  const int team = tid / L, h = tid % L;
 
-  double2* tiles = reinterpret_cast<double2*>(smem_raw);  // [2][TR][D]
-  double* aEs = reinterpret_cast<double*>(tiles + 2 * TR * D);  // [2][TR]
-  double* Gs = aEs + 2 * TR;                                    // [nt][D]
-  double* Es = Gs + (size_t)nt * D;                             // [nt]
-  double* xs = Es + nt;                                         // [maxf][D]
-  double* rs = xs + (size_t)maxf * D;                           // [maxf][NA][3]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rs + (size_t)maxf * NA * 3);
+  double2* tiles = reinterpret_cast<double2*>(smem_raw);         // [2][TR][Dp]
+  double* aEs = reinterpret_cast<double*>(tiles + 2 * TR * Dp);  // [2][TR]
+  double* Gs = aEs + 2 * TR;                                     // [qc][D]
+  double* Es = Gs + (size_t)qc * D;                              // [qc]
+  double* xs = Es + qc;                                          // [maxf][D]
+  double* rs = xs + (size_t)maxf * D;                            // [maxf][NA][3]
+  double* etab = rs + (size_t)maxf * NA * 3;                     // [64] 2^(j/64)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(etab + (1 << kExpTableBits));
 
   const long long nq = a.n_frag * P;
-  const long long q0 = (long long)blockIdx.x * nt;
-  const long long q_end = (q0 + nt < nq) ? q0 + nt : nq;  // exclusive
+  const long long q0 = (long long)blockIdx.x * qc;
+  const long long q_end = (q0 + qc < nq) ? q0 + qc : nq;  // exclusive
   const long long f_lo = q0 / P;
   const int nf = (int)((q_end - 1) / P - f_lo) + 1;
 
   const int n_tiles = a.T_pad / TR;
-  constexpr uint32_t kTileBytes = TR * D * 16;
+  constexpr uint32_t kTileBytes = TR * Dp * 16;
   constexpr uint32_t kStageBytes = kTileBytes + (USE_E ? TR * 8 : 0);
 
+  // bars[0..1]: "full" (TMA landed a tile in stage s); bars[2..3]: "empty" (every warp is done with stage s).
+  // There is no CTA-wide barrier in the main loop: warps drift apart freely, which keeps the FP64 pipe fed
+  // by one warp's dot products while another warp sits in its latency-bound scalar chain.
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -131,10 +259,12 @@ __global__ void __launch_bounds__(kMaternThreads, 1) k_matern(const MaternArgs a
     for (int s = 0; s < 2; ++s)
       if (s < n_tiles) {
         mbar_expect_tx(&bars[s], kStageBytes);
-        tma_load_1d(tiles + s * TR * D, a.XA + (size_t)s * TR * D, kTileBytes, &bars[s]);
+        tma_load_1d(tiles + s * TR * Dp, a.XA + (size_t)s * TR * Dp, kTileBytes, &bars[s]);
         if (USE_E) tma_load_1d(aEs + s * TR, a.alphaE + (size_t)s * TR, TR * 8, &bars[s]);
       }
   }
+
+  if (tid < (1 << kExpTableBits)) etab[tid] = a.exp2_table[tid];
 
   // ---- prologue: geometry of this CTA's fragments (same code as the cull kernel) ----
   for (int fl = tid; fl < nf; fl += nt) {
@@ -158,81 +288,159 @@ __global__ void __launch_bounds__(kMaternThreads, 1) k_matern(const MaternArgs a
   }
   __syncthreads();
 
-  // ---- this thread's query: fragment fl_q under permutation perm ----
-  const long long q = q0 + tid;
-  const bool active = q < nq;
-  const int fl_q = active ? (int)(q / P - f_lo) : 0;
-  const int perm = active ? (int)(q % P) : 0;
-  const int* ip = a.iperm + perm * D;
-  double y[D], G[D];
+  // ---- this lane's Q queries (fragment, permutation) and its slice of their descriptors ----
+  bool active[Q];
+  const int* ip[Q];
+  double y[Q][DL], G[Q][DL];
 #pragma unroll
-  for (int e = 0; e < D; ++e) {
-    y[e] = xs[fl_q * D + ip[e]];
-    G[e] = 0.0;
+  for (int j = 0; j < Q; ++j) {
+    const long long q = q0 + (long long)team * Q + j;
+    active[j] = q < nq;
+    const int fl_q = active[j] ? (int)(q / P - f_lo) : 0;
+    ip[j] = a.iperm + (active[j] ? (int)(q % P) : 0) * D;
+#pragma unroll
+    for (int e = 0; e < DL; ++e) {
+      const int eg = h * DL + e;
+      y[j][e] = (eg < D) ? xs[fl_q * D + ip[j][eg]] : 0.0;
+      G[j][e] = 0.0;
+    }
   }
-  double Eacc = 0.0, s1 = 0.0;
-  const double sig = a.sig;
-  const double sig_inv = 1.0 / sig;
-  const double base_fact = 5.0 / (3.0 * sig * sig * sig);
-  const double diag_fact = 5.0 / sig;
-  const double sqrt5 = 2.23606797749978969641;
-  const double third_sig_inv = 1.0 / (3.0 * sig);
+  constexpr int OWN = (L == 1) ? Q : 1;  // queries whose exp/sqrt chain this lane evaluates
+  double Eacc[OWN], s1[OWN];
+#pragma unroll
+  for (int j = 0; j < OWN; ++j) Eacc[j] = 0.0, s1[j] = 0.0;
+  PairConsts pc;
+  pc.sig = a.sig;
+  pc.neg_sig_inv = -1.0 / a.sig;
+  pc.base_fact = 5.0 / (3.0 * a.sig * a.sig * a.sig);
+  pc.diag_fact = 5.0 / a.sig;
+  pc.third_sig_inv = 1.0 / (3.0 * a.sig);
 
   // ---- main loop over training tiles ----
+  // Per block of RB rows: (a) the scalar chains of the block (shuffle -> sqrt -> exp -> shuffle; latency
+  // bound), (b) the dot products of the NEXT block (throughput bound, independent of (a)), (c) the
+  // accumulation of the block.  Measured on B200 (profiles/r1_kernel_tuning.md): with 2 warps per SM
+  // sub-partition the FP64 pipe idles when both warps sit in (a), so (a) is kept short (branch-free math,
+  // RB interleaved chains) -- skewing the warps or dropping the per-tile barrier did not help.
+  // Dimensions are processed in chunks of CH so that dependent FP64 instructions (difference -> FMA,
+  // and the two FMAs into one accumulator) are CH*Q instructions apart, beyond the ~9-cycle DFMA latency.
+  constexpr int CH = (DL % 3 == 0) ? 3 : (DL % 2 == 0) ? 2 : 1;
+  auto dots = [&](uint32_t row, double (&n2)[Q], double (&aa)[Q]) {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) n2[j] = 0.0, aa[j] = 0.0;
+#pragma unroll
+    for (int e0 = 0; e0 < DL; e0 += CH) {
+      double2 v[CH];
+      double d[CH][Q];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[c] = lds_row(row + (e0 + c) * 16);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) d[c][j] = y[j][e0 + c] - v[c].x;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          n2[j] = fma(d[c][j], d[c][j], n2[j]);
+          aa[j] = fma(d[c][j], v[c].y, aa[j]);
+        }
+    }
+  };
+  auto weights = [&](const double (&n2)[Q], const double (&aa)[Q], double aE, double (&w1)[Q], double (&c2)[Q]) {
+    if constexpr (L == 1) {
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        const PairWeights pw = matern_pair<USE_E>(n2[j], aa[j], aE, pc, etab);
+        w1[j] = pw.w1, c2[j] = pw.c2;
+        Eacc[j] += pw.e;
+        s1[j] += pw.w1;
+      }
+    } else {  // L == 2, Q == 2: lane h owns query h; swap the other query's partial sums
+      const double own_n = (h ? n2[1] : n2[0]) + __shfl_xor_sync(0xffffffffu, h ? n2[0] : n2[1], 1);
+      const double own_a = (h ? aa[1] : aa[0]) + __shfl_xor_sync(0xffffffffu, h ? aa[0] : aa[1], 1);
+      const PairWeights pw = matern_pair<USE_E>(own_n, own_a, aE, pc, etab);
+      Eacc[0] += pw.e;
+      s1[0] += pw.w1;
+      const double w1x = __shfl_xor_sync(0xffffffffu, pw.w1, 1);
+      const double c2x = __shfl_xor_sync(0xffffffffu, pw.c2, 1);
+      w1[0] = h ? w1x : pw.w1, w1[1] = h ? pw.w1 : w1x;
+      c2[0] = h ? c2x : pw.c2, c2[1] = h ? pw.c2 : c2x;
+    }
+  };
+  auto accumulate = [&](uint32_t row, const double (&w1)[Q], const double (&c2)[Q]) {
+#pragma unroll
+    for (int e0 = 0; e0 < DL; e0 += CH) {
+      double2 v[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[c] = lds_row(row + (e0 + c) * 16);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) G[j][e0 + c] = fma(-w1[j], v[c].x, G[j][e0 + c]);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) G[j][e0 + c] = fma(-c2[j], v[c].y, G[j][e0 + c]);
+    }
+  };
+  // The loop handles RB rows per iteration so that every lane carries RB (x Q when L == 1) independent
+  // scalar chains: the compiler interleaves them, and one chain latency is paid per RB rows instead of per row.
+  constexpr int RB = 2;
+  static_assert(TR % RB == 0, "tile rows must be a multiple of the row block");
   for (int tile = 0; tile < n_tiles; ++tile) {
     const int s = tile & 1;
     mbar_wait(&bars[s], (tile >> 1) & 1);
-    const uint32_t tb = smem_u32(tiles + s * TR * D);
+    const uint32_t tb = smem_u32(tiles + s * TR * Dp) + h * (DL * 16);
     const double* ab = aEs + s * TR;
+    double n2[RB][Q], aa[RB][Q];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) dots(tb + r * (Dp * 16), n2[r], aa[r]);
 #pragma unroll 1
-    for (int t = 0; t < TR; ++t) {
-      const uint32_t row = tb + t * (D * 16);
-      double n2a = 0.0, n2b = 0.0, aa = 0.0, ab2 = 0.0;
+    for (int t = 0; t < TR; t += RB) {
+      const uint32_t row = tb + t * (Dp * 16);
+      double w1[RB][Q], c2[RB][Q];
 #pragma unroll
-      for (int e = 0; e < D; ++e) {
-        const double2 v = lds_row(row + e * 16);
-        const double d = y[e] - v.x;
-        if (e & 1) {
-          n2b = fma(d, d, n2b);
-          ab2 = fma(d, v.y, ab2);
-        } else {
-          n2a = fma(d, d, n2a);
-          aa = fma(d, v.y, aa);
-        }
-      }
-      const double adot = aa + ab2;
-      const double nrm = sqrt5 * sqrt(n2a + n2b);
-      const double ex = exp(-nrm * sig_inv);
-      const double c1 = ex * base_fact;
-      const double c2 = c1 * (nrm + sig);
-      double w1 = adot * c1 * diag_fact;
-      Eacc = fma(adot, c2, Eacc);
-      if (USE_E) {  // gdml_predict.py:132-140
-        const double aE = ab[t];
-        w1 = fma(aE, c2, w1);
-        Eacc = fma(aE * ex, 1.0 + (nrm * sig_inv) * (1.0 + nrm * third_sig_inv), Eacc);
-      }
-      s1 += w1;
+      for (int r = 0; r < RB; ++r) weights(n2[r], aa[r], USE_E ? ab[t + r] : 0.0, w1[r], c2[r]);  // (a) rows t..t+RB-1
+      const uint32_t nxt = row + (t + RB < TR ? RB * Dp * 16 : 0);  // last block: recomputed, unused
 #pragma unroll
-      for (int e = 0; e < D; ++e) {
-        const double2 v = lds_row(row + e * 16);
-        G[e] = fma(-w1, v.x, G[e]);
-        G[e] = fma(-c2, v.y, G[e]);
-      }
+      for (int r = 0; r < RB; ++r) dots(nxt + r * (Dp * 16), n2[r], aa[r]);                        // (b) next block
+#pragma unroll
+      for (int r = 0; r < RB; ++r) accumulate(row + r * (Dp * 16), w1[r], c2[r]);                  // (c) rows t..
     }
     __syncthreads();  // every thread is done with stage s
     if (tid == 0 && tile + 2 < n_tiles) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bars[s], kStageBytes);
-      tma_load_1d(tiles + s * TR * D, a.XA + (size_t)(tile + 2) * TR * D, kTileBytes, &bars[s]);
+      tma_load_1d(tiles + s * TR * Dp, a.XA + (size_t)(tile + 2) * TR * Dp, kTileBytes, &bars[s]);
       if (USE_E) tma_load_1d(aEs + s * TR, a.alphaE + (size_t)(tile + 2) * TR, TR * 8, &bars[s]);
     }
   }
 
-  // ---- epilogue: un-permute, reduce over permutations, project, scale, scatter ----
+  // ---- epilogue: G += s1 y, un-permute, reduce over permutations, project, scale, scatter ----
+  double s1q[Q];
+  if constexpr (L == 1) {
 #pragma unroll
-  for (int e = 0; e < D; ++e) Gs[tid * D + ip[e]] = active ? fma(s1, y[e], G[e]) : 0.0;
-  Es[tid] = active ? Eacc : 0.0;
+    for (int j = 0; j < Q; ++j) s1q[j] = s1[j];
+  } else {
+    const double s1x = __shfl_xor_sync(0xffffffffu, s1[0], 1);
+    s1q[0] = h ? s1x : s1[0], s1q[1] = h ? s1[0] : s1x;
+  }
+#pragma unroll
+  for (int j = 0; j < Q; ++j) {
+    const int ql = team * Q + j;
+#pragma unroll
+    for (int e = 0; e < DL; ++e) {
+      const int eg = h * DL + e;
+      if (eg < D) Gs[ql * D + ip[j][eg]] = active[j] ? fma(s1q[j], y[j][e], G[j][e]) : 0.0;
+    }
+  }
+  if constexpr (L == 1) {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) Es[team * Q + j] = active[j] ? Eacc[j] : 0.0;
+  } else {
+    Es[team * Q + h] = (h ? active[1] : active[0]) ? Eacc[0] : 0.0;
+  }
   __syncthreads();
 
   // F_d of fragment fl -> first row of its segment; E likewise.

@@ -23,11 +23,20 @@ MASSES = {
 }
 
 
+_MASS_TABLE = np.full(max(MASSES) + 1, np.nan)
+for _z, _m in MASSES.items():
+    _MASS_TABLE[_z] = _m
+
+
 def masses_of(Z, strict=True):
     """Per-atom masses for atomic numbers ``Z`` (KeyError for an unknown element if ``strict``)."""
-    if strict:
-        return np.array([MASSES[int(z)] for z in Z], dtype=np.float64)
-    return np.array([MASSES.get(int(z), np.nan) for z in Z], dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.int64)
+    known = (Z >= 0) & (Z < len(_MASS_TABLE))
+    out = np.full(Z.shape, np.nan)
+    out[known] = _MASS_TABLE[Z[known]]
+    if strict and np.isnan(out).any():
+        raise KeyError(f"no mass tabulated for atomic number {int(Z[np.isnan(out)][0])}")
+    return out
 
 
 def _as_batch(R):
