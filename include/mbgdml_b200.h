@@ -35,6 +35,11 @@ extern "C" {
 #define MBG_ERR_UNSUPPORTED (-3) /* valid request this build has no kernel for (no CPU fallback exists) */
 #define MBG_ERR_NOMEM (-4)
 
+/* Contraction kernel selection (mbg_context_set_contraction). */
+#define MBG_CONTRACT_AUTO 0 /* the faster one for the fragment size (DMMA in this build)                     */
+#define MBG_CONTRACT_FMA 1  /* difference form on the FP64 FMA pipe                      (csrc/matern.cuh)     */
+#define MBG_CONTRACT_DMMA 2 /* GEMM recast on the FP64 tensor pipe, mma.sync.m8n8k4.f64  (csrc/matern_mma.cuh) */
+
 #define MBG_MAX_ORDER 8       /* entities per fragment */
 #define MBG_MAX_FRAG_ATOMS 24 /* atoms per fragment */
 #define MBG_MAX_ALCHEMY 16    /* alchemical scalers per job */
@@ -125,6 +130,9 @@ int mbg_context_destroy(mbg_context_t ctx);
 /* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = context's own. */
 int mbg_context_set_stream(mbg_context_t ctx, void *cuda_stream);
 int mbg_context_synchronize(mbg_context_t ctx);
+/* Choose the kernel that evaluates _predict_gdml_wkr (gdml_predict.py:94-142): MBG_CONTRACT_*.  Both give the
+ * same results to rounding; the choice exists so that the benchmark can time one against the other. */
+int mbg_context_set_contraction(mbg_context_t ctx, int kind);
 /* Launch counters since context creation: number of kernels this library launched. */
 int mbg_context_launch_count(mbg_context_t ctx, int64_t *n_launches);
 /* Device time (ms, CUDA events on the context's stream) of the Matern contraction launches and of

@@ -20,11 +20,12 @@ MBG_OK, MBG_ERR_ARG, MBG_ERR_CUDA, MBG_ERR_UNSUPPORTED, MBG_ERR_NOMEM = 0, -1, -
 CRIT_NONE, CRIT_COM_DISTANCE_SUM, CRIT_MAX_ATOM_PAIR_DIST = 0, 1, 2
 BOUND_UPPER, BOUND_LOWER, BOUND_RANGE = 0, 1, 2
 FLAG_R_ON_DEVICE, FLAG_OUT_ON_DEVICE, FLAG_VIRIAL, FLAG_ACCUMULATE = 1, 2, 4, 8
+CONTRACT_AUTO, CONTRACT_FMA, CONTRACT_DMMA = 0, 1, 2
 
 # every symbol include/mbgdml_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mbg_last_error", "mbg_abi_version", "mbg_device_count", "mbg_context_create", "mbg_context_destroy",
-    "mbg_context_set_stream", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
+    "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_enumerate",
     "mbg_criteria_eval", "mbg_r_mic", "mbg_measure_fp64_peak",
@@ -89,6 +90,7 @@ def load_library():
         lib.mbg_context_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         lib.mbg_context_destroy.argtypes = [C.c_void_p]
         lib.mbg_context_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mbg_context_set_contraction.argtypes = [C.c_void_p, C.c_int]
         lib.mbg_context_synchronize.argtypes = [C.c_void_p]
         lib.mbg_context_launch_count.argtypes = [C.c_void_p, _lp]
         lib.mbg_context_last_timing.argtypes = [C.c_void_p, _dp, _dp, _lp]
@@ -170,6 +172,11 @@ class Context:
 
     def set_stream(self, cuda_stream):
         check(self.lib.mbg_context_set_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    def set_contraction(self, kind):
+        """'auto' | 'fma' | 'dmma': which kernel evaluates the Matern contraction."""
+        code = {"auto": CONTRACT_AUTO, "fma": CONTRACT_FMA, "dmma": CONTRACT_DMMA}[kind] if isinstance(kind, str) else kind
+        check(self.lib.mbg_context_set_contraction(self.handle, int(code)))
 
     def synchronize(self):
         check(self.lib.mbg_context_synchronize(self.handle))

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmbgdml_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "geom.cuh", "enumerate.cuh", "matern.cuh", "hostmath.h",
+HEADERS = ["common.cuh", "geom.cuh", "enumerate.cuh", "matern.cuh", "hostmath.h", "matern_mma.cuh",
            os.path.join("..", "..", "include", "mbgdml_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -30,7 +30,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [
+    extra = ["-DMBG_TUNING_VARIANTS"] if os.environ.get("MBG_TUNING_VARIANTS") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [
         os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

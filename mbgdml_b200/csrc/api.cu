@@ -13,6 +13,7 @@
 #include "enumerate.cuh"
 #include "hostmath.h"
 #include "matern.cuh"
+#include "matern_mma.cuh"
 
 using namespace mbg;
 
@@ -74,6 +75,8 @@ struct mbg_context_s {
   cudaStream_t own_stream = nullptr;
   int sm_count = 0;
   int64_t launches = 0;
+  int contraction = MBG_CONTRACT_AUTO;  // which contraction kernel mbg_predict uses
+  int mma_cfg = 0;                      // developer builds: MT*1000 + threads of the trimer DMMA kernel
   // scratch
   DevBuf sys_ints, sys_masses, R, outE, outF, outV;
   DevBuf job_ints, flags, blk_acc, blk_enum, blk_off, totals;
@@ -87,7 +90,7 @@ struct mbg_context_s {
   double ms_contract = 0, ms_other = 0;
   int64_t n_contract = 0;
   bool timing_pending = false;
-  struct LaunchRec { int n_frag_atoms; long long n_frag; int n_train, n_perms; float ms; };
+  struct LaunchRec { int n_frag_atoms; long long n_frag; int n_train, n_perms; float ms; int kind; };
   std::vector<LaunchRec> launch_recs;
 };
 
@@ -96,7 +99,9 @@ struct mbg_model_s {
   int n_atoms, order, D, T, T_pad, P;
   double sig, c, std;
   bool use_E;
-  double2* XA = nullptr;
+  double2* XA = nullptr;     // FMA-pipe kernel: [T_pad][Dp] (X, A) interleaved
+  double* tiles_mma = nullptr;  // DMMA kernel: packed tiles (matern_mma.cuh)
+  double* mu = nullptr;         // DMMA kernel: centre of the training descriptors [D]
   double* alphaE = nullptr;
   int* iperm = nullptr;
   CritDev crit;
@@ -163,9 +168,55 @@ static int launch_matern_t(mbg_context_t ctx, const MaternArgs& a) {
   cudaEventRecord(e1, ctx->stream);
   ctx->launches++;
   ctx->n_contract++;
-  ctx->launch_recs.push_back({NA, a.n_frag, a.T_pad, a.P, 0.f});
+  ctx->launch_recs.push_back({NA, a.n_frag, a.T_pad, a.P, 0.f, MBG_CONTRACT_FMA});
   CUDA_TRY(cudaGetLastError());
   return MBG_OK;
+}
+
+template <int NA, int MT, int NTHR, bool USE_E>
+static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a) {
+  int dev_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  const int nt = NTHR;
+  const size_t smem = mma_smem_bytes<NA, MT>(nt, a.P);
+  if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(k_matern_mma<NA, MT, NTHR, USE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long nq = a.n_frag * a.P;
+  const int qc = mma_queries_per_cta<NA, MT>(nt);
+  const long long grid = (nq + qc - 1) / qc;
+  if (grid > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "too many fragments in one launch");
+  cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+  k_matern_mma<NA, MT, NTHR, USE_E><<<(unsigned)grid, nt, smem, ctx->stream>>>(a);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches++;
+  ctx->n_contract++;
+  ctx->launch_recs.push_back({NA, a.n_frag, a.T_pad, a.P, 0.f, MBG_CONTRACT_DMMA});
+  CUDA_TRY(cudaGetLastError());
+  return MBG_OK;
+}
+
+static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const MaternMmaArgs& a) {
+#ifdef MBG_TUNING_VARIANTS  // developer build: extra (MT, threads) shapes of the trimer kernel, chosen by MBG_MMA_CFG
+  if (na == 9 && !use_E) {
+    switch (ctx->mma_cfg) {
+      case 2384: return launch_matern_mma_t<9, 2, 384, false>(ctx, a);
+      case 2512: return launch_matern_mma_t<9, 2, 512, false>(ctx, a);
+      case 4256: return launch_matern_mma_t<9, 4, 256, false>(ctx, a);
+      case 3256: return launch_matern_mma_t<9, 3, 256, false>(ctx, a);
+      default: break;
+    }
+  }
+#endif
+  switch (na) {
+#define X(N) \
+  case N:    \
+    return use_E ? launch_matern_mma_t<N, 2, 256, true>(ctx, a) : launch_matern_mma_t<N, 2, 256, false>(ctx, a);
+    MBG_FOR_EACH_NA(X)
+#undef X
+    default:
+      return fail(MBG_ERR_UNSUPPORTED, "no contraction kernel for fragments of %d atoms", na);
+  }
 }
 
 static int launch_matern(mbg_context_t ctx, int na, bool use_E, const MaternArgs& a) {
@@ -440,6 +491,25 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
                                                                          NA * 3, out.E, out.F);
       ctx->launches++;
     }
+    if (ctx->contraction != MBG_CONTRACT_FMA) {
+      MaternMmaArgs a;
+      a.sys = s;
+      a.R = dR;
+      a.tiles = m->tiles_mma, a.mu = m->mu, a.iperm = m->iperm;
+      a.exp2_table = ctx->exp2_table.as<double>();
+      a.T_pad = m->T_pad, a.P = m->P;
+      a.sig = m->sig, a.c = m->c, a.std = m->std;
+      a.n_frag = rec_pending;
+      a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
+      a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
+      a.n_slots_per_frame = (int)j.cand_per_frame;
+      a.decomp = decomp ? 1 : 0;
+      a.want_virial = want_virial ? 1 : 0;
+      a.E = out.E, a.F = out.F, a.virial = out.V;
+      TRY(launch_matern_mma(ctx, NA, m->use_E, a));
+      rec_pending = 0;
+      return MBG_OK;
+    }
     MaternArgs a;
     a.sys = s;
     a.R = dR;
@@ -589,6 +659,11 @@ int mbg_context_create(int device, mbg_context_t* out) {
   }
   CUDA_TRY(cudaEventCreate(&ctx->ev_call0));
   CUDA_TRY(cudaEventCreate(&ctx->ev_call1));
+  if (const char* v = getenv("MBG_CONTRACT")) {  // developer override; mbg_context_set_contraction wins
+    if (!strcmp(v, "fma")) ctx->contraction = MBG_CONTRACT_FMA;
+    if (!strcmp(v, "dmma")) ctx->contraction = MBG_CONTRACT_DMMA;
+  }
+  if (const char* v = getenv("MBG_MMA_CFG")) ctx->mma_cfg = atoi(v);
   *out = ctx;
   return MBG_OK;
 }
@@ -620,6 +695,14 @@ int mbg_context_synchronize(mbg_context_t ctx) {
   if (!ctx) return fail(MBG_ERR_ARG, "ctx is NULL");
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MBG_OK;
+}
+
+int mbg_context_set_contraction(mbg_context_t ctx, int kind) {
+  if (!ctx) return fail(MBG_ERR_ARG, "ctx is NULL");
+  if (kind != MBG_CONTRACT_AUTO && kind != MBG_CONTRACT_FMA && kind != MBG_CONTRACT_DMMA)
+    return fail(MBG_ERR_ARG, "unknown contraction kind %d", kind);
+  ctx->contraction = kind;
   return MBG_OK;
 }
 
@@ -700,6 +783,45 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   }
   CUDA_TRY(cudaMemcpy(m->XA, xa.data(), xa.size() * sizeof(double2), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(m->iperm, iperm.data(), iperm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  {
+    // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row 5|X'|^2 and X'.A_s,
+    // packed per tile of 64 rows; side arrays in column order (column j of a block <-> row tau(j)).
+    static_assert(kMmaTileRows == kTileRows, "both kernels pad T to the same tile size");
+    const int Dq = mma_row_pad(d->n_atoms), TILE = mma_tile_doubles(d->n_atoms), TRm = kMmaTileRows;
+    std::vector<double> mu(D, 0.0);
+    for (int e = 0; e < D; ++e) {
+      long double acc = 0;
+      for (int t = 0; t < T; ++t) acc += d->R_desc[(size_t)e * T + t];
+      mu[e] = (double)(acc / T);
+    }
+    const double diag = 5.0 / d->sig;
+    std::vector<double> tl((size_t)(T_pad / TRm) * TILE, 0.0);
+    for (int t = 0; t < T; ++t) {
+      double* tile = tl.data() + (size_t)(t / TRm) * TILE;
+      const int r = t % TRm;
+      double* xrow = tile + (size_t)r * Dq;
+      double* arow = tile + (size_t)TRm * Dq + (size_t)r * Dq;
+      long double xx = 0, xa = 0;
+      for (int e = 0; e < D; ++e) {
+        const double xv = d->R_desc[(size_t)e * T + t] - mu[e];
+        const double av = diag * d->R_d_desc_alpha[(size_t)t * D + e];
+        xrow[e] = xv, arow[e] = av;
+        xx += (long double)xv * xv, xa += (long double)xv * av;
+      }
+      // position of row r in column order: r = 8 b + tau(j)  ->  8 b + j  (tau is an involution)
+      const int pos = (r / 8) * 8 + mma_tau(r % 8);
+      double* side = tile + (size_t)2 * TRm * Dq;
+      side[2 * pos] = (double)(5.0L * xx), side[2 * pos + 1] = (double)xa;
+      if (d->alphas_E) side[2 * TRm + pos] = d->alphas_E[t];
+    }
+    if (cudaMalloc(&m->tiles_mma, tl.size() * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&m->mu, (size_t)D * sizeof(double)) != cudaSuccess) {
+      cleanup();
+      return fail(MBG_ERR_NOMEM, "cudaMalloc for model failed");
+    }
+    CUDA_TRY(cudaMemcpy(m->tiles_mma, tl.data(), tl.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->mu, mu.data(), (size_t)D * sizeof(double), cudaMemcpyHostToDevice));
+  }
   if (m->use_E) {
     std::vector<double> aE(T_pad, 0.0);
     for (int t = 0; t < T; ++t) aE[t] = d->alphas_E[t];
@@ -739,6 +861,8 @@ int mbg_model_destroy(mbg_model_t m) {
   if (!m) return MBG_OK;
   cudaSetDevice(m->ctx->device);
   if (m->XA) cudaFree(m->XA);
+  if (m->tiles_mma) cudaFree(m->tiles_mma);
+  if (m->mu) cudaFree(m->mu);
   if (m->alphaE) cudaFree(m->alphaE);
   if (m->iperm) cudaFree(m->iperm);
   delete m;

@@ -1,0 +1,421 @@
+// K3 + K4, tensor-core version: the Matern-5/2 contraction with its two dot products and its two rank-1
+// accumulations recast as FP64 GEMMs on the DMMA pipe (mma.sync.m8n8k4.f64), the sqrt/exp chain fused
+// between them on the FMA/MUFU pipes, and the same fused epilogue (J^T projection, scaling, alchemical
+// factor, scatter) as the FMA-pipe kernel in matern.cuh.
+//
+// Reference: mbgdml/predictors/gdml_predict.py:94-142 (contraction), 151-163 (J^T F_d), 251-267 (scale,
+//            scatter, virial); mbgdml/models/gdml_model.py:109-118 (permutation expansion).
+//
+// Math.  As in matern.cuh the *query* is permuted (y_p[e] = x[pi_p^-1(e)]) and contracts against the T
+// un-permuted training rows.  With mu = mean_t X_t, y' = y - mu, X' = X - mu, A_s = (5/sig) A:
+//     |diff|^2 = |y'|^2 + |X'_t|^2 - 2 y'.X'_t            a_s = (5/sig) diff.A_t = y'.A_s,t - X'_t.A_s,t
+// so the D-wide work per (query, row) is two length-D dot products (GEMM 1: [queries x D] x [D x rows] against
+// the X' and the A_s plane) and two rank-1 updates  Gacc += w X'_t + c2s A_s,t  (GEMM 2: [queries x rows] x
+// [rows x D]) -- 4 D multiply-adds instead of the 5 D instructions of the difference form.  Centring by mu
+// keeps the cancellation in |diff|^2 harmless (|y'|^2 ~ |diff|^2).  Per pair, on the FMA pipe:
+//     s = 5|diff|^2 ; n = sqrt(s) ; ex = exp(-n/sig) ; w = a_s ex ; c2s = ex (n + sig) sig/5
+//     E_s += a_s c2s ; s1 += w                       [+ the alphas_E terms, gdml_predict.py:132-140]
+// and at the end, with base = 5/(3 sig^3):  G = base (s1 y' - Gacc),  E_raw = base E_s,
+// F_d[d] = sum_p G_p[pi_p(d)]  -- algebraically the reference's  F_d += w1 diff - c2 A_j,  E += a c2.
+//
+// Mapping.  One warp owns 8*MT queries (MT m-tiles).  For every block of 8 training rows:
+//   GEMM 1: A operand = y' (registers, loaded once), B operand = the X' / A_s rows (shared memory),
+//           C fragment: thread (g = lane/4, l = lane%4) holds columns 2l, 2l+1 of row g;
+//   chain:  element-wise on the C fragments (2*MT pairs per thread);
+//   GEMM 2: the weights are already laid out as an A operand if the k index l of the two k-steps is taken
+//           to mean columns 2l (+0 / +1) -- the sum over rows does not care about their order -- so no
+//           shuffle is needed; B operand = the same rows read along e; accumulators G[q][e] in registers.
+// Column j of a block maps to physical row tau(j) = {0,1,2,3,5,4,7,6}[j]: with a row stride of 32 (mod 128)
+// bytes this makes every 8-byte shared-memory load of both GEMMs bank-conflict free.
+// Tiles of 64 rows ([X' plane | A_s plane | (5|X'|^2, X'.A_s) | alphas_E], packed per tile by the host) are
+// staged by one TMA bulk copy each, double buffered on mbarriers.
+#pragma once
+#include "matern.cuh"
+
+namespace mbg {
+
+template <int NA>
+struct MmaShape {
+  static constexpr int D = NA * (NA - 1) / 2;
+  static constexpr int KS = (D + 3) / 4;                      // k-steps of GEMM 1
+  static constexpr int NT = (D + 7) / 8;                      // n-tiles of GEMM 2
+  static constexpr int Dp = (D <= 4) ? 4 : ((D - 4 + 7) / 8 * 8 + 4);  // row length: >= D and = 4 (mod 8)
+  static_assert(Dp >= 4 * KS && Dp % 8 == 4, "row padding");
+};
+
+constexpr int kMmaTileRows = 64;
+__host__ __device__ constexpr int mma_row_pad(int na) {
+  const int D = na * (na - 1) / 2;
+  return (D <= 4) ? 4 : ((D - 4 + 7) / 8 * 8 + 4);
+}
+// doubles per packed tile: two planes, (xx5, xa) per row, alphas_E per row
+__host__ __device__ constexpr int mma_tile_doubles(int na) { return kMmaTileRows * (2 * mma_row_pad(na) + 3); }
+__host__ __device__ constexpr int mma_tau(int j) { return j < 4 ? j : (j ^ 1); }  // {0,1,2,3,5,4,7,6}
+
+struct MaternMmaArgs {
+  SysDev sys;
+  const double* R;           // [n_frames][n_atoms][3]
+  const double* tiles;       // [T_pad/64][mma_tile_doubles]
+  const double* mu;          // [D] centre of the training descriptors
+  const double* exp2_table;  // [64] 2^(j/64)
+  const int* iperm;          // [P][D]: pi_p^-1
+  int T_pad, P;
+  double sig, c, std;
+  long long n_frag;
+  const int* rec_frame;
+  const int* rec_atoms;
+  const double* rec_lambda;
+  const long long* rec_slot;
+  int n_slots_per_frame;
+  int decomp;
+  int want_virial;
+  double* E;
+  double* F;
+  double* virial;
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+// sqrt(x) for x > 0 (caller clamps): rsqrt seed + Goldschmidt + one residual correction (~1 ulp).
+__device__ __forceinline__ double sqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, hh = 0.5 * y;
+  const double r = fma(-g, hh, 0.5);
+  g = fma(g, r, g);
+  hh = fma(hh, r, hh);
+  return fma(fma(-g, g, x), hh, g);
+}
+
+// 2^(u/64) for u <= 0, given as the product v * k64 (evaluated inside the FMAs, one rounding):
+// u = k + r, k integer, |r| <= 1/2;  2^(u/64) = 2^(k>>6) 2^((k&63)/64) exp(r ln2/64).
+__device__ __forceinline__ double exp2_64_prod(double v, double k64, const double* __restrict__ tab) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(v, k64, kMagic);
+  const int k = __double2loint(t);
+  const double kf = t - kMagic;
+  const double r = fma(v, k64, -kf);
+  // exp(r c) - 1, c = ln2/64, |r c| <= 5.42e-3: degree 5 (truncation 3.5e-17)
+  double p = fma(r, 1.2417843701716925e-12, 5.732851688640402e-10);  // c^5/120, c^4/24
+  p = fma(p, r, 2.1173137155464776e-07);                            // c^3/6
+  p = fma(p, r, 5.86490495505617e-05);                              // c^2/2
+  p = fma(p, r, 0.010830424696249145);                              // c
+  p = p * r;
+  const double tj = tab[k & 63];
+  const double res = fma(tj, p, tj);
+  // the caller keeps u >= -60000, so the scaled result stays a normal number
+  return __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+}
+
+template <int NA, int MT>
+__host__ __device__ constexpr int mma_queries_per_cta(int nt) {
+  return nt / 32 * 8 * MT;
+}
+
+template <int NA, int MT>
+__host__ __device__ constexpr size_t mma_smem_bytes(int nt, int P) {
+  constexpr int D = MmaShape<NA>::D;
+  const int qc = mma_queries_per_cta<NA, MT>(nt);
+  const int maxf = (qc + P - 1) / P + 1;
+  const size_t tiles = (size_t)2 * mma_tile_doubles(NA) * 8;
+  const size_t gs = (size_t)qc * (D + 1) * 8;  // epilogue staging, aliased onto the tile buffers
+  return (tiles > gs ? tiles : gs) + (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + (size_t)D * 8 + 8 + 64 * 8 + 64;
+}
+
+template <int NA, int MT, int NTHR, bool USE_E>
+__global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
+  using S = MmaShape<NA>;
+  constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
+  constexpr int TR = kMmaTileRows;
+  constexpr int TILE = mma_tile_doubles(NA);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, l = lane & 3;
+  const int P = a.P;
+  const int qc = mma_queries_per_cta<NA, MT>(nt);
+  const int maxf = (qc + P - 1) / P + 1;
+
+  double* tiles = reinterpret_cast<double*>(smem_raw);  // [2][TILE]; reused as Gs[qc][D], Es[qc] in the epilogue
+  const size_t tiles_bytes = (size_t)2 * TILE * 8, gs_bytes = (size_t)qc * (D + 1) * 8;
+  double* xs = reinterpret_cast<double*>(smem_raw + (tiles_bytes > gs_bytes ? tiles_bytes : gs_bytes));  // [maxf][D]
+  double* rs = xs + (size_t)maxf * D;                                                                    // [maxf][NA][3]
+  double* mus = rs + (size_t)maxf * NA * 3;                                                              // [D] (+1 pad)
+  double* etab = mus + D + 1;                                                                            // [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(etab + 64);
+
+  const long long nq = a.n_frag * P;
+  const long long q0 = (long long)blockIdx.x * qc;
+  const long long q_end = (q0 + qc < nq) ? q0 + qc : nq;
+  const long long f_lo = q0 / P;
+  const int nf = (int)((q_end - 1) / P - f_lo) + 1;
+  const int n_tiles = a.T_pad / TR;
+  constexpr uint32_t kTileBytes = TILE * 8;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (s < n_tiles) {
+        mbar_expect_tx(&bars[s], kTileBytes);
+        tma_load_1d(tiles + (size_t)s * TILE, a.tiles + (size_t)s * TILE, kTileBytes, &bars[s]);
+      }
+  }
+  if (tid < 64) etab[tid] = a.exp2_table[tid];
+  if (tid < D) mus[tid] = a.mu[tid];
+
+  // ---- prologue: geometry + descriptor of this CTA's fragments (desc.py:79-158) ----
+  for (int fl = tid; fl < nf; fl += nt) {
+    const long long frag = f_lo + fl;
+    const int* atoms = a.rec_atoms + frag * NA;
+    const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
+    double r[NA][3];
+    int at[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) at[k] = atoms[k];
+    fragment_coords<NA>(a.sys, Rf, at, r);
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      rs[(fl * NA + i) * 3 + 0] = r[i][0], rs[(fl * NA + i) * 3 + 1] = r[i][1], rs[(fl * NA + i) * 3 + 2] = r[i][2];
+#pragma unroll
+      for (int j = 0; j < i; ++j, ++k)
+        xs[fl * D + k] = __ddiv_rn(1.0, norm3_rn(__dsub_rn(r[i][0], r[j][0]), __dsub_rn(r[i][1], r[j][1]),
+                                                  __dsub_rn(r[i][2], r[j][2])));
+    }
+  }
+  __syncthreads();
+
+  // ---- this thread's slices of the warp's queries: A fragments of y' (row g of each m-tile) ----
+  double Y[MT][KS], yy5[MT];
+  bool active[MT];
+  int fl_q[MT];
+  const int* ip[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const long long q = q0 + (long long)warp * (8 * MT) + 8 * i + g;
+    active[i] = q < nq;
+    fl_q[i] = active[i] ? (int)(q / P - f_lo) : 0;
+    ip[i] = a.iperm + (active[i] ? (int)(q % P) : 0) * D;
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int e = 4 * k + l;
+      const double v = (e < D && active[i]) ? xs[fl_q[i] * D + ip[i][e]] - mus[e] : 0.0;
+      Y[i][k] = v;
+      part = fma(v, v, part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    yy5[i] = 5.0 * part;
+  }
+  double G[MT][NT][2];
+  double Eacc[MT], s1[MT], E2[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    Eacc[i] = 0.0, s1[i] = 0.0, E2[i] = 0.0;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) G[i][n][0] = 0.0, G[i][n][1] = 0.0;
+  }
+
+  const double sig = a.sig;
+  const double k64 = -64.0 * 1.4426950408889634 / sig;  // u = n * k64 = -64 log2(e) n / sig
+  const double kc1 = sig / 5.0, kc0 = sig * sig / 5.0;  // c2s = ex (n kc1 + kc0) = ex (n + sig) sig/5
+  // clamp of s = 5|diff|^2: below, rounding may have made it <= 0; above, exp underflows anyway
+  const double s_max = (60000.0 / k64) * (60000.0 / k64);
+
+  // per-thread element offsets of the B operands inside a tile
+  const int offB1 = mma_tau(g) * Dp + l;                                        // GEMM 1: row tau(g), column 4k + l
+  const int offB2[2] = {mma_tau(2 * l) * Dp + g, mma_tau(2 * l + 1) * Dp + g};  // GEMM 2: row tau(2l+par), column 8n + g
+
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int s = tile & 1;
+    mbar_wait(&bars[s], (tile >> 1) & 1);
+    const double* Xs = tiles + (size_t)s * TILE;
+    const double* As = Xs + TR * Dp;
+    const double2* side = reinterpret_cast<const double2*>(As + TR * Dp);  // [TR] (xx5, xa) in column order
+    const double* aEs = reinterpret_cast<const double*>(side + TR);        // [TR] alphas_E in column order
+#pragma unroll 1
+    for (int b = 0; b < TR / 8; ++b) {
+      const double* Xb = Xs + b * 8 * Dp;
+      const double* Ab = As + b * 8 * Dp;
+      // ---- GEMM 1 ----
+      double c1[MT][2], c2[MT][2];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) c1[i][0] = c1[i][1] = c2[i][0] = c2[i][1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const double bx = Xb[offB1 + 4 * k], ba = Ab[offB1 + 4 * k];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          dmma884(c1[i][0], c1[i][1], Y[i][k], bx);
+          dmma884(c2[i][0], c2[i][1], Y[i][k], ba);
+        }
+      }
+      // ---- scalar chain on the C fragments ----
+      const double2 sd0 = side[b * 8 + 2 * l], sd1 = side[b * 8 + 2 * l + 1];
+      double aE0 = 0.0, aE1 = 0.0;
+      if (USE_E) aE0 = aEs[b * 8 + 2 * l], aE1 = aEs[b * 8 + 2 * l + 1];
+      double w[MT][2], u[MT][2];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double xx5 = j ? sd1.x : sd0.x, xa = j ? sd1.y : sd0.y;
+          double sq = fma(c1[i][j], -10.0, yy5[i] + xx5);
+          sq = fmin(fmax(sq, 1e-300), s_max);
+          const double nrm = sqrt_pos(sq);
+          const double ex = exp2_64_prod(nrm, k64, etab);
+          const double as = c2[i][j] - xa;
+          double wv = as * ex;
+          const double uv = fma(nrm, kc1, kc0) * ex;
+          Eacc[i] = fma(as, uv, Eacc[i]);
+          if (USE_E) {  // gdml_predict.py:132-140 (scaled by 1/base like everything else; E2 is not)
+            const double aE = j ? aE1 : aE0;
+            const double nos = nrm / sig;
+            wv = fma(aE * (5.0 / sig), uv, wv);  // + aE c2 / base = aE ex (n + sig) = aE (5/sig) u
+            E2[i] = fma(aE * ex, 1.0 + nos * (1.0 + nos * (1.0 / 3.0)), E2[i]);
+          }
+          s1[i] += wv;
+          w[i][j] = wv, u[i][j] = uv;
+        }
+      // ---- GEMM 2 ----
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        double bx[NT], ba[NT];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) bx[n] = Xb[offB2[par] + 8 * n], ba[n] = Ab[offB2[par] + 8 * n];
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) dmma884(G[i][n][0], G[i][n][1], w[i][par], bx[n]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) dmma884(G[i][n][0], G[i][n][1], u[i][par], ba[n]);
+      }
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (tid == 0 && tile + 2 < n_tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars[s], kTileBytes);
+      tma_load_1d(tiles + (size_t)s * TILE, a.tiles + (size_t)(tile + 2) * TILE, kTileBytes, &bars[s]);
+    }
+  }
+  // all warps have left the main loop (the __syncthreads of the last tile): the tile buffers are free
+
+  // ---- epilogue: G = base (s1 y' - Gacc), un-permute, reduce over permutations, project, scatter ----
+  double* Gs = tiles;                // [qc][D]
+  double* Es = Gs + (size_t)qc * D;  // [qc]
+  const double base = 5.0 / (3.0 * sig * sig * sig);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    double s1q = s1[i], eq = Eacc[i], e2q = E2[i];
+    s1q += __shfl_xor_sync(0xffffffffu, s1q, 1);
+    s1q += __shfl_xor_sync(0xffffffffu, s1q, 2);
+    eq += __shfl_xor_sync(0xffffffffu, eq, 1);
+    eq += __shfl_xor_sync(0xffffffffu, eq, 2);
+    if (USE_E) {
+      e2q += __shfl_xor_sync(0xffffffffu, e2q, 1);
+      e2q += __shfl_xor_sync(0xffffffffu, e2q, 2);
+    }
+    const int ql = warp * (8 * MT) + 8 * i + g;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int e = 8 * n + 2 * l + cc;
+        if (e < D) {
+          const int d = ip[i][e];
+          const double yv = xs[fl_q[i] * D + d] - mus[e];
+          Gs[ql * D + d] = active[i] ? base * fma(s1q, yv, -G[i][n][cc]) : 0.0;
+        }
+      }
+    if (l == 0) Es[ql] = active[i] ? fma(base, eq, e2q) : 0.0;
+  }
+  __syncthreads();
+
+  for (int idx = tid; idx < nf * (D + 1); idx += nt) {
+    const int fl = idx / (D + 1), d = idx - fl * (D + 1);
+    const long long fq0 = (f_lo + fl) * P;
+    const int t_lo = (int)((fq0 > q0 ? fq0 : q0) - q0);
+    const long long fq1 = fq0 + P;
+    const int t_hi = (int)((fq1 < q_end ? fq1 : q_end) - q0);
+    double sum = 0.0;
+    if (d < D) {
+      for (int t = t_lo; t < t_hi; ++t) sum += Gs[t * D + d];
+      Gs[t_lo * D + d] = sum;
+    } else {
+      for (int t = t_lo; t < t_hi; ++t) sum += Es[t];
+      Es[t_lo] = sum;
+    }
+  }
+  __syncthreads();
+
+  for (int idx = tid; idx < nf * (NA * 3 + 1); idx += nt) {
+    const int fl = idx / (NA * 3 + 1), rem = idx - fl * (NA * 3 + 1);
+    const long long frag = f_lo + fl;
+    const long long fq0 = frag * P;
+    const int t_lo = (int)((fq0 > q0 ? fq0 : q0) - q0);
+    const double lam = a.rec_lambda[frag];
+    const double* Fd = Gs + t_lo * D;
+    const double* rf = rs + fl * NA * 3;
+    const double* xf = xs + fl * D;
+    if (rem == NA * 3) {
+      const double e = (Es[t_lo] * a.std + (fq0 >= q0 ? a.c : 0.0)) * lam;
+      double* dst = a.decomp ? a.E + ((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag])
+                             : a.E + a.rec_frame[frag];
+      atomicAdd(dst, e);
+    } else {
+      const int m = rem / 3, c = rem - m * 3;
+      double f = 0.0;
+#pragma unroll
+      for (int bb = 0; bb < NA; ++bb) {
+        if (bb == m) continue;
+        const int i = bb > m ? bb : m, j = bb > m ? m : bb;
+        const double inv = xf[i * (i - 1) / 2 + j];
+        f = fma((rf[bb * 3 + c] - rf[m * 3 + c]) * (inv * inv * inv), Fd[i * (i - 1) / 2 + j], f);
+      }
+      f *= a.std * lam;
+      double* dst =
+          a.decomp
+              ? a.F + (((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag]) * NA + m) * 3 + c
+              : a.F + ((long long)a.rec_frame[frag] * a.sys.n_atoms + a.rec_atoms[frag * NA + m]) * 3 + c;
+      atomicAdd(dst, f);
+    }
+  }
+
+  if (a.want_virial) {  // stress.virial_atom_loop on the minimum-image coordinates (gdml_predict.py:266-267)
+    for (int idx = tid; idx < nf * 9; idx += nt) {
+      const int fl = idx / 9, ij = idx - fl * 9, vi = ij / 3, vj = ij - vi * 3;
+      const long long frag = f_lo + fl;
+      const long long fq0 = frag * P;
+      const int t_lo = (int)((fq0 > q0 ? fq0 : q0) - q0);
+      const double* Fd = Gs + t_lo * D;
+      const double* rf = rs + fl * NA * 3;
+      const double* xf = xs + fl * D;
+      double wv = 0.0;
+      for (int m = 0; m < NA; ++m) {
+        double f = 0.0;
+        for (int bb = 0; bb < NA; ++bb) {
+          if (bb == m) continue;
+          const int i = bb > m ? bb : m, j = bb > m ? m : bb;
+          const double inv = xf[i * (i - 1) / 2 + j];
+          f = fma((rf[bb * 3 + vj] - rf[m * 3 + vj]) * (inv * inv * inv), Fd[i * (i - 1) / 2 + j], f);
+        }
+        wv = fma(rf[m * 3 + vi], f, wv);
+      }
+      atomicAdd(a.virial + (long long)a.rec_frame[frag] * 9 + ij, wv * a.std * a.rec_lambda[frag]);
+    }
+  }
+}
+
+}  // namespace mbg

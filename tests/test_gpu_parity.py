@@ -17,6 +17,16 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9  # north_star bar; observed errors are ~1e-13
 
 
+@pytest.fixture(autouse=True, params=["dmma", "fma"])
+def contraction(request):
+    """Every parity test runs against both contraction kernels (tensor-pipe GEMM recast and FMA-pipe
+    difference form); the C ABI selects one per context (mbg_context_set_contraction)."""
+    ctx = _native.get_context()
+    ctx.set_contraction(request.param)
+    yield request.param
+    ctx.set_contraction("auto")
+
+
 def alch(rows):
     return [mb.mbeAlchemyScale(int(e), int(o), mb.linear_switching, {"factor": float(f)}) for e, o, f in rows]
 
