@@ -204,6 +204,9 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
       case 2512: return launch_matern_mma_t<9, 2, 512, false>(ctx, a);
       case 4256: return launch_matern_mma_t<9, 4, 256, false>(ctx, a);
       case 3256: return launch_matern_mma_t<9, 3, 256, false>(ctx, a);
+      case 1512: return launch_matern_mma_t<9, 1, 512, false>(ctx, a);
+      case 1768: return launch_matern_mma_t<9, 1, 768, false>(ctx, a);
+      case 11024: return launch_matern_mma_t<9, 1, 1024, false>(ctx, a);
       default: break;
     }
   }
@@ -498,6 +501,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
       a.tiles = m->tiles_mma, a.mu = m->mu, a.iperm = m->iperm;
       a.exp2_table = ctx->exp2_table.as<double>();
       a.T_pad = m->T_pad, a.P = m->P;
+      a.n_row_blocks = (m->T + 7) / 8;
       a.sig = m->sig, a.c = m->c, a.std = m->std;
       a.n_frag = rec_pending;
       a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();

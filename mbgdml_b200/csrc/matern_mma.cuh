@@ -44,6 +44,7 @@ struct MmaShape {
 };
 
 constexpr int kMmaTileRows = 64;
+constexpr int kMmaStages = 3;  // tile buffers in flight
 __host__ __device__ constexpr int mma_row_pad(int na) {
   const int D = na * (na - 1) / 2;
   return (D <= 4) ? 4 : ((D - 4 + 7) / 8 * 8 + 4);
@@ -60,6 +61,7 @@ struct MaternMmaArgs {
   const double* exp2_table;  // [64] 2^(j/64)
   const int* iperm;          // [P][D]: pi_p^-1
   int T_pad, P;
+  int n_row_blocks;  // ceil(T / 8): blocks of 8 training rows that hold data (the rest of the last tile is padding)
   double sig, c, std;
   long long n_frag;
   const int* rec_frame;
@@ -121,16 +123,16 @@ __host__ __device__ constexpr size_t mma_smem_bytes(int nt, int P) {
   constexpr int D = MmaShape<NA>::D;
   const int qc = mma_queries_per_cta<NA, MT>(nt);
   const int maxf = (qc + P - 1) / P + 1;
-  const size_t tiles = (size_t)2 * mma_tile_doubles(NA) * 8;
+  const size_t tiles = (size_t)kMmaStages * mma_tile_doubles(NA) * 8;
   const size_t gs = (size_t)qc * (D + 1) * 8;  // epilogue staging, aliased onto the tile buffers
-  return (tiles > gs ? tiles : gs) + (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + (size_t)D * 8 + 8 + 64 * 8 + 64;
+  return (tiles > gs ? tiles : gs) + (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + (size_t)D * 8 + 8 + 64 * 8 + 2 * kMmaStages * 8 + 16;
 }
 
 template <int NA, int MT, int NTHR, bool USE_E>
 __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
   using S = MmaShape<NA>;
   constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
-  constexpr int TR = kMmaTileRows;
+  constexpr int TR = kMmaTileRows, ST = kMmaStages;
   constexpr int TILE = mma_tile_doubles(NA);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -139,8 +141,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
   const int qc = mma_queries_per_cta<NA, MT>(nt);
   const int maxf = (qc + P - 1) / P + 1;
 
-  double* tiles = reinterpret_cast<double*>(smem_raw);  // [2][TILE]; reused as Gs[qc][D], Es[qc] in the epilogue
-  const size_t tiles_bytes = (size_t)2 * TILE * 8, gs_bytes = (size_t)qc * (D + 1) * 8;
+  double* tiles = reinterpret_cast<double*>(smem_raw);  // [ST][TILE]; reused as Gs[qc][D], Es[qc] in the epilogue
+  const size_t tiles_bytes = (size_t)ST * TILE * 8, gs_bytes = (size_t)qc * (D + 1) * 8;
   double* xs = reinterpret_cast<double*>(smem_raw + (tiles_bytes > gs_bytes ? tiles_bytes : gs_bytes));  // [maxf][D]
   double* rs = xs + (size_t)maxf * D;                                                                    // [maxf][NA][3]
   double* mus = rs + (size_t)maxf * NA * 3;                                                              // [D] (+1 pad)
@@ -155,15 +157,19 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
   const int n_tiles = a.T_pad / TR;
   constexpr uint32_t kTileBytes = TILE * 8;
 
+  // bars[0..ST): "full" (TMA landed a tile in stage s); bars[ST..2ST): "empty" (every warp is done with stage s).
+  // There is no CTA-wide barrier in the main loop: warps drift apart by up to a tile, which keeps the FP64
+  // pipe fed by one warp's DMMAs while another warp sits in its latency-bound sqrt/exp chain.
+  const int n_warps = nt >> 5;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int s = 0; s < ST; ++s) mbar_init(&bars[s], 1), mbar_init(&bars[ST + s], n_warps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < ST; ++s)
       if (s < n_tiles) {
         mbar_expect_tx(&bars[s], kTileBytes);
         tma_load_1d(tiles + (size_t)s * TILE, a.tiles + (size_t)s * TILE, kTileBytes, &bars[s]);
@@ -231,20 +237,31 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
   const double kc1 = sig / 5.0, kc0 = sig * sig / 5.0;  // c2s = ex (n kc1 + kc0) = ex (n + sig) sig/5
   // clamp of s = 5|diff|^2: below, rounding may have made it <= 0; above, exp underflows anyway
   const double s_max = (60000.0 / k64) * (60000.0 / k64);
+  const int hi_max = __double2hiint(s_max);
 
   // per-thread element offsets of the B operands inside a tile
   const int offB1 = mma_tau(g) * Dp + l;                                        // GEMM 1: row tau(g), column 4k + l
   const int offB2[2] = {mma_tau(2 * l) * Dp + g, mma_tau(2 * l + 1) * Dp + g};  // GEMM 2: row tau(2l+par), column 8n + g
 
   for (int tile = 0; tile < n_tiles; ++tile) {
-    const int s = tile & 1;
-    mbar_wait(&bars[s], (tile >> 1) & 1);
+    const int s = tile % ST;
+    if (tid == 0 && tile >= 2 && tile + ST - 2 < n_tiles) {
+      // refill the stage of tile-2 (every warp has left it, or will within the wait) with tile+ST-2
+      const int u = tile - 2, su = u % ST;
+      mbar_wait(&bars[ST + su], (u / ST) & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars[su], kTileBytes);
+      tma_load_1d(tiles + (size_t)su * TILE, a.tiles + (size_t)(u + ST) * TILE, kTileBytes, &bars[su]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[s], (tile / ST) & 1);
+    const int nb = min(TR / 8, a.n_row_blocks - tile * (TR / 8));
     const double* Xs = tiles + (size_t)s * TILE;
     const double* As = Xs + TR * Dp;
     const double2* side = reinterpret_cast<const double2*>(As + TR * Dp);  // [TR] (xx5, xa) in column order
     const double* aEs = reinterpret_cast<const double*>(side + TR);        // [TR] alphas_E in column order
 #pragma unroll 1
-    for (int b = 0; b < TR / 8; ++b) {
+    for (int b = 0; b < nb; ++b) {
       const double* Xb = Xs + b * 8 * Dp;
       const double* Ab = As + b * 8 * Dp;
       // ---- GEMM 1 ----
@@ -265,28 +282,89 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
       double aE0 = 0.0, aE1 = 0.0;
       if (USE_E) aE0 = aEs[b * 8 + 2 * l], aE1 = aEs[b * 8 + 2 * l + 1];
       double w[MT][2], u[MT][2];
+      {
+        // The NC = 2 MT chains of this thread advance in lock step: every arithmetic step is written for
+        // all chains before the next one, in program-ordered (volatile) instructions, so that dependent
+        // FP64 operations are NC instructions apart instead of back to back.
+        constexpr int NC = 2 * MT;
+        double sq[NC], as[NC], g_[NC], h_[NC], r_[NC], t_[NC];
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
+        for (int c = 0; c < NC; ++c) sq[c] = vadd(yy5[c >> 1], (c & 1) ? sd1.x : sd0.x);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const double xx5 = j ? sd1.x : sd0.x, xa = j ? sd1.y : sd0.y;
-          double sq = fma(c1[i][j], -10.0, yy5[i] + xx5);
-          sq = fmin(fmax(sq, 1e-300), s_max);
-          const double nrm = sqrt_pos(sq);
-          const double ex = exp2_64_prod(nrm, k64, etab);
-          const double as = c2[i][j] - xa;
-          double wv = as * ex;
-          const double uv = fma(nrm, kc1, kc0) * ex;
-          Eacc[i] = fma(as, uv, Eacc[i]);
-          if (USE_E) {  // gdml_predict.py:132-140 (scaled by 1/base like everything else; E2 is not)
-            const double aE = j ? aE1 : aE0;
-            const double nos = nrm / sig;
-            wv = fma(aE * (5.0 / sig), uv, wv);  // + aE c2 / base = aE ex (n + sig) = aE (5/sig) u
-            E2[i] = fma(aE * ex, 1.0 + nos * (1.0 + nos * (1.0 / 3.0)), E2[i]);
-          }
-          s1[i] += wv;
-          w[i][j] = wv, u[i][j] = uv;
+        for (int c = 0; c < NC; ++c) sq[c] = vfma(c1[c >> 1][c & 1], -10.0, sq[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {  // clamp to [1e-300, s_max] on the integer pipe (high word)
+          const int hi = min(max(__double2hiint(sq[c]), 0x01A56E1F), hi_max);
+          sq[c] = __hiloint2double(hi, __double2loint(sq[c]));
         }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(t_[c]) : "d"(sq[c]));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) as[c] = vadd(c2[c >> 1][c & 1], (c & 1) ? -sd1.y : -sd0.y);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) g_[c] = vmul(sq[c], t_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vmul(t_[c], 0.5);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], h_[c], 0.5);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) g_[c] = vfma(g_[c], r_[c], g_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], h_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], g_[c], sq[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) g_[c] = vfma(r_[c], h_[c], g_[c]);  // g_ = nrm = sqrt(5)|diff|
+        // ex = 2^(nrm k64 / 64)
+        const double kMagic = 6755399441055744.0;
+        int kk[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) t_[c] = vfma(g_[c], k64, kMagic);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kk[c] = __double2loint(t_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) t_[c] = vadd(t_[c], -kMagic);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) r_[c] = vfma(g_[c], k64, -t_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], 1.2417843701716925e-12, 5.732851688640402e-10);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) t_[c] = etab[kk[c] & 63];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 2.1173137155464776e-07);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) sq[c] = vfma(g_[c], kc1, kc0);  // (n + sig) sig/5
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 5.86490495505617e-05);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 0.010830424696249145);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vmul(h_[c], r_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h_[c] = vfma(t_[c], h_[c], t_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)  // scale by 2^(k >> 6); the clamp of sq keeps the result normal
+          h_[c] = __hiloint2double(__double2hiint(h_[c]) + ((kk[c] >> 6) << 20), __double2loint(h_[c]));  // ex
+#pragma unroll
+        for (int c = 0; c < NC; ++c) r_[c] = vmul(as[c], h_[c]);  // w
+#pragma unroll
+        for (int c = 0; c < NC; ++c) sq[c] = vmul(sq[c], h_[c]);  // u = c2s
+        if (USE_E) {  // gdml_predict.py:132-140 (scaled by 1/base like everything else; E2 is not)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const double aE = (c & 1) ? aE1 : aE0;
+            const double nos = g_[c] / sig;
+            r_[c] = fma(aE * (5.0 / sig), sq[c], r_[c]);  // + aE c2 / base = aE ex (n + sig) = aE (5/sig) u
+            E2[c >> 1] = fma(aE * h_[c], 1.0 + nos * (1.0 + nos * (1.0 / 3.0)), E2[c >> 1]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Eacc[c >> 1] = vfma(as[c], sq[c], Eacc[c >> 1]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s1[c >> 1] = vadd(s1[c >> 1], r_[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) w[c >> 1][c & 1] = r_[c], u[c >> 1][c & 1] = sq[c];
+      }
       // ---- GEMM 2 ----
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
@@ -303,14 +381,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
           for (int i = 0; i < MT; ++i) dmma884(G[i][n][0], G[i][n][1], u[i][par], ba[n]);
       }
     }
-    __syncthreads();  // every thread is done with stage s
-    if (tid == 0 && tile + 2 < n_tiles) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&bars[s], kTileBytes);
-      tma_load_1d(tiles + (size_t)s * TILE, a.tiles + (size_t)(tile + 2) * TILE, kTileBytes, &bars[s]);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[ST + s]);  // this warp is done with stage s
   }
-  // all warps have left the main loop (the __syncthreads of the last tile): the tile buffers are free
+  __syncthreads();  // all warps have left the main loop: the tile buffers are free (no TMA is in flight)
 
   // ---- epilogue: G = base (s1 y' - Gacc), un-permute, reduce over permutations, project, scatter ----
   double* Gs = tiles;                // [qc][D]
