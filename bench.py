@@ -183,7 +183,22 @@ def cpu_reference_pass(w, n_candidates, pool, cores):
 
 
 def cpu_sample_size(w):
-    return {"box140": 24000, "trimers64": 640, "monomers": 60000}[w["name"]]
+    """Candidate tuples per CPU sample: ~10-20 s of work on 16 host cores (the GPU does all of them)."""
+    return {"box140": 200000, "trimers64": 6000, "monomers": 100000}[w["name"]]
+
+
+def ncu_traffic(workload, n_frag_atoms, frames, use_dmma):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum from the
+    committed `ncu --set full` capture of the same command, profiles/ncu_traffic.json), else None."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+    for row in table:
+        if (row["workload"] == workload and row["n_frag_atoms"] == n_frag_atoms and row["frames"] == frames
+                and row["contraction"] == ("dmma" if use_dmma else "fma")):
+            return row["dram_bytes_per_launch"]
+    return None
 
 
 def run_reference_arm(args):
@@ -304,7 +319,12 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), last
 
-    peak_tflops, clk_est = ctx.measure_fp64_peak() if rank == 0 else (0.0, 0.0)
+    ctx.set_contraction(args.contraction)
+    use_dmma = args.contraction != "fma"
+    peak_fma, clk_est = ctx.measure_fp64_peak() if rank == 0 else (0.0, 0.0)
+    peak_dmma = ctx.measure_fp64_tensor_peak() if rank == 0 else 0.0
+    # the roofline of a kernel is the peak of the pipe it runs on
+    peak_tflops = peak_dmma if use_dmma else peak_fma
 
     for _ in range(max(args.warmup, 3)):
         st = step_device()
@@ -347,14 +367,21 @@ def run_gpu_arm(args):
         flop = sum(r["n_fragments"] * wfrag[r["n_frag_atoms"]] for r in dom)
         ms = sum(r["ms"] for r in dom)
         achieved = flop / (ms * 1e-3) / 1e12
+        kname = f"k_matern_mma<NA={best['n_frag_atoms']}>" if use_dmma else f"k_matern<NA={best['n_frag_atoms']}>"
         roofline = {
-            "bound": "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-            "frac": achieved / peak_tflops if peak_tflops else None, "traffic": None,
-            "kernel": f"k_matern<NA={best['n_frag_atoms']}>", "launches_in_step": len(dom),
+            "bound": "tensor" if use_dmma else "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved / peak_tflops if peak_tflops else None,
+            "traffic": ncu_traffic(args.workload, best["n_frag_atoms"], args.frames, use_dmma),
+            "kernel": kname, "launches_in_step": len(dom),
             "avg_launch_ms": ms / len(dom), "alg_flop_per_fragment": wfrag[best["n_frag_atoms"]],
             "fragments_per_launch": sum(r["n_fragments"] for r in dom) / len(dom),
-            "peak_source": "measured live: DFMA microbenchmark (mbg_measure_fp64_peak); MEASURED_PEAKS.json "
-                           "has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2 TFLOP/s",
+            "pipe": ("FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA.8x8x4)" if use_dmma else "FP64 FMA pipe (DFMA)"),
+            "peak_source": "measured live on this GPU, CUDA events: back-to-back DMMA m8n8k4 on 8 independent accumulators "
+                           "(mbg_measure_fp64_tensor_peak) for the tensor pipe, 8 independent DFMA chains "
+                           "(mbg_measure_fp64_peak) for the FMA pipe; MEASURED_PEAKS.json has no FP64 entry; "
+                           "nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2 TFLOP/s for either",
+            "peak_fp64_fma_tflops": peak_fma, "peak_fp64_tensor_tflops": peak_dmma,
+            "frac_of_fma_pipe_peak": achieved / peak_fma if peak_fma else None,
             "contract_share_of_step": sum(r["ms"] for r in recs) / (ms_dev / args.steps),
         }
         try:
@@ -393,7 +420,8 @@ def run_gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(R_host.nbytes), "d2h_bytes_per_step": int(8 * n_frames * (1 + 3 * n_atoms))},
         "gpu_launches": int(nl.item()), "clocks": clocks,
-        "fp64_peak_tflops_measured": peak_tflops, "sm_clock_mhz_implied_by_peak": clk_est,
+        "fp64_peak_tflops_measured": {"fma_pipe": peak_fma, "tensor_pipe": peak_dmma},
+        "sm_clock_mhz_implied_by_fma_peak": clk_est, "contraction": "dmma" if use_dmma else "fma",
     }
     print(json.dumps(line))
     if world > 1:
@@ -410,6 +438,8 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--n-train", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contraction", default="auto", choices=["auto", "fma", "dmma"],
+                    help="contraction kernel: FP64 tensor pipe (dmma, default) or FMA pipe (fma)")
     args = ap.parse_args()
     if args.frames is None:
         args.frames = {"box140": 8, "trimers64": 4, "monomers": 1}[args.workload]

@@ -182,6 +182,9 @@ int mbg_r_mic(mbg_context_t ctx, const double *cell, double cutoff, const double
 /* Measured FP64 FMA-pipe peak of this GPU (dependent-chain-free DFMA loop, CUDA-event timed),
  * in TFLOP/s: the roofline denominator bench.py reports against. */
 int mbg_measure_fp64_peak(mbg_context_t ctx, double *tflops, double *sm_clock_mhz_est);
+/* Measured peak of the FP64 tensor pipe (back-to-back mma.sync.m8n8k4.f64 on independent accumulators),
+ * in TFLOP/s: the roofline denominator for the MBG_CONTRACT_DMMA kernel. */
+int mbg_measure_fp64_tensor_peak(mbg_context_t ctx, double *tflops);
 
 #ifdef __cplusplus
 }

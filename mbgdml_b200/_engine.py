@@ -24,10 +24,14 @@ class System:
         self.n_atoms = int(Z.shape[0])
         self.n_entities = int(entity_ids.max()) + 1 if entity_ids.size else 0
         # np.where(entity_ids == e)[0] for every e: a stable sort keeps atoms ascending within an entity
-        self.entity_atoms = _native.as_i32(np.argsort(entity_ids, kind="stable"))
-        counts = np.bincount(entity_ids.astype(np.int64), minlength=self.n_entities)
+        # (already-sorted ids, the usual case, need no sort)
+        if entity_ids.size and np.all(entity_ids[1:] >= entity_ids[:-1]):
+            self.entity_atoms = np.arange(self.n_atoms, dtype=np.int32)
+        else:
+            self.entity_atoms = _native.as_i32(np.argsort(entity_ids, kind="stable"))
+        counts = np.bincount(entity_ids, minlength=self.n_entities)
         self.entity_offsets = np.zeros(self.n_entities + 1, dtype=np.int32)
-        self.entity_offsets[1:] = np.cumsum(counts)
+        np.cumsum(counts, out=self.entity_offsets[1:])
         self.masses = _native.as_f64(masses_of(Z, strict=need_masses))
         self.cell = None
         cutoff = 0.0

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_enumerate",
-    "mbg_criteria_eval", "mbg_r_mic", "mbg_measure_fp64_peak",
+    "mbg_criteria_eval", "mbg_r_mic", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -106,6 +106,7 @@ def load_library():
         lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
         lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
         lib.mbg_measure_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+        lib.mbg_measure_fp64_tensor_peak.argtypes = [C.c_void_p, _dp]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(lib, name)
             if name != "mbg_last_error":
@@ -209,6 +210,11 @@ class Context:
         t, f = C.c_double(0), C.c_double(0)
         check(self.lib.mbg_measure_fp64_peak(self.handle, C.byref(t), C.byref(f)))
         return t.value, f.value
+
+    def measure_fp64_tensor_peak(self):
+        t = C.c_double(0)
+        check(self.lib.mbg_measure_fp64_tensor_peak(self.handle, C.byref(t)))
+        return t.value
 
     # -- models ---------------------------------------------------------------------
     def model_handle(self, key, build_desc):

@@ -173,21 +173,22 @@ static int launch_matern_t(mbg_context_t ctx, const MaternArgs& a) {
   return MBG_OK;
 }
 
-template <int NA, int MT, int NTHR, bool USE_E>
+template <int NA, int MT, int NTHR, int MINB, bool USE_E>
 static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a) {
   int dev_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   const int nt = NTHR;
   const size_t smem = mma_smem_bytes<NA, MT>(nt, a.P);
   if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
-  CUDA_TRY(cudaFuncSetAttribute(k_matern_mma<NA, MT, NTHR, USE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = k_matern_mma<NA, MT, NTHR, MINB, USE_E>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nq = a.n_frag * a.P;
   const int qc = mma_queries_per_cta<NA, MT>(nt);
   const long long grid = (nq + qc - 1) / qc;
   if (grid > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "too many fragments in one launch");
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
-  k_matern_mma<NA, MT, NTHR, USE_E><<<(unsigned)grid, nt, smem, ctx->stream>>>(a);
+  kern<<<(unsigned)grid, nt, smem, ctx->stream>>>(a);
   cudaEventRecord(e1, ctx->stream);
   ctx->launches++;
   ctx->n_contract++;
@@ -197,24 +198,25 @@ static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a) {
 }
 
 static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const MaternMmaArgs& a) {
-#ifdef MBG_TUNING_VARIANTS  // developer build: extra (MT, threads) shapes of the trimer kernel, chosen by MBG_MMA_CFG
+#ifdef MBG_TUNING_VARIANTS  // developer build: extra shapes of the trimer kernel, MBG_MMA_CFG = MT*10000 + threads*10 + CTAs/SM
   if (na == 9 && !use_E) {
     switch (ctx->mma_cfg) {
-      case 2384: return launch_matern_mma_t<9, 2, 384, false>(ctx, a);
-      case 2512: return launch_matern_mma_t<9, 2, 512, false>(ctx, a);
-      case 4256: return launch_matern_mma_t<9, 4, 256, false>(ctx, a);
-      case 3256: return launch_matern_mma_t<9, 3, 256, false>(ctx, a);
-      case 1512: return launch_matern_mma_t<9, 1, 512, false>(ctx, a);
-      case 1768: return launch_matern_mma_t<9, 1, 768, false>(ctx, a);
-      case 11024: return launch_matern_mma_t<9, 1, 1024, false>(ctx, a);
+#define V(MT, NT, MB) case MT * 10000 + NT * 10 + MB: return launch_matern_mma_t<9, MT, NT, MB, false>(ctx, a);
+      V(2, 384, 1) V(2, 512, 1) V(4, 256, 1) V(3, 256, 1) V(2, 256, 1)
+      V(3, 128, 2) V(2, 128, 3) V(4, 128, 2) V(2, 128, 2) V(2, 192, 2) V(1, 256, 2) V(1, 128, 4) V(1, 128, 5)
+#undef V
       default: break;
     }
   }
 #endif
+  // Shape per fragment size (measured on B200, profiles/r1_dmma_tuning.md): 8 warps per SM, as many m-tiles
+  // per warp as the register file allows without spilling (3 for D = 28, 36; 4 below).
   switch (na) {
-#define X(N) \
-  case N:    \
-    return use_E ? launch_matern_mma_t<N, 2, 256, true>(ctx, a) : launch_matern_mma_t<N, 2, 256, false>(ctx, a);
+#define X(N)                                                                                        \
+  case N: {                                                                                         \
+    constexpr int MT = (N >= 8) ? 3 : 4;                                                            \
+    return use_E ? launch_matern_mma_t<N, MT, 256, 1, true>(ctx, a) : launch_matern_mma_t<N, MT, 256, 1, false>(ctx, a); \
+  }
     MBG_FOR_EACH_NA(X)
 #undef X
     default:
@@ -267,6 +269,22 @@ __global__ void k_dfma_peak(double* out, int iters, double seed) {
   double s = 0;
 #pragma unroll
   for (int k = 0; k < CHAINS; ++k) s += acc[k];
+  if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
+}
+
+template <int CHAINS>
+__global__ void k_dmma_peak(double* out, int iters, double seed) {
+  double c0[CHAINS], c1[CHAINS];
+#pragma unroll
+  for (int k = 0; k < CHAINS; ++k) c0[k] = seed + k, c1[k] = seed - k;
+  const double av = 1.0 + threadIdx.x * 1e-6, bv = 1.0 - threadIdx.x * 1e-6;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) dmma884_v(c0[k], c1[k], av, bv);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < CHAINS; ++k) s += c0[k] + c1[k];
   if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
 }
 
@@ -790,7 +808,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   {
     // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row 5|X'|^2 and X'.A_s,
     // packed per tile of 64 rows; side arrays in column order (column j of a block <-> row tau(j)).
-    static_assert(kMmaTileRows == kTileRows, "both kernels pad T to the same tile size");
+    static_assert(kTileRows % kMmaTileRows == 0, "T_pad (multiple of kTileRows) must be whole DMMA tiles");
     const int Dq = mma_row_pad(d->n_atoms), TILE = mma_tile_doubles(d->n_atoms), TRm = kMmaTileRows;
     std::vector<double> mu(D, 0.0);
     for (int e = 0; e < D; ++e) {
@@ -1135,6 +1153,34 @@ int mbg_measure_fp64_peak(mbg_context_t ctx, double* tflops, double* sm_clock_mh
   *tflops = best;
   // 64 FP64 FMA lanes per SM per clock on sm_100
   if (sm_clock_mhz_est) *sm_clock_mhz_est = best * 1e12 / (2.0 * 64 * ctx->sm_count) / 1e6;
+  return MBG_OK;
+}
+
+int mbg_measure_fp64_tensor_peak(mbg_context_t ctx, double* tflops) {
+  if (!ctx || !tflops) return fail(MBG_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(ctx->totals.ensure(2 * sizeof(long long)));
+  constexpr int kChains = 8;
+  const int threads = 256, blocks = ctx->sm_count * 2, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    k_dmma_peak<kChains><<<blocks, threads, 0, ctx->stream>>>(ctx->totals.as<double>(), iters, 1.0 + rep);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    // one m8n8k4 DMMA = 8 x 8 x 4 multiply-adds per warp
+    const double flop = 2.0 * 256 * kChains * (double)iters * (threads / 32) * blocks;
+    if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
   return MBG_OK;
 }
 

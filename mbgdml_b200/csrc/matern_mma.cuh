@@ -43,7 +43,7 @@ struct MmaShape {
   static_assert(Dp >= 4 * KS && Dp % 8 == 4, "row padding");
 };
 
-constexpr int kMmaTileRows = 64;
+constexpr int kMmaTileRows = 32;
 constexpr int kMmaStages = 3;  // tile buffers in flight
 __host__ __device__ constexpr int mma_row_pad(int na) {
   const int D = na * (na - 1) / 2;
@@ -80,6 +80,28 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(d0), "+d"(d1)
       : "d"(a), "d"(b));
+}
+
+// Program-ordered (volatile) variants: the compiler keeps volatile asm statements in source order.
+__device__ __forceinline__ void dmma884_v(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void dmma884_zv(double& d0, double& d1, double a, double b) {  // C = 0
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(0.0));
+}
+__device__ __forceinline__ double lds64v(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds128v(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
 }
 
 // sqrt(x) for x > 0 (caller clamps): rsqrt seed + Goldschmidt + one residual correction (~1 ulp).
@@ -125,14 +147,14 @@ __host__ __device__ constexpr size_t mma_smem_bytes(int nt, int P) {
   const int maxf = (qc + P - 1) / P + 1;
   const size_t tiles = (size_t)kMmaStages * mma_tile_doubles(NA) * 8;
   const size_t gs = (size_t)qc * (D + 1) * 8;  // epilogue staging, aliased onto the tile buffers
-  return (tiles > gs ? tiles : gs) + (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + (size_t)D * 8 + 8 + 64 * 8 + 2 * kMmaStages * 8 + 16;
+  return (tiles > gs ? tiles : gs) + (size_t)maxf * D * 8 + (size_t)maxf * NA * 3 * 8 + (size_t)D * 8 + 8 + 64 * 8 + 2 * kMmaStages * 8 + (size_t)maxf * 4 + 16;
 }
 
-template <int NA, int MT, int NTHR, bool USE_E>
-__global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
+template <int NA, int MT, int NTHR, int MINB, bool USE_E>
+__global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a) {
   using S = MmaShape<NA>;
   constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
-  constexpr int TR = kMmaTileRows, ST = kMmaStages;
+  constexpr int TR = kMmaTileRows, ST = kMmaStages, BPT = TR / 8;  // BPT: row blocks per tile
   constexpr int TILE = mma_tile_doubles(NA);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -178,25 +200,52 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
   if (tid < 64) etab[tid] = a.exp2_table[tid];
   if (tid < D) mus[tid] = a.mu[tid];
 
-  // ---- prologue: geometry + descriptor of this CTA's fragments (desc.py:79-158) ----
-  for (int fl = tid; fl < nf; fl += nt) {
+  // ---- prologue: geometry + descriptor of this CTA's fragments (periodic.py:61-107, desc.py:79-158) ----
+  // One thread per (fragment, atom), then one per (fragment, atom pair): a single thread per fragment would
+  // spend ~15 us in 36 dependent IEEE sqrt/div sequences while the FP64 pipe of the SM idles.
+  // Same arithmetic as fragment_coords<NA> (geom.cuh), which the culling kernel used to accept the fragment.
+  int* bad = reinterpret_cast<int*>(bars + 2 * ST);  // [maxf] naive minimum image not valid for the fragment
+  for (int fl = tid; fl < nf; fl += nt) bad[fl] = 0;
+  __syncthreads();
+  for (int idx = tid; idx < nf * NA; idx += nt) {
+    const int fl = idx / NA, k = idx - fl * NA;
     const long long frag = f_lo + fl;
-    const int* atoms = a.rec_atoms + frag * NA;
     const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
-    double r[NA][3];
-    int at[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k) at[k] = atoms[k];
-    fragment_coords<NA>(a.sys, Rf, at, r);
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-      rs[(fl * NA + i) * 3 + 0] = r[i][0], rs[(fl * NA + i) * 3 + 1] = r[i][1], rs[(fl * NA + i) * 3 + 2] = r[i][2];
-#pragma unroll
-      for (int j = 0; j < i; ++j, ++k)
-        xs[fl * D + k] = __ddiv_rn(1.0, norm3_rn(__dsub_rn(r[i][0], r[j][0]), __dsub_rn(r[i][1], r[j][1]),
-                                                  __dsub_rn(r[i][2], r[j][2])));
+    const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
+    double v[3] = {p[0], p[1], p[2]};
+    if (a.sys.periodic) {
+      const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
+      const double d[3] = {__dsub_rn(v[0], p0[0]), __dsub_rn(v[1], p0[1]), __dsub_rn(v[2], p0[2])};
+      if (!(mic_naive(a.sys, d, v) < a.sys.half_min_len)) bad[fl] = 1;
     }
+    rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
+  }
+  __syncthreads();
+  if (a.sys.periodic) {  // find_mic falls back to the general algorithm for the whole fragment
+    for (int idx = tid; idx < nf * NA; idx += nt) {
+      const int fl = idx / NA, k = idx - fl * NA;
+      if (!bad[fl]) continue;
+      const long long frag = f_lo + fl;
+      const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
+      const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
+      const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
+      const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
+      double v[3];
+      mic_general(a.sys, d, v);
+      rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < nf * D; idx += nt) {  // x_k = 1 / |r_i - r_j|, np.tril_indices(n, -1) order
+    const int fl = idx / D, k = idx - fl * D;
+    int i = 1;
+#pragma unroll
+    for (int ii = 1; ii < NA; ++ii)
+      if (k >= ii * (ii + 1) / 2) i = ii + 1;
+    const int j = k - i * (i - 1) / 2;
+    const double* ri = rs + (fl * NA + i) * 3;
+    const double* rj = rs + (fl * NA + j) * 3;
+    xs[idx] = __ddiv_rn(1.0, norm3_rn(__dsub_rn(ri[0], rj[0]), __dsub_rn(ri[1], rj[1]), __dsub_rn(ri[2], rj[2])));
   }
   __syncthreads();
 
@@ -243,146 +292,193 @@ __global__ void __launch_bounds__(NTHR, 1) k_matern_mma(const MaternMmaArgs a) {
   const int offB1 = mma_tau(g) * Dp + l;                                        // GEMM 1: row tau(g), column 4k + l
   const int offB2[2] = {mma_tau(2 * l) * Dp + g, mma_tau(2 * l + 1) * Dp + g};  // GEMM 2: row tau(2l+par), column 8n + g
 
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int s = tile % ST;
-    if (tid == 0 && tile >= 2 && tile + ST - 2 < n_tiles) {
-      // refill the stage of tile-2 (every warp has left it, or will within the wait) with tile+ST-2
-      const int u = tile - 2, su = u % ST;
-      mbar_wait(&bars[ST + su], (u / ST) & 1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&bars[su], kTileBytes);
-      tma_load_1d(tiles + (size_t)su * TILE, a.tiles + (size_t)(u + ST) * TILE, kTileBytes, &bars[su]);
+  // ---- main loop: flat over the blocks of 8 training rows, software pipelined -------------------------
+  // Iteration gb runs the scalar chains of block gb with the k-steps of GEMM 1 of block gb+1 slotted between
+  // the chain steps (so dependent FP64 instructions are separated by independent DMMAs and the pipe never
+  // waits on this warp's own latencies), then GEMM 2 of block gb.  Everything in the loop body is
+  // program-ordered (volatile) on purpose.
+  const uint32_t tiles_s = smem_u32(tiles);
+  const int NB = a.n_row_blocks;
+  constexpr uint32_t kPlane = TR * Dp * 8;  // bytes from a row of the X' plane to the same row of the A_s plane
+  auto block_base = [&](int gb) -> uint32_t {  // shared address of row 0 of block gb in the X' plane
+    return tiles_s + (uint32_t)(((gb / BPT) % ST) * TILE + (gb % BPT) * 8 * Dp) * 8u;
+  };
+  double c1[MT][2], c2[MT][2];
+  double bxr[2], bar[2];
+  mbar_wait(&bars[0], 0);
+  {  // GEMM 1 of block 0
+    const uint32_t x0 = block_base(0) + offB1 * 8;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const double bx = lds64v(x0 + k * 32), ba = lds64v(x0 + kPlane + k * 32);
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        if (k == 0) {
+          dmma884_zv(c1[i][0], c1[i][1], Y[i][0], bx);
+          dmma884_zv(c2[i][0], c2[i][1], Y[i][0], ba);
+        } else {
+          dmma884_v(c1[i][0], c1[i][1], Y[i][k], bx);
+          dmma884_v(c2[i][0], c2[i][1], Y[i][k], ba);
+        }
+      }
     }
-    __syncwarp();
-    mbar_wait(&bars[s], (tile / ST) & 1);
-    const int nb = min(TR / 8, a.n_row_blocks - tile * (TR / 8));
-    const double* Xs = tiles + (size_t)s * TILE;
-    const double* As = Xs + TR * Dp;
-    const double2* side = reinterpret_cast<const double2*>(As + TR * Dp);  // [TR] (xx5, xa) in column order
-    const double* aEs = reinterpret_cast<const double*>(side + TR);        // [TR] alphas_E in column order
+  }
 #pragma unroll 1
-    for (int b = 0; b < nb; ++b) {
-      const double* Xb = Xs + b * 8 * Dp;
-      const double* Ab = As + b * 8 * Dp;
-      // ---- GEMM 1 ----
-      double c1[MT][2], c2[MT][2];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) c1[i][0] = c1[i][1] = c2[i][0] = c2[i][1] = 0.0;
-#pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const double bx = Xb[offB1 + 4 * k], ba = Ab[offB1 + 4 * k];
+  for (int gb = 0; gb < NB; ++gb) {
+    const int s = (gb / BPT) % ST, b = gb % BPT;
+    const int gn = (gb + 1 < NB) ? gb + 1 : gb;  // last block: GEMM 1 is recomputed on itself, unused
+    if (gn % BPT == 0 && gn != gb) {             // GEMM 1 of the next block enters a new tile
+      const int tn = gn / BPT;
+      if (tid == 0 && tn >= 2 && tn - 2 + ST < n_tiles) {
+        // refill the stage of tile tn-2 (every warp has left it, or will within the wait) with tile tn-2+ST
+        const int u = tn - 2, su = u % ST;
+        mbar_wait(&bars[ST + su], (u / ST) & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[su], kTileBytes);
+        tma_load_1d(tiles + (size_t)su * TILE, a.tiles + (size_t)(u + ST) * TILE, kTileBytes, &bars[su]);
+      }
+      __syncwarp();
+      mbar_wait(&bars[tn % ST], (tn / ST) & 1);
+    }
+    const uint32_t xcur = block_base(gb);
+    const uint32_t xnxt = block_base(gn) + offB1 * 8;
+    const uint32_t side_s = tiles_s + (uint32_t)(s * TILE + 2 * TR * Dp) * 8u + (uint32_t)(b * 8 + 2 * l) * 16u;
+    const double2 sd0 = lds128v(side_s), sd1 = lds128v(side_s + 16);
+    double aE0 = 0.0, aE1 = 0.0;
+    if (USE_E) {
+      const double* aEs = tiles + (size_t)s * TILE + 2 * TR * Dp + 2 * TR;
+      aE0 = aEs[b * 8 + 2 * l], aE1 = aEs[b * 8 + 2 * l + 1];
+    }
+    bxr[0] = lds64v(xnxt), bar[0] = lds64v(xnxt + kPlane);
+    // k-step k of GEMM 1 of the next block (operands of step k+1 are fetched first)
+    auto G1 = [&](const int k) {
+      if (k < KS) {
+        if (k + 1 < KS) bxr[(k + 1) & 1] = lds64v(xnxt + (k + 1) * 32), bar[(k + 1) & 1] = lds64v(xnxt + kPlane + (k + 1) * 32);
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-          dmma884(c1[i][0], c1[i][1], Y[i][k], bx);
-          dmma884(c2[i][0], c2[i][1], Y[i][k], ba);
-        }
-      }
-      // ---- scalar chain on the C fragments ----
-      const double2 sd0 = side[b * 8 + 2 * l], sd1 = side[b * 8 + 2 * l + 1];
-      double aE0 = 0.0, aE1 = 0.0;
-      if (USE_E) aE0 = aEs[b * 8 + 2 * l], aE1 = aEs[b * 8 + 2 * l + 1];
-      double w[MT][2], u[MT][2];
-      {
-        // The NC = 2 MT chains of this thread advance in lock step: every arithmetic step is written for
-        // all chains before the next one, in program-ordered (volatile) instructions, so that dependent
-        // FP64 operations are NC instructions apart instead of back to back.
-        constexpr int NC = 2 * MT;
-        double sq[NC], as[NC], g_[NC], h_[NC], r_[NC], t_[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) sq[c] = vadd(yy5[c >> 1], (c & 1) ? sd1.x : sd0.x);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) sq[c] = vfma(c1[c >> 1][c & 1], -10.0, sq[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {  // clamp to [1e-300, s_max] on the integer pipe (high word)
-          const int hi = min(max(__double2hiint(sq[c]), 0x01A56E1F), hi_max);
-          sq[c] = __hiloint2double(hi, __double2loint(sq[c]));
-        }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(t_[c]) : "d"(sq[c]));
-#pragma unroll
-        for (int c = 0; c < NC; ++c) as[c] = vadd(c2[c >> 1][c & 1], (c & 1) ? -sd1.y : -sd0.y);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) g_[c] = vmul(sq[c], t_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vmul(t_[c], 0.5);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], h_[c], 0.5);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) g_[c] = vfma(g_[c], r_[c], g_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], h_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], g_[c], sq[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) g_[c] = vfma(r_[c], h_[c], g_[c]);  // g_ = nrm = sqrt(5)|diff|
-        // ex = 2^(nrm k64 / 64)
-        const double kMagic = 6755399441055744.0;
-        int kk[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) t_[c] = vfma(g_[c], k64, kMagic);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) kk[c] = __double2loint(t_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) t_[c] = vadd(t_[c], -kMagic);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) r_[c] = vfma(g_[c], k64, -t_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], 1.2417843701716925e-12, 5.732851688640402e-10);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) t_[c] = etab[kk[c] & 63];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 2.1173137155464776e-07);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) sq[c] = vfma(g_[c], kc1, kc0);  // (n + sig) sig/5
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 5.86490495505617e-05);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 0.010830424696249145);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vmul(h_[c], r_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) h_[c] = vfma(t_[c], h_[c], t_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c)  // scale by 2^(k >> 6); the clamp of sq keeps the result normal
-          h_[c] = __hiloint2double(__double2hiint(h_[c]) + ((kk[c] >> 6) << 20), __double2loint(h_[c]));  // ex
-#pragma unroll
-        for (int c = 0; c < NC; ++c) r_[c] = vmul(as[c], h_[c]);  // w
-#pragma unroll
-        for (int c = 0; c < NC; ++c) sq[c] = vmul(sq[c], h_[c]);  // u = c2s
-        if (USE_E) {  // gdml_predict.py:132-140 (scaled by 1/base like everything else; E2 is not)
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const double aE = (c & 1) ? aE1 : aE0;
-            const double nos = g_[c] / sig;
-            r_[c] = fma(aE * (5.0 / sig), sq[c], r_[c]);  // + aE c2 / base = aE ex (n + sig) = aE (5/sig) u
-            E2[c >> 1] = fma(aE * h_[c], 1.0 + nos * (1.0 + nos * (1.0 / 3.0)), E2[c >> 1]);
+          if (k == 0) {
+            dmma884_zv(c1[i][0], c1[i][1], Y[i][0], bxr[0]);
+            dmma884_zv(c2[i][0], c2[i][1], Y[i][0], bar[0]);
+          } else {
+            dmma884_v(c1[i][0], c1[i][1], Y[i][k < KS ? k : 0], bxr[k & 1]);
+            dmma884_v(c2[i][0], c2[i][1], Y[i][k < KS ? k : 0], bar[k & 1]);
           }
         }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) Eacc[c >> 1] = vfma(as[c], sq[c], Eacc[c >> 1]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) s1[c >> 1] = vadd(s1[c >> 1], r_[c]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) w[c >> 1][c & 1] = r_[c], u[c >> 1][c & 1] = sq[c];
       }
-      // ---- GEMM 2 ----
+    };
+    double w[MT][2], u[MT][2];
+    constexpr int NC = 2 * MT;  // chains of this thread, advanced in lock step
+    double sq[NC], as[NC], g_[NC], h_[NC], r_[NC], t_[NC];
+    int kk[NC];
+    const double kMagic = 6755399441055744.0;
 #pragma unroll
-      for (int par = 0; par < 2; ++par) {
-        double bx[NT], ba[NT];
+    for (int c = 0; c < NC; ++c) sq[c] = vadd(yy5[c >> 1], (c & 1) ? sd1.x : sd0.x);
 #pragma unroll
-        for (int n = 0; n < NT; ++n) bx[n] = Xb[offB2[par] + 8 * n], ba[n] = Ab[offB2[par] + 8 * n];
+    for (int c = 0; c < NC; ++c) sq[c] = vfma(c1[c >> 1][c & 1], -10.0, sq[c]);
 #pragma unroll
-        for (int n = 0; n < NT; ++n)
+    for (int c = 0; c < NC; ++c) as[c] = vadd(c2[c >> 1][c & 1], (c & 1) ? -sd1.y : -sd0.y);
 #pragma unroll
-          for (int i = 0; i < MT; ++i) dmma884(G[i][n][0], G[i][n][1], w[i][par], bx[n]);
+    for (int c = 0; c < NC; ++c) {  // clamp to [1e-300, s_max] on the integer pipe (high word)
+      const int hi = min(max(__double2hiint(sq[c]), 0x01A56E1F), hi_max);
+      sq[c] = __hiloint2double(hi, __double2loint(sq[c]));
+    }
 #pragma unroll
-        for (int n = 0; n < NT; ++n)
+    for (int c = 0; c < NC; ++c) asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(t_[c]) : "d"(sq[c]));
+    G1(0);
 #pragma unroll
-          for (int i = 0; i < MT; ++i) dmma884(G[i][n][0], G[i][n][1], u[i][par], ba[n]);
+    for (int c = 0; c < NC; ++c) g_[c] = vmul(sq[c], t_[c]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vmul(t_[c], 0.5);
+    G1(1);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], h_[c], 0.5);
+    G1(2);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) g_[c] = vfma(g_[c], r_[c], g_[c]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], h_[c]);
+    G1(3);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], g_[c], sq[c]);
+    G1(4);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) g_[c] = vfma(r_[c], h_[c], g_[c]);  // g_ = nrm = sqrt(5)|diff|
+    G1(5);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) t_[c] = vfma(g_[c], k64, kMagic);  // ex = 2^(nrm k64 / 64)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sq[c] = vfma(g_[c], kc1, kc0);  // (n + sig) sig/5
+    G1(6);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) kk[c] = __double2loint(t_[c]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) t_[c] = vadd(t_[c], -kMagic);
+    G1(7);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r_[c] = vfma(g_[c], k64, -t_[c]);
+    G1(8);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], 1.2417843701716925e-12, 5.732851688640402e-10);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) t_[c] = etab[kk[c] & 63];
+    // first operands of GEMM 2
+    const uint32_t x2[2] = {xcur + offB2[0] * 8, xcur + offB2[1] * 8};
+    bxr[0] = lds64v(x2[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 2.1173137155464776e-07);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 5.86490495505617e-05);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 0.010830424696249145);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vmul(h_[c], r_[c]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(t_[c], h_[c], t_[c]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)  // scale by 2^(k >> 6); the clamp of sq keeps the result normal
+      h_[c] = __hiloint2double(__double2hiint(h_[c]) + ((kk[c] >> 6) << 20), __double2loint(h_[c]));  // ex
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r_[c] = vmul(as[c], h_[c]);  // w
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sq[c] = vmul(sq[c], h_[c]);  // u = c2s
+    if (USE_E) {  // gdml_predict.py:132-140 (scaled by 1/base like everything else; E2 is not)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double aE = (c & 1) ? aE1 : aE0;
+        const double nos = g_[c] / sig;
+        r_[c] = fma(aE * (5.0 / sig), sq[c], r_[c]);  // + aE c2 / base = aE ex (n + sig) = aE (5/sig) u
+        E2[c >> 1] = fma(aE * h_[c], 1.0 + nos * (1.0 + nos * (1.0 / 3.0)), E2[c >> 1]);
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[ST + s]);  // this warp is done with stage s
+#pragma unroll
+    for (int c = 0; c < NC; ++c) w[c >> 1][c & 1] = r_[c], u[c >> 1][c & 1] = sq[c];
+    // ---- GEMM 2 of block gb.  Items (par, plane, n): for each parity all X'-plane tiles, then all A_s-plane
+    // tiles, so that the two DMMAs into one accumulator are NT*MT instructions apart (beyond the DMMA latency);
+    // the operand of the next item is fetched first. ----
+    constexpr int NI = 4 * NT;
+    auto item_addr = [&](const int it) -> uint32_t {
+      const int par = it / (2 * NT), plane = (it / NT) & 1, n = it % NT;
+      return x2[par] + plane * kPlane + n * 64;
+    };
+#pragma unroll
+    for (int it = 0; it < NI; ++it) {
+      const int par = it / (2 * NT), plane = (it / NT) & 1, n = it % NT;
+      if (it + 1 < NI) bxr[(it + 1) & 1] = lds64v(item_addr(it + 1));
+#pragma unroll
+      for (int i = 0; i < MT; ++i) dmma884_v(G[i][n][0], G[i][n][1], plane ? u[i][par] : w[i][par], bxr[it & 1]);
+      if (it == 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Eacc[c >> 1] = vfma(as[c], sq[c], Eacc[c >> 1]);
+      }
+      if (it == 2) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s1[c >> 1] = vadd(s1[c >> 1], r_[c]);
+      }
+    }
+    if (b == BPT - 1 || gb == NB - 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[ST + s]);  // this warp is done with stage s
+    }
   }
   __syncthreads();  // all warps have left the main loop: the tile buffers are free (no TMA is in flight)
 

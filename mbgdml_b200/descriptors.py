@@ -30,10 +30,15 @@ for _z, _m in MASSES.items():
 
 def masses_of(Z, strict=True):
     """Per-atom masses for atomic numbers ``Z`` (KeyError for an unknown element if ``strict``)."""
-    Z = np.asarray(Z, dtype=np.int64)
-    known = (Z >= 0) & (Z < len(_MASS_TABLE))
-    out = np.full(Z.shape, np.nan)
-    out[known] = _MASS_TABLE[Z[known]]
+    Z = np.asarray(Z)
+    if Z.size and (Z.min() < 0 or Z.max() >= len(_MASS_TABLE)):
+        if strict:
+            raise KeyError(f"no mass tabulated for atomic number {int(Z.max() if Z.min() >= 0 else Z.min())}")
+        out = np.full(Z.shape, np.nan)
+        known = (Z >= 0) & (Z < len(_MASS_TABLE))
+        out[known] = _MASS_TABLE[Z[known]]
+        return out
+    out = _MASS_TABLE[Z]
     if strict and np.isnan(out).any():
         raise KeyError(f"no mass tabulated for atomic number {int(Z[np.isnan(out)][0])}")
     return out

@@ -191,6 +191,19 @@ int main() {
     snprintf(nm, sizeof nm, "mixed 4 DMMA884 + 4 DFMA, %d thr, %d blk", threads, blocks);
     rep(nm, (512.0 * 4 + 64.0 * 4) * iters * warps, time_ms([&] { k_mixed<4, 4><<<blocks, threads>>>(d, iters, 1.0); }));
   }
+  {  // DMMA latency: 1 warp per SM sub-partition, CH independent accumulators per warp
+    const int threads = 128, blocks = sm;
+    const double warps = (double)threads / 32 * blocks;
+    char nm[96];
+#define LAT(CH)                                                                                            \
+    {                                                                                                      \
+      const double ms = time_ms([&] { k_dmma884<CH><<<blocks, threads>>>(d, iters, 1.0); });              \
+      snprintf(nm, sizeof nm, "DMMA m8n8k4 %d acc, 1 warp/subpart: %.1f ns/DMMA/warp", CH, ms * 1e6 / (iters * CH)); \
+      rep(nm, 512.0 * CH * iters * warps, ms);                                                             \
+    }
+    LAT(1) LAT(2) LAT(3) LAT(4) LAT(6) LAT(8)
+#undef LAT
+  }
   {
     const int threads = 256, blocks = sm * 4, it = 1 << 12;
     const double n = 4.0 * it * threads * blocks;
