@@ -33,11 +33,22 @@ MEOH_R = np.array(
         [-0.363, -0.514, -0.890],
     ]
 )
-MONOMERS = {"h2o": (WATER_Z, WATER_R), "meoh": (MEOH_Z, MEOH_R)}
+# small extra species so that every fragment size the kernels are instantiated for (2..9 atoms) can be built
+HF_Z = np.array([9, 1])
+HF_R = np.array([[0.0, 0.0, 0.0], [0.917, 0.0, 0.0]])
+NH3_Z = np.array([7, 1, 1, 1])
+NH3_R = np.array([[0.0, 0.0, 0.116], [0.0, 0.939, -0.272], [0.813, -0.470, -0.272], [-0.813, -0.470, -0.272]])
+CH4_Z = np.array([6, 1, 1, 1, 1])
+CH4_R = 0.629 * np.array([[0.0, 0.0, 0.0], [1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]])
+MONOMERS = {"h2o": (WATER_Z, WATER_R), "meoh": (MEOH_Z, MEOH_R), "hf": (HF_Z, HF_R), "nh3": (NH3_Z, NH3_R),
+            "ch4": (CH4_Z, CH4_R)}
 # Atom permutations that leave a monomer invariant (identity first).
 MONOMER_PERMS = {
     "h2o": [[0, 1, 2], [0, 2, 1]],
     "meoh": [[0, 1, 2, 3, 4, 5], [0, 1, 2, 4, 5, 3], [0, 1, 2, 5, 3, 4]],
+    "hf": [[0, 1]],
+    "nh3": [[0, 1, 2, 3], [0, 2, 3, 1], [0, 3, 1, 2]],
+    "ch4": [[0, 1, 2, 3, 4], [0, 2, 1, 4, 3], [0, 3, 4, 1, 2], [0, 4, 3, 2, 1]],
 }
 
 

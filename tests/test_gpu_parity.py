@@ -297,6 +297,38 @@ def test_full_size_properties_64_h2o_trimers():
     assert relerr(Ed, Eo) <= TOL and relerr(Fd, Fo) <= TOL
 
 
+@pytest.mark.parametrize("family,n_train", [
+    (["hf"], 5), (["h2o"], 1), (["nh3"], 8), (["hf", "hf"], 9), (["ch4"], 31), (["hf", "h2o"], 33),
+    (["meoh"], 64), (["h2o", "h2o"], 65), (["nh3", "h2o"], 7), (["nh3", "nh3"], 40), (["ch4", "h2o"], 17),
+    (["h2o", "h2o", "h2o"], 100), (["hf", "hf", "ch4"], 23), (["h2o", "meoh"], 129),
+])
+def test_every_fragment_size_and_ragged_train_sizes(family, n_train):
+    """Fragments of 2..9 atoms (every kernel instantiation) with training-set sizes that are not multiples of
+    the 8-row block / 32- and 64-row tiles, with and without alphas_E, against the NumPy oracle."""
+    comps = list(dict.fromkeys(family))  # entity ids ascend in the model's component order (gen_combs keeps only ascending tuples)
+    n_each = 4 if len(family) < 3 else 3
+    comp_list = [c for c in comps for _ in range(n_each)]
+    Z, R, eids, cids = synthetic.make_cluster(len(comp_list), seed=11, spacing=3.4, comp=comp_list)
+    for use_E in (False, True):
+        md = synthetic.make_model(family, n_train=n_train, sig=37.0, seed=3, c=-1.5, std=2.25, use_E=use_E)
+        pred = mb.mbePredict([mb.gdmlModel(dict(md))], mb.predict_gdml)
+        E, F = pred.predict(Z, R, eids, cids)
+        Eo, Fo = orc.mbe_predict([orc.Model(dict(md))], Z, R[None], eids, cids)
+        assert pred.last_stats[0][2] > 0
+        assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+
+
+def test_extreme_kernel_widths():
+    """sig far below / above the descriptor scale: the exp argument clamp and the exponent scaling paths."""
+    Z, R, eids, cids = synthetic.make_cluster(5, seed=5, spacing=3.0)
+    for sig in (0.05, 0.5, 5000.0):
+        md = synthetic.make_model(["h2o", "h2o"], n_train=50, sig=sig, seed=9)
+        E, F = mb.mbePredict([mb.gdmlModel(dict(md))], mb.predict_gdml).predict(Z, R, eids, cids)
+        Eo, Fo = orc.mbe_predict([orc.Model(dict(md))], Z, R[None], eids, cids)
+        assert np.all(np.isfinite(F))
+        assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+
+
 def test_errors_surface_as_reference_exceptions():
     md = synthetic.make_model(["h2o", "h2o"], n_train=8)
     Z, R, eids, cids = synthetic.make_cluster(3)
