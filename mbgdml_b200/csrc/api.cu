@@ -79,7 +79,7 @@ struct mbg_context_s {
   int mma_cfg = 0;                      // developer builds: MT*1000 + threads of the trimer DMMA kernel
   // scratch
   DevBuf sys_ints, sys_masses, R, outE, outF, outV;
-  DevBuf job_ints, flags, blk_acc, blk_enum, blk_off, totals;
+  DevBuf job_ints, job_binom, flags, blk_acc, blk_enum, blk_off, totals;
   DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
   DevBuf exp2_table;  // 2^(j/64), j = 0..63
   long long* h_totals = nullptr;  // pinned [2]
@@ -472,6 +472,40 @@ static int build_job(mbg_context_t ctx, const mbg_system_desc* sys, const mbg_jo
     if (n) CUDA_TRY(cudaMemcpyAsync(d_ints, job->set_entities, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     j.set_ent = d_ints;
     *ints_used = n;
+    // Homogeneous sets (e.g. [h2o, h2o, h2o]): the ascending tuples of the product are exactly the C(n, order)
+    // combinations in lexicographic order, so the device unranks them directly instead of filtering n^order tuples.
+    if (m->order >= 2 && prod > 0) {
+      const int n0 = job->set_offsets[1] - job->set_offsets[0];
+      bool homo = true;
+      for (int s = 0; s < m->order && homo; ++s) {
+        if (job->set_offsets[s + 1] - job->set_offsets[s] != n0) homo = false;
+        for (int k = 0; k < n0 && homo; ++k) {
+          const int e = job->set_entities[job->set_offsets[s] + k];
+          if (e != job->set_entities[k] || (k > 0 && e <= job->set_entities[k - 1])) homo = false;
+        }
+      }
+      const size_t w = (size_t)m->order + 1, tbl = ((size_t)n0 + 1) * w;
+      if (homo && tbl * sizeof(long long) <= (64u << 20)) {
+        std::vector<long long> binom(tbl, 0);
+        const long long kSat = 1ll << 61;
+        for (int a = 0; a <= n0; ++a) {
+          binom[(size_t)a * w] = 1;
+          for (int r = 1; r <= m->order; ++r) {
+            const long long up = a ? binom[(size_t)(a - 1) * w + r] : 0, ul = a ? binom[(size_t)(a - 1) * w + r - 1] : 0;
+            binom[(size_t)a * w + r] = std::min(kSat, up + ul);
+          }
+        }
+        const long long n_comb = binom[(size_t)n0 * w + m->order];
+        if (n_comb < kSat) {
+          TRY(ctx->job_binom.ensure(tbl * sizeof(long long)));
+          CUDA_TRY(cudaMemcpyAsync(ctx->job_binom.p, binom.data(), tbl * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+          j.homogeneous = 1;
+          j.n_set = n0;
+          j.binom = ctx->job_binom.as<long long>();
+          j.cand_per_frame = n_comb;
+        }
+      }
+    }
   }
   if (job->n_alchemy < 0 || job->n_alchemy > kMaxAlchemy)
     return fail(MBG_ERR_UNSUPPORTED, "at most %d alchemical scalers per model", kMaxAlchemy);
@@ -694,7 +728,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   if (!ctx) return MBG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints,
+  for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints, &ctx->job_binom,
                     &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
                     &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table})
     b->release();

@@ -41,10 +41,14 @@ struct JobDev {
   int order;
   int n_frag_atoms;
   int explicit_combs;       // 0: product of sets (ascending filter), 1: explicit tuples
+  int homogeneous;          // 1: every slot draws from the same ascending set -> candidates are the C(n, order)
+                            //    combinations, unranked in lexicographic order (== product order of the ascending tuples)
+  int n_set;                // size of that set
+  const long long* binom;   // [(n_set + 1) x (order + 1)] binomial table, binom[m * (order + 1) + r] = C(m, r)
   int set_off[kMaxOrder + 1];
   const int* set_ent;       // concatenated per-slot entity ids (device)
   const int* combs;         // [n][order] (device) when explicit
-  long long cand_per_frame; // product size, or n_combs
+  long long cand_per_frame; // product size, C(n_set, order), or n_combs
   int n_alch;
   int alch_ent[kMaxAlchemy];
   double alch_fac[kMaxAlchemy];

@@ -42,11 +42,14 @@ __global__ void __launch_bounds__(kCullThreads) k_cull(const CullArgs a) {
     const long long cand = g - frame * a.job.cand_per_frame;
     int ent[kMaxOrder];
     if (decode_tuple(a.job, cand, ent)) {
-      int atoms[kMaxFragAtoms];
-      gather_atoms(a.sys, a.job, ent, atoms);
-      double r[NA][3];
       const double* Rf = a.R + frame * 3ll * a.sys.n_atoms;
-      flag = fragment_accept<NA>(a.sys, a.crit, Rf, atoms, r) ? 1 : 2;
+      flag = 2;
+      if (first_atoms_may_pass(a.sys, a.job, Rf, ent)) {
+        int atoms[kMaxFragAtoms];
+        gather_atoms(a.sys, a.job, ent, atoms);
+        double r[NA][3];
+        flag = fragment_accept<NA>(a.sys, a.crit, Rf, atoms, r) ? 1 : 2;
+      }
     }
   }
   a.flags[(long long)blockIdx.x * kCullThreads + threadIdx.x] = (unsigned char)flag;

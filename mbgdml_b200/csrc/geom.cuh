@@ -67,6 +67,33 @@ __device__ __forceinline__ bool decode_tuple(const JobDev& j, long long cand, in
     for (int s = 0; s < j.order; ++s) ent[s] = j.combs[cand * j.order + s];
     return true;
   }
+  if (j.homogeneous) {
+    // unrank combination number `cand` (lexicographic): slot s takes the smallest position p > prev with
+    // #(combinations whose slot s is in (prev, p]) = C(n-prev-1, r+1) - C(n-p-1, r+1) > rem, r = slots after s
+    const int n = j.n_set, w = j.order + 1;
+    long long rem = cand;
+    int prev = -1;
+    for (int s = 0; s < j.order; ++s) {
+      const int r = j.order - s - 1;
+      int p;
+      if (r == 0) {
+        p = prev + 1 + (int)rem;
+      } else {
+        const long long top = j.binom[(long long)(n - prev - 1) * w + (r + 1)];
+        const long long target = top - rem;  // largest m with C(m, r+1) < target
+        int lo = r, hi = n - prev - 2;       // C(r, r+1) = 0 < target always
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (j.binom[(long long)mid * w + (r + 1)] < target) lo = mid; else hi = mid - 1;
+        }
+        p = n - 1 - lo;
+        rem -= top - j.binom[(long long)(n - p) * w + (r + 1)];
+      }
+      ent[s] = j.set_ent[p];
+      prev = p;
+    }
+    return true;
+  }
   long long idx = cand;
   for (int s = j.order - 1; s >= 0; --s) {
     const int n_s = j.set_off[s + 1] - j.set_off[s];
@@ -197,6 +224,32 @@ __device__ __forceinline__ bool criteria_accept(const CritDev& c, double v) {
   if (c.bound == MBG_BOUND_RANGE) return (c.lo < v) && (v < c.hi);
   if (c.bound == MBG_BOUND_UPPER) return v < c.hi;
   return v > c.lo;
+}
+
+// Cheap exact pre-filter for the culling kernel: the subset of fragment_coords' rejection tests that only
+// involves the FIRST atom of every entity (under an orthorhombic cell with cutoff <= L_min/2, where a failed
+// naive minimum image already implies rejection).  Every test here is evaluated by fragment_coords with
+// bit-identical arithmetic, and any single failing test rejects the fragment, so returning false early
+// never changes the accept mask.  Consecutive candidates share their leading entities, so warps exit together.
+__device__ __forceinline__ bool first_atoms_may_pass(const SysDev& s, const JobDev& j, const double* __restrict__ Rf,
+                                                     const int ent[kMaxOrder]) {
+  if (!(s.periodic && s.fast_reject)) return true;
+  double v[kMaxOrder][3];
+  const double* p0 = Rf + 3ll * s.ent_atoms[s.ent_off[ent[0]]];
+#pragma unroll
+  for (int k = 0; k < kMaxOrder; ++k) {
+    if (k >= j.order) break;
+    const double* p = Rf + 3ll * s.ent_atoms[s.ent_off[ent[k]]];
+    const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
+    if (!(mic_naive(s, d, v[k]) < s.half_min_len)) return false;
+#pragma unroll
+    for (int i = 0; i < kMaxOrder; ++i) {
+      if (i >= k) break;
+      const double dist = norm3_rn(__dsub_rn(v[i][0], v[k][0]), __dsub_rn(v[i][1], v[k][1]), __dsub_rn(v[i][2], v[k][2]));
+      if (dist >= s.cutoff) return false;
+    }
+  }
+  return true;
 }
 
 // Full accept decision for one fragment; r receives the coordinates the descriptor is built from.
