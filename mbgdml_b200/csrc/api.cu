@@ -81,7 +81,8 @@ struct mbg_context_s {
   DevBuf sys_ints, sys_masses, R, outE, outF, outV;
   DevBuf job_ints, job_binom, flags, blk_acc, blk_enum, blk_off, totals;
   DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
-  DevBuf exp2_table;  // 2^(j/64), j = 0..63
+  DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
+  DevBuf exp2_table_mma;  // 2^(j/1024), j = 0..1023  (DMMA kernel)
   long long* h_totals = nullptr;  // pinned [2]
   // timing of the last call
   std::vector<cudaEvent_t> ev_pool;
@@ -551,7 +552,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
       a.sys = s;
       a.R = dR;
       a.tiles = m->tiles_mma, a.mu = m->mu, a.iperm = m->iperm;
-      a.exp2_table = ctx->exp2_table.as<double>();
+      a.exp2_table = ctx->exp2_table_mma.as<double>();
       a.T_pad = m->T_pad, a.P = m->P;
       a.n_row_blocks = (m->T + 7) / 8;
       a.sig = m->sig, a.c = m->c, a.std = m->std;
@@ -712,6 +713,10 @@ int mbg_context_create(int device, mbg_context_t* out) {
     for (int j = 0; j < (1 << kExpTableBits); ++j) tab[j] = (double)exp2l((long double)j / (1 << kExpTableBits));
     TRY(ctx->exp2_table.ensure(sizeof(tab)));
     CUDA_TRY(cudaMemcpy(ctx->exp2_table.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    double tab2[kMmaExpTable];
+    for (int j = 0; j < kMmaExpTable; ++j) tab2[j] = (double)exp2l((long double)j / kMmaExpTable);
+    TRY(ctx->exp2_table_mma.ensure(sizeof(tab2)));
+    CUDA_TRY(cudaMemcpy(ctx->exp2_table_mma.p, tab2, sizeof(tab2), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaEventCreate(&ctx->ev_call0));
   CUDA_TRY(cudaEventCreate(&ctx->ev_call1));
@@ -730,7 +735,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints, &ctx->job_binom,
                     &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
-                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table})
+                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_call0);
@@ -864,6 +869,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
         xrow[e] = xv, arow[e] = av;
         xx += (long double)xv * xv, xa += (long double)xv * av;
       }
+      xrow[D] = 1.0;  // spare column of GEMM 2: Gacc[q][D] = sum_t w = s1
       // position of row r in column order: r = 8 b + tau(j)  ->  8 b + j  (tau is an involution)
       const int pos = (r / 8) * 8 + mma_tau(r % 8);
       double* side = tile + (size_t)2 * TRm * Dq;
