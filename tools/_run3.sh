@@ -1,5 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for cfg in 0 23841 25121 32561 31282 21283 41282; do
+for cfg in 0 23841 25121 32561 31282 21283 41282 42561 21922; do
   MBG_MMA_CFG=$cfg python bench.py --workload trimers64 --frames 2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_mma_$cfg.txt 2>&1
   python - <<PY
 import json
@@ -10,4 +10,3 @@ else:
     print(open("gpurun_out/b_mma_$cfg.txt").read()[-2000:])
 PY
 done
-./tools/microbench | grep -E "DMMA|DFMA 8 chains, 256"
