@@ -179,6 +179,21 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
 int mbg_r_mic(mbg_context_t ctx, const double *cell, double cutoff, const double *r, int32_t n,
               double *out, int32_t *accepted);
 
+/* mbe_worker + the add/remove step of mbe_contrib (mbe.py:73-197, 381-427), used by decomp_to_total
+ * (mbe.py:432-508): for each selected reference structure i (row ref_rows[i] of E[n_total] /
+ * Deriv[n_total][n_atoms_ref][3], updated in place) the pairs [pair_offsets[i], pair_offsets[i+1]) name the
+ * lower-order structures found for its entity combinations, in itertools.combinations order;
+ * slot_entity[p][k] is the entity id of the reference structure that slot k of lower structure lower_idx[p]
+ * is added onto.  atom_entity / atom_rank describe the reference atoms (entity id, index within the entity),
+ * lower_off / lower_atoms the atoms of each slot of a lower structure.  Sums run in pair order, so the result
+ * is bit-identical to the reference's sequential loop.  sign = +1 ("add") or -1 ("remove"). */
+int mbg_mbe_accumulate(mbg_context_t ctx, int64_t n_ref, const int64_t *ref_rows, const int64_t *pair_offsets,
+                       const int64_t *lower_idx, const int32_t *slot_entity, int32_t n_slots,
+                       int32_t n_atoms_ref, const int32_t *atom_entity, const int32_t *atom_rank,
+                       int32_t n_atoms_lower, const int32_t *lower_off, const int32_t *lower_atoms,
+                       const double *E_lower, const double *Deriv_lower, int64_t n_lower, double sign,
+                       double *E, double *Deriv, int64_t n_total);
+
 /* Measured FP64 FMA-pipe peak of this GPU (dependent-chain-free DFMA loop, CUDA-event timed),
  * in TFLOP/s: the roofline denominator bench.py reports against. */
 int mbg_measure_fp64_peak(mbg_context_t ctx, double *tflops, double *sm_clock_mhz_est);

@@ -9,7 +9,7 @@ See DESIGN.md.
 """
 from .alchemy import mbeAlchemyScale
 from .descriptors import Criteria, com_distance_sum, max_atom_pair_dist
-from .mbe import mbePredict
+from .mbe import decomp_to_total, mbe_contrib, mbePredict
 from .models import gdmlModel
 from .periodic import Cell
 from .predictors import predict_gdml, predict_gdml_decomp
@@ -18,5 +18,6 @@ from .utils import gen_combs
 
 __all__ = [
     "mbePredict", "gdmlModel", "predict_gdml", "predict_gdml_decomp", "Criteria", "com_distance_sum",
-    "max_atom_pair_dist", "Cell", "mbeAlchemyScale", "linear_switching", "gen_combs",
+    "max_atom_pair_dist", "Cell", "mbeAlchemyScale", "linear_switching", "gen_combs", "mbe_contrib",
+    "decomp_to_total",
 ]

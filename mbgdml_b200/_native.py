@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_enumerate",
-    "mbg_criteria_eval", "mbg_r_mic", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
+    "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -105,6 +105,8 @@ def load_library():
         lib.mbg_enumerate.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, _lp]
         lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
         lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
+        lib.mbg_mbe_accumulate.argtypes = [C.c_void_p, C.c_int64, _lp, _lp, _lp, _ip, C.c_int32, C.c_int32, _ip, _ip,
+                                           C.c_int32, _ip, _ip, _dp, _dp, C.c_int64, C.c_double, _dp, _dp, C.c_int64]
         lib.mbg_measure_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
         lib.mbg_measure_fp64_tensor_peak.argtypes = [C.c_void_p, _dp]
         for name in EXPORTED_SYMBOLS:
@@ -256,6 +258,23 @@ class Context:
         check(self.lib.mbg_criteria_eval(self.handle, kind, n_atoms, ptr(m, _dp), ptr(e, _ip), ptr(R, _dp), n_R,
                                          ptr(out, _dp)))
         return out
+
+    def mbe_accumulate(self, ref_rows, pair_offsets, lower_idx, slot_entity, atom_entity, atom_rank, lower_off,
+                       lower_atoms, E_lower, Deriv_lower, sign, E, Deriv):
+        """In-place E[ref_rows] / Deriv[ref_rows] += sign * (sum of the paired lower-order rows); see the header."""
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        ref_rows, pair_offsets, lower_idx = i64(ref_rows), i64(pair_offsets), i64(lower_idx)
+        slot_entity = as_i32(slot_entity).reshape(len(lower_idx), -1) if len(lower_idx) else np.zeros((0, len(lower_off) - 1), np.int32)
+        atom_entity, atom_rank, lower_off, lower_atoms = map(as_i32, (atom_entity, atom_rank, lower_off, lower_atoms))
+        E_lower, Deriv_lower = as_f64(E_lower), as_f64(Deriv_lower)
+        assert E.dtype == np.float64 and Deriv.dtype == np.float64 and E.flags.c_contiguous and Deriv.flags.c_contiguous
+        n_slots = len(lower_off) - 1
+        n_atoms_lower = Deriv_lower.shape[1] if Deriv_lower.ndim == 3 else int(lower_off[-1])
+        check(self.lib.mbg_mbe_accumulate(
+            self.handle, len(ref_rows), ptr(ref_rows, _lp), ptr(pair_offsets, _lp), ptr(lower_idx, _lp),
+            ptr(slot_entity, _ip), n_slots, Deriv.shape[1], ptr(atom_entity, _ip), ptr(atom_rank, _ip), n_atoms_lower,
+            ptr(lower_off, _ip), ptr(lower_atoms, _ip), ptr(E_lower, _dp), ptr(Deriv_lower, _dp), len(E_lower),
+            float(sign), ptr(E, _dp), ptr(Deriv, _dp), len(E)))
 
     def r_mic(self, cell, cutoff, r):
         r = as_f64(r)

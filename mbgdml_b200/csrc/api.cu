@@ -14,6 +14,7 @@
 #include "hostmath.h"
 #include "matern.cuh"
 #include "matern_mma.cuh"
+#include "mbe_accum.cuh"
 
 using namespace mbg;
 
@@ -1193,6 +1194,109 @@ int mbg_measure_fp64_peak(mbg_context_t ctx, double* tflops, double* sm_clock_mh
   *tflops = best;
   // 64 FP64 FMA lanes per SM per clock on sm_100
   if (sm_clock_mhz_est) *sm_clock_mhz_est = best * 1e12 / (2.0 * 64 * ctx->sm_count) / 1e6;
+  return MBG_OK;
+}
+
+int mbg_mbe_accumulate(mbg_context_t ctx, int64_t n_ref, const int64_t* ref_rows, const int64_t* pair_offsets,
+                       const int64_t* lower_idx, const int32_t* slot_entity, int32_t n_slots, int32_t n_atoms_ref,
+                       const int32_t* atom_entity, const int32_t* atom_rank, int32_t n_atoms_lower,
+                       const int32_t* lower_off, const int32_t* lower_atoms, const double* E_lower,
+                       const double* Deriv_lower, int64_t n_lower, double sign, double* E, double* Deriv,
+                       int64_t n_total) {
+  if (!ctx || !ref_rows || !pair_offsets || !atom_entity || !atom_rank || !lower_off || !lower_atoms || !E || !Deriv)
+    return fail(MBG_ERR_ARG, "NULL argument");
+  if (n_ref < 0 || n_slots < 1 || n_atoms_ref < 1 || n_atoms_lower < 1 || n_lower < 0 || n_total < 0)
+    return fail(MBG_ERR_ARG, "bad sizes");
+  if (!(sign == 1.0 || sign == -1.0)) return fail(MBG_ERR_ARG, "sign must be +1 (add) or -1 (remove)");
+  if (n_ref == 0) return MBG_OK;
+  const int64_t n_pairs = pair_offsets[n_ref];
+  if (pair_offsets[0] != 0 || n_pairs < 0) return fail(MBG_ERR_ARG, "pair_offsets must start at 0");
+  if (n_pairs > 0 && (!lower_idx || !slot_entity || !E_lower || !Deriv_lower)) return fail(MBG_ERR_ARG, "NULL argument");
+  for (int64_t i = 0; i < n_ref; ++i) {
+    if (pair_offsets[i + 1] < pair_offsets[i]) return fail(MBG_ERR_ARG, "pair_offsets not monotone");
+    if (ref_rows[i] < 0 || ref_rows[i] >= n_total) return fail(MBG_ERR_ARG, "ref_rows[%lld] out of range", (long long)i);
+  }
+  for (int64_t p = 0; p < n_pairs; ++p)
+    if (lower_idx[p] < 0 || lower_idx[p] >= n_lower) return fail(MBG_ERR_ARG, "lower_idx[%lld] out of range", (long long)p);
+  if (lower_off[0] != 0 || lower_off[n_slots] > n_atoms_lower) return fail(MBG_ERR_ARG, "bad lower_off");
+  {  // entity sizes must agree: Deriv[i][i_z] += deriv_lower[i_z_lower] (mbe.py:193) needs len(i_z) == len(i_z_lower)
+    int n_ent = 0;
+    for (int at = 0; at < n_atoms_ref; ++at) {
+      if (atom_entity[at] < 0 || atom_rank[at] < 0) return fail(MBG_ERR_ARG, "atom_entity / atom_rank must be >= 0");
+      n_ent = std::max(n_ent, atom_entity[at] + 1);
+    }
+    std::vector<int> ent_size(n_ent, 0);
+    for (int at = 0; at < n_atoms_ref; ++at) ent_size[atom_entity[at]]++;
+    for (int64_t p = 0; p < n_pairs; ++p)
+      for (int k = 0; k < n_slots; ++k) {
+        const int e = slot_entity[p * n_slots + k];
+        if (e < 0 || e >= n_ent) return fail(MBG_ERR_ARG, "slot_entity[%lld][%d] out of range", (long long)p, k);
+        if (ent_size[e] != lower_off[k + 1] - lower_off[k])
+          return fail(MBG_ERR_ARG, "entity %d has %d atoms but slot %d of the lower structure has %d", e, ent_size[e], k,
+                      lower_off[k + 1] - lower_off[k]);
+      }
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  // one staging allocation: [int64 block | int32 block | double block]
+  const size_t n64 = (size_t)n_ref + (size_t)n_ref + 1 + (size_t)n_pairs;
+  const size_t n32 = (size_t)n_pairs * n_slots + 2 * (size_t)n_atoms_ref + (size_t)n_slots + 1 + (size_t)lower_off[n_slots];
+  const size_t nd_low = (size_t)n_lower * (1 + 3 * (size_t)n_atoms_lower);
+  const size_t nd_out = (size_t)n_total * (1 + 3 * (size_t)n_atoms_ref);
+  const size_t bytes = n64 * 8 + ((n32 * 4 + 7) / 8) * 8 + (nd_low + nd_out) * 8;
+  TRY(ctx->flags.ensure(bytes + 64));
+  char* base = ctx->flags.as<char>();
+  long long* d64 = reinterpret_cast<long long*>(base);
+  int* d32 = reinterpret_cast<int*>(base + n64 * 8);
+  double* dd = reinterpret_cast<double*>(base + n64 * 8 + ((n32 * 4 + 7) / 8) * 8);
+  auto up = [&](void* dst, const void* src, size_t nbytes) {
+    return nbytes ? cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+  };
+  MbeAccumArgs a;
+  a.n_ref = n_ref, a.n_atoms_ref = n_atoms_ref, a.n_atoms_lower = n_atoms_lower, a.n_slots = n_slots;
+  long long* q = d64;
+  a.ref_rows = q;
+  CUDA_TRY(up(q, ref_rows, (size_t)n_ref * 8));
+  q += n_ref;
+  a.pair_offsets = q;
+  CUDA_TRY(up(q, pair_offsets, ((size_t)n_ref + 1) * 8));
+  q += n_ref + 1;
+  a.lower_idx = q;
+  CUDA_TRY(up(q, lower_idx, (size_t)n_pairs * 8));
+  int* r = d32;
+  a.slot_entity = r;
+  CUDA_TRY(up(r, slot_entity, (size_t)n_pairs * n_slots * 4));
+  r += (size_t)n_pairs * n_slots;
+  a.atom_entity = r;
+  CUDA_TRY(up(r, atom_entity, (size_t)n_atoms_ref * 4));
+  r += n_atoms_ref;
+  a.atom_rank = r;
+  CUDA_TRY(up(r, atom_rank, (size_t)n_atoms_ref * 4));
+  r += n_atoms_ref;
+  a.lower_off = r;
+  CUDA_TRY(up(r, lower_off, ((size_t)n_slots + 1) * 4));
+  r += n_slots + 1;
+  a.lower_atoms = r;
+  CUDA_TRY(up(r, lower_atoms, (size_t)lower_off[n_slots] * 4));
+  double* w = dd;
+  a.E_lower = w;
+  CUDA_TRY(up(w, E_lower, (size_t)n_lower * 8));
+  w += n_lower;
+  a.D_lower = w;
+  CUDA_TRY(up(w, Deriv_lower, (size_t)n_lower * n_atoms_lower * 3 * 8));
+  w += (size_t)n_lower * n_atoms_lower * 3;
+  a.E = w;
+  CUDA_TRY(up(w, E, (size_t)n_total * 8));
+  w += n_total;
+  a.D = w;
+  CUDA_TRY(up(w, Deriv, (size_t)n_total * n_atoms_ref * 3 * 8));
+  a.sign = sign;
+  const long long n_thr = n_ref * ((long long)n_atoms_ref * 3 + 1);
+  k_mbe_accumulate<<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(E, a.E, (size_t)n_total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(Deriv, a.D, (size_t)n_total * n_atoms_ref * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MBG_OK;
 }
 

@@ -22,6 +22,137 @@ from .stress import to_voigt, virial_finite_diff
 from .utils import gen_combs
 
 
+def gen_r_entity_combs(r_prov_spec, entity_ids_lower):
+    """mbe.py:36-70: entity-id combinations (without replacement) of one structure's provenance spec."""
+    n_entities_lower = len(set(np.asarray(entity_ids_lower).tolist()))
+    for comb in itertools.combinations(r_prov_spec[2:], n_entities_lower):
+        yield comb
+
+
+def gen_r_idxs_worker(r_prov_specs, r_prov_ids_lower, n_workers):
+    """mbe.py:200-233: structure indices whose r_prov_id appears in the lower-order data, split over workers."""
+    r_idxs = []
+    for r_prov_id_lower in r_prov_ids_lower.keys():
+        r_idxs.extend(np.where(r_prov_specs[:, 0] == r_prov_id_lower)[0].tolist())
+    task_size = int(np.ceil(len(r_idxs) / n_workers)) if r_idxs else 1
+    for i in range(0, len(r_idxs), task_size):
+        yield r_idxs[i:i + task_size]
+
+
+def _mbe_pairs(entity_ids, r_prov_specs, r_idxs, entity_ids_lower, r_prov_specs_lower):
+    """Host side of mbe_worker (mbe.py:73-197): which lower-order row belongs to which (structure, entity
+    combination).  The reference scans all lower rows per combination (np.all(...) , mbe.py:154-156: O(n^2));
+    this is a sort join.  Returns (pair_offsets, lower_idx, slot_entity) in the reference's loop order:
+    structures in r_idxs order, combinations in itertools.combinations order, missing fragments skipped."""
+    specs = np.asarray(r_prov_specs)[np.asarray(r_idxs, dtype=np.int64)].astype(np.int64)
+    lower = np.asarray(r_prov_specs_lower).astype(np.int64)
+    n_sel, n_ent = specs.shape[0], specs.shape[1] - 2
+    n_low = len(set(np.asarray(entity_ids_lower).tolist()))
+    if lower.shape[1] != 2 + n_low:
+        raise ValueError("r_prov_specs_lower has the wrong number of columns for entity_ids_lower")
+    pos = np.array(list(itertools.combinations(range(n_ent), n_low)), dtype=np.int64).reshape(-1, n_low)
+    n_comb = pos.shape[0]
+    ents = specs[:, 2:][:, pos]  # (n_sel, n_comb, n_low) provenance entity ids of every combination
+    keys = np.concatenate([np.broadcast_to(specs[:, None, :2], (n_sel, n_comb, 2)), ents], axis=2).reshape(-1, 2 + n_low)
+    # first occurrence of every key among the lower rows (np.where(...)[0][0])
+    both = np.concatenate([lower, keys], axis=0)
+    _, inv = np.unique(both, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    first = np.full(inv.max() + 1 if inv.size else 0, -1, dtype=np.int64)
+    n_lower_rows = lower.shape[0]
+    first[inv[:n_lower_rows][::-1]] = np.arange(n_lower_rows - 1, -1, -1)
+    match = first[inv[n_lower_rows:]].reshape(n_sel, n_comb)
+    found = match >= 0
+    # entity id (position in the structure's spec) each slot lands on: first occurrence of the provenance id
+    # (np.where(r_prov_spec[2:] == entity_id_prov)[0][0], mbe.py:183)
+    slot_entity = (specs[:, None, None, 2:] == ents[..., None]).argmax(axis=-1)
+    pair_offsets = np.zeros(n_sel + 1, dtype=np.int64)
+    np.cumsum(found.sum(axis=1), out=pair_offsets[1:])
+    return pair_offsets, match[found], slot_entity[found].astype(np.int32)
+
+
+def mbe_worker(r_shape, entity_ids, r_prov_specs, r_idxs, E_lower, Deriv_lower, entity_ids_lower, r_prov_specs_lower):
+    """mbe.py:73-197: summed lower-order contributions of the structures ``r_idxs`` (no sign applied)."""
+    E = np.zeros(len(r_idxs))
+    Deriv = np.zeros((len(r_idxs), *r_shape))
+    _mbe_accumulate(E, Deriv, np.arange(len(r_idxs)), entity_ids, r_prov_specs, r_idxs, E_lower, Deriv_lower,
+                    entity_ids_lower, r_prov_specs_lower, 1.0)
+    return r_idxs, E, Deriv
+
+
+def _mbe_accumulate(E, Deriv, rows, entity_ids, r_prov_specs, r_idxs, E_lower, Deriv_lower, entity_ids_lower,
+                    r_prov_specs_lower, sign):
+    entity_ids = np.asarray(entity_ids)
+    entity_ids_lower = np.asarray(entity_ids_lower)
+    if len(r_idxs) == 0:
+        return
+    pair_offsets, lower_idx, slot_entity = _mbe_pairs(entity_ids, r_prov_specs, r_idxs, entity_ids_lower,
+                                                      r_prov_specs_lower)
+    # atoms of the reference structure: entity id and index within the entity (np.where(entity_ids == e)[0] order)
+    atom_rank = np.zeros(len(entity_ids), dtype=np.int32)
+    for e in np.unique(entity_ids):
+        idx = np.where(entity_ids == e)[0]
+        atom_rank[idx] = np.arange(len(idx))
+    n_low = len(set(entity_ids_lower.tolist()))
+    lower_atoms = [np.where(entity_ids_lower == k)[0] for k in range(n_low)]
+    lower_off = np.zeros(n_low + 1, dtype=np.int32)
+    lower_off[1:] = np.cumsum([len(x) for x in lower_atoms])
+    _native.get_context().mbe_accumulate(
+        rows, pair_offsets, lower_idx, slot_entity, entity_ids, atom_rank, lower_off,
+        np.concatenate(lower_atoms) if lower_atoms else np.zeros(0), E_lower, Deriv_lower, sign, E, Deriv)
+
+
+def mbe_contrib(E, Deriv, entity_ids, r_prov_ids, r_prov_specs, E_lower, Deriv_lower, entity_ids_lower,
+                r_prov_ids_lower, r_prov_specs_lower, operation="remove", use_ray=False, ray_address="auto",
+                n_workers=1):
+    """Add or remove lower-order energy / derivative contributions (mbe.py:237-429).  ``E`` and ``Deriv`` are
+    updated in place and returned, like the reference.  The matching of lower-order rows is a host sort join;
+    the accumulation is a device segmented scatter in the reference's summation order (bit-identical)."""
+    if use_ray:
+        raise NotImplementedError("use_ray=True: the ray CPU fan-out (mbe.py:399-427) is replaced by one GPU kernel")
+    if operation not in ("add", "remove"):
+        raise ValueError(f'{operation} is not "add" or "remove"')
+    if (r_prov_ids is not None) and (r_prov_ids != {}):
+        for r_prov_id_lower, r_prov_md5_lower in r_prov_ids_lower.items():
+            assert r_prov_md5_lower == r_prov_ids[r_prov_id_lower]
+    else:  # assume that all lower models apply (mbe.py:367-377)
+        assert r_prov_specs is None or r_prov_specs.shape == (1, 0)
+        assert len(set(np.asarray(r_prov_specs_lower)[:, 0].tolist())) == 1
+        n_r = len(E)
+        n_entities = len(set(np.asarray(entity_ids).tolist()))
+        r_prov_specs = np.empty((n_r, 2 + n_entities), dtype=int)
+        r_prov_specs[:, 0] = np.asarray(r_prov_specs_lower)[0][0]
+        r_prov_specs[:, 1] = np.arange(n_r)
+        for entity_id in range(n_entities):
+            r_prov_specs[:, entity_id + 2] = entity_id
+    r_idxs = next(gen_r_idxs_worker(r_prov_specs, r_prov_ids_lower, 1), [])
+    if not (isinstance(E, np.ndarray) and E.dtype == np.float64 and E.flags.c_contiguous
+            and isinstance(Deriv, np.ndarray) and Deriv.dtype == np.float64 and Deriv.flags.c_contiguous):
+        raise TypeError("E and Deriv must be C-contiguous float64 arrays (they are updated in place)")
+    _mbe_accumulate(E, Deriv, np.asarray(r_idxs, dtype=np.int64), entity_ids, r_prov_specs, r_idxs, E_lower, Deriv_lower,
+                    entity_ids_lower, r_prov_specs_lower, 1.0 if operation == "add" else -1.0)
+    return E, Deriv
+
+
+def decomp_to_total(E_nbody, F_nbody, entity_ids, entity_combs, use_ray=False, n_workers=1, ray_address="auto"):
+    """Sum decomposed n-body energies and forces into totals (mbe.py:432-508); NaN rows count as zero."""
+    entity_ids = np.asarray(entity_ids)
+    entity_combs = np.asarray(entity_combs)
+    n_atoms = len(entity_ids)
+    n_r = len(np.unique(entity_combs[:, 0]))
+    E = np.zeros((n_r,))
+    F = np.zeros((n_r, n_atoms, 3))
+    entity_ids_lower = []
+    for i in range(len(entity_combs[0][1:])):
+        entity_ids_lower.extend([i for j in range(np.count_nonzero(entity_ids == i))])
+    entity_ids_lower = np.array(entity_ids_lower)
+    r_prov_specs_lower = np.hstack((np.zeros((len(entity_combs), 1)), entity_combs))
+    E_nbody = np.nan_to_num(E_nbody, copy=False, nan=0.0)
+    F_nbody = np.nan_to_num(F_nbody, copy=False, nan=0.0)
+    return mbe_contrib(E, F, entity_ids, None, None, E_nbody, F_nbody, entity_ids_lower, {0: ""}, r_prov_specs_lower,
+                       operation="add", use_ray=use_ray, n_workers=n_workers, ray_address=ray_address)
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -229,4 +360,5 @@ class mbePredict:  # pylint: disable=invalid-name
         return E_data, F_data, entity_comb_data, nbody_orders
 
 
-__all__ = ["mbePredict", "predict_gdml", "predict_gdml_decomp", "gen_combs", "itertools"]
+__all__ = ["mbePredict", "predict_gdml", "predict_gdml_decomp", "gen_combs", "mbe_contrib", "decomp_to_total",
+           "mbe_worker", "gen_r_entity_combs", "gen_r_idxs_worker"]

@@ -377,6 +377,57 @@ def case_reference_fixtures():
     print("  com_distance_sum: 120 dimers bit-exact; known answer and NaN index set reproduced")
 
 
+def case_mbe_contrib():
+    """mbe.mbe_contrib / decomp_to_total (reference tests/test_mbe.py:38-100, tests/test_predictsets.py:40-77)."""
+    from mbgdml.mbe import mbe_contrib, decomp_to_total  # the reference
+
+    mdir = os.path.join(REF, "tests/data/mbe")
+    d4 = dict(np.load(os.path.join(mdir, "4h2o.npz"), allow_pickle=True))
+    lows = [dict(np.load(os.path.join(mdir, f"4h2o-{k}body.npz"), allow_pickle=True)) for k in (1, 2, 3)]
+    keys = [("energy_ele_mp2.def2tzvp_orca", "grads_mp2.def2tzvp_orca")] + \
+           [("energy_ele_nbody_mp2.def2tzvp_orca", "grads_nbody_mp2.def2tzvp_orca")] * 2
+    E_true, G_true = d4["energy_ele_mp2.def2tzvp_orca"], d4["grads_mp2.def2tzvp_orca"]
+    entity_ids = d4["entity_ids"]
+    out = {"entity_ids": entity_ids, "E_true": E_true, "G_true": G_true}
+    E_ref, G_ref = np.zeros(E_true.shape), np.zeros(G_true.shape)
+    E_orc, G_orc = np.zeros(E_true.shape), np.zeros(G_true.shape)
+    for k, (low, (ek, gk)) in enumerate(zip(lows, keys)):
+        args = (low[ek], low[gk], low["entity_ids"], low["r_prov_ids"].item(), low["r_prov_specs"])
+        E_ref, G_ref = mbe_contrib(E_ref, G_ref, entity_ids, None, None, *args, operation="add", use_ray=False)
+        E_orc, G_orc = orc.mbe_contrib(E_orc, G_orc, entity_ids, None, None, *args, operation="add")
+        assert np.array_equal(E_ref, E_orc) and np.array_equal(G_ref, G_orc), "mbe_contrib must be bit-exact"
+        out.update({f"low{k}_E": low[ek], f"low{k}_G": low[gk], f"low{k}_entity_ids": low["entity_ids"],
+                    f"low{k}_r_prov_specs": low["r_prov_specs"], f"low{k}_r_prov_id": np.array(list(args[3].keys())),
+                    f"add{k}_E": E_ref.copy(), f"add{k}_G": G_ref.copy()})
+    assert np.allclose(E_ref, np.array([-305.30075391, -305.29900387, -305.29489548]))  # tests/test_mbe.py:99-100
+    # "remove" with explicit provenance of the reference structures and a lower set that misses some fragments
+    r_prov_ids = {0: "x"}
+    specs = np.array([[0, i, 0, 1, 2, 3] for i in range(3)])
+    low = lows[1]
+    keep = np.ones(len(low["r_prov_specs"]), dtype=bool)
+    keep[[1, 7, 8]] = False
+    args = (low[keys[1][0]][keep], low[keys[1][1]][keep], low["entity_ids"], {0: "x"}, low["r_prov_specs"][keep])
+    E_r, G_r = mbe_contrib(E_true.copy(), G_true.copy(), entity_ids, r_prov_ids, specs, *args, operation="remove",
+                           use_ray=False)
+    E_o, G_o = orc.mbe_contrib(E_true.copy(), G_true.copy(), entity_ids, r_prov_ids, specs, *args, operation="remove")
+    assert np.array_equal(E_r, E_o) and np.array_equal(G_r, G_o)
+    out.update({"rm_keep": keep, "rm_specs": specs, "rm_E": E_r, "rm_G": G_r})
+    # decomp_to_total on a synthetic decomposition with NaN rows (rejected fragments), 2 structures
+    rng = np.random.default_rng(4)
+    eids6 = np.repeat(np.arange(5), 3)
+    combs = np.array([(s, i, j) for s in range(2) for i in range(5) for j in range(i + 1, 5)])
+    E_n, F_n = rng.normal(size=len(combs)), rng.normal(size=(len(combs), 6, 3))
+    E_n[[3, 11]] = np.nan
+    F_n[[3, 11]] = np.nan
+    E_t, F_t = decomp_to_total(E_n.copy(), F_n.copy(), eids6, combs)
+    E_to, F_to = orc.decomp_to_total(E_n.copy(), F_n.copy(), eids6, combs)
+    assert np.array_equal(E_t, E_to) and np.array_equal(F_t, F_to)
+    out.update({"d2t_entity_ids": eids6, "d2t_combs": combs, "d2t_E_nbody": E_n, "d2t_F_nbody": F_n,
+                "d2t_E": E_t, "d2t_F": F_t})
+    np.savez_compressed(os.path.join(GOLD, "mbe_contrib_4h2o.npz"), **out)
+    print("  mbe_contrib add x3 (known answer reproduced), remove with missing fragments, decomp_to_total: bit-exact")
+
+
 if __name__ == "__main__":
     np.seterr(all="raise", under="ignore")
     print("gen_combs"); case_gen_combs()
@@ -385,5 +436,6 @@ if __name__ == "__main__":
     print("periodic"); case_periodic()
     print("mixed"); case_mixed()
     print("reference fixtures"); case_reference_fixtures()
+    print("mbe_contrib"); case_mbe_contrib()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden fixtures written: %.1f KB" % (total / 1024))

@@ -516,3 +516,80 @@ def mbe_predict_decomp(models, Z, R, entity_ids, comp_ids):
         F_data.append(np.array(Fs))
         comb_data.append(np.array(Cs))
     return E_data, F_data, comb_data, orders
+
+
+# --------------------------------------------------------------------------
+# MBE recombination (add / remove lower-order contributions)
+# --------------------------------------------------------------------------
+def mbe_worker(r_shape, entity_ids, r_prov_specs, r_idxs, E_lower, Deriv_lower, entity_ids_lower,
+               r_prov_specs_lower):
+    """mbe.py:73-197: for every structure, every combination of its entities of the lower order
+    (itertools.combinations of r_prov_spec[2:]), first lower-order row with that provenance spec;
+    missing rows are skipped; derivatives land on the atoms of the matching entity."""
+    entity_ids = np.asarray(entity_ids)
+    entity_ids_lower = np.asarray(entity_ids_lower)
+    E = np.zeros(len(r_idxs))
+    Deriv = np.zeros((len(r_idxs), *r_shape))
+    n_lower = len(set(entity_ids_lower.tolist()))
+    for i, i_r in enumerate(r_idxs):
+        spec = r_prov_specs[i_r]
+        for comb in itertools.combinations(spec[2:], n_lower):
+            spec_lower = np.block([spec[:2], np.array(comb)])
+            hits = np.where(np.all(r_prov_specs_lower == spec_lower, axis=1))[0]
+            if hits.size == 0:
+                continue
+            i_low = hits[0]
+            E[i] += E_lower[i_low]
+            for prov in spec_lower[2:]:
+                entity_id = np.where(spec[2:] == prov)[0][0]
+                i_z = np.where(entity_ids == entity_id)[0]
+                entity_id_lower = np.where(spec_lower[2:] == prov)[0][0]
+                i_z_lower = np.where(entity_ids_lower == entity_id_lower)[0]
+                Deriv[i][i_z] += Deriv_lower[i_low][i_z_lower]
+    return r_idxs, E, Deriv
+
+
+def mbe_contrib(E, Deriv, entity_ids, r_prov_ids, r_prov_specs, E_lower, Deriv_lower, entity_ids_lower,
+                r_prov_ids_lower, r_prov_specs_lower, operation="remove"):
+    """mbe.py:237-429 (use_ray=False branch); updates E and Deriv in place."""
+    if operation not in ("add", "remove"):
+        raise ValueError(f'{operation} is not "add" or "remove"')
+    if (r_prov_ids is not None) and (r_prov_ids != {}):
+        for k, md5 in r_prov_ids_lower.items():
+            assert md5 == r_prov_ids[k]
+    else:
+        n_r = len(E)
+        n_entities = len(set(np.asarray(entity_ids).tolist()))
+        r_prov_specs = np.empty((n_r, 2 + n_entities), dtype=int)
+        r_prov_specs[:, 0] = r_prov_specs_lower[0][0]
+        r_prov_specs[:, 1] = np.arange(n_r)
+        for e in range(n_entities):
+            r_prov_specs[:, e + 2] = e
+    r_idxs = []
+    for k in r_prov_ids_lower.keys():
+        r_idxs.extend(np.where(r_prov_specs[:, 0] == k)[0].tolist())
+    _, E_w, D_w = mbe_worker(Deriv.shape[1:], entity_ids, r_prov_specs, r_idxs, E_lower, Deriv_lower,
+                             entity_ids_lower, r_prov_specs_lower)
+    if operation == "remove":
+        E[r_idxs] -= E_w
+        Deriv[r_idxs] -= D_w
+    else:
+        E[r_idxs] += E_w
+        Deriv[r_idxs] += D_w
+    return E, Deriv
+
+
+def decomp_to_total(E_nbody, F_nbody, entity_ids, entity_combs):
+    """mbe.py:432-508."""
+    entity_ids = np.asarray(entity_ids)
+    n_r = len(np.unique(entity_combs[:, 0]))
+    E = np.zeros((n_r,))
+    F = np.zeros((n_r, len(entity_ids), 3))
+    entity_ids_lower = []
+    for i in range(len(entity_combs[0][1:])):
+        entity_ids_lower.extend([i] * np.count_nonzero(entity_ids == i))
+    r_prov_specs_lower = np.hstack((np.zeros((len(entity_combs), 1)), entity_combs))
+    E_nbody = np.nan_to_num(E_nbody, copy=True, nan=0.0)
+    F_nbody = np.nan_to_num(F_nbody, copy=True, nan=0.0)
+    return mbe_contrib(E, F, entity_ids, None, None, E_nbody, F_nbody, np.array(entity_ids_lower), {0: ""},
+                       r_prov_specs_lower, operation="add")
