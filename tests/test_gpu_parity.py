@@ -405,3 +405,75 @@ def test_errors_surface_as_reference_exceptions():
         mb.predict_gdml(Z, R, eids, [(0, 1)], bad)
     E, F = mb.predict_gdml(Z, R, eids, [], model)  # empty fragment list -> zeros (gdml_predict.py:198-199)
     assert E == 0.0 and not F.any()
+
+
+class _FakeAtoms:
+    """The five ase.Atoms methods mbeCalculator.calculate uses (ASE is not part of the image)."""
+
+    def __init__(self, Z, R, cell):
+        self.Z, self.R, self.cell = np.array(Z), np.array(R, dtype=float), np.array(cell, dtype=float)
+        self.wrapped = False
+
+    def wrap(self):  # ase.Atoms.wrap for an orthorhombic cell
+        L = np.diag(self.cell)
+        self.R = self.R - L * np.floor(self.R / L)
+        self.wrapped = True
+
+    def copy(self):
+        return _FakeAtoms(self.Z, self.R, self.cell)
+
+    def get_cell(self):
+        return self.cell
+
+    def get_atomic_numbers(self):
+        return self.Z
+
+    def get_positions(self):
+        return self.R
+
+
+def test_ase_calculator_front_end():
+    """interfaces/ase.py:65-108: wrap, refresh the cell (cutoff reset to L/2), force stress, unit conversion."""
+    from mbgdml_b200.interfaces import mbeCalculator
+
+    g = load("periodic_40h2o.npz")
+    mds = unpack_models(g)
+    models = b200_models(mds, cutoffs_from(g["crit_cutoffs"]))
+    Z, R, eids, cids, cell_v = g["cub_Z"], g["cub_R"][0], g["cub_eids"], g["cub_cids"], g["cub_cell"]
+    pred = mb.mbePredict(models, mb.predict_gdml, periodic_cell=mb.Cell(cell_v, cutoff=3.0, pbc=True))
+    calc = mbeCalculator(pred, parameters={"entity_ids": eids, "comp_ids": cids}, e_conv=0.5, f_conv=2.0)
+    atoms = _FakeAtoms(Z, R + 2 * cell_v[0], cell_v)  # outside the box: calculate() wraps
+    calc.calculate(atoms)
+    assert atoms.wrapped and pred.compute_stress and pred.use_voigt
+    assert pred.periodic_cell.cutoff == np.min(np.linalg.norm(cell_v, axis=1)) / 2  # user cutoff silently reset
+    ref = mb.mbePredict(models, mb.predict_gdml, periodic_cell=mb.Cell(cell_v, pbc=True), compute_stress=True)
+    ref.use_voigt = True
+    E, F, S = ref.predict(Z, R, eids, cids)
+    assert abs(calc.results["energy"] - 0.5 * E[0]) <= 1e-9 * abs(E[0])
+    assert relerr(calc.results["forces"], 2.0 * F[0]) <= 1e-9
+    assert calc.results["stress"].shape == (6,) and relerr(calc.results["stress"], 0.5 * S[0]) <= 1e-9
+    assert calc.todict()["comp_ids"] == list(cids)
+
+
+def test_sgdml_bulk_predictor():
+    """GDMLPredict.predict (_gdml/predict.py:1031-1182): M geometries of one molecule in one call."""
+    from mbgdml_b200.gdml_predict import GDMLPredict
+
+    md = synthetic.make_model(["h2o", "meoh"], n_train=77, sig=25.0, seed=4, c=-3.0, std=1.7, use_E=True)
+    rng = np.random.default_rng(8)
+    R = synthetic.fragment_geometries(rng, ["h2o", "meoh"], 40).reshape(40, -1)
+    gp = GDMLPredict(dict(md))
+    E, F = gp.predict(R)
+    (F_only,) = gp.predict(R[3], return_E=False)
+    om = orc.Model(dict(md))
+    eids = np.zeros(9, dtype=int)
+    for i in range(40):
+        e_o, f_o = orc.predict_gdml(md["z"], R[i].reshape(9, 3), eids, [(0,)], _single_entity(om))[:2]
+        assert abs(E[i] - e_o) <= TOL * max(abs(e_o), 1.0) and relerr(F[i], f_o.ravel()) <= TOL
+    assert relerr(F_only[0], F[3]) <= 1e-12
+
+
+def _single_entity(om):
+    om.nbody_order = 1
+    om.comp_ids = np.array(["mol"])
+    return om
