@@ -121,7 +121,10 @@ static cudaEvent_t next_event(mbg_context_t ctx) {
 // ------------------------------------------------------------------------------------
 // kernel dispatch tables (one instantiation per supported fragment size)
 // ------------------------------------------------------------------------------------
-#define MBG_FOR_EACH_NA(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+// fragment sizes with kernels: culling + tensor-pipe contraction for 2..18 atoms (water/methanol trimers reach 18),
+// FMA-pipe contraction for 2..9
+#define MBG_FOR_EACH_NA_FMA(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+#define MBG_FOR_EACH_NA(X) MBG_FOR_EACH_NA_FMA(X) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18)
 
 static bool na_supported(int na) {
   switch (na) {
@@ -216,7 +219,7 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
   switch (na) {
 #define X(N)                                                                                        \
   case N: {                                                                                         \
-    constexpr int MT = (N >= 8) ? 3 : 4;                                                            \
+    constexpr int MT = (N >= 13) ? 1 : (N >= 10) ? 2 : (N >= 8) ? 3 : 4;                            \
     return use_E ? launch_matern_mma_t<N, MT, 256, 1, true>(ctx, a) : launch_matern_mma_t<N, MT, 256, 1, false>(ctx, a); \
   }
     MBG_FOR_EACH_NA(X)
@@ -231,10 +234,10 @@ static int launch_matern(mbg_context_t ctx, int na, bool use_E, const MaternArgs
 #define X(N) \
   case N:    \
     return use_E ? launch_matern_t<N, true>(ctx, a) : launch_matern_t<N, false>(ctx, a);
-    MBG_FOR_EACH_NA(X)
+    MBG_FOR_EACH_NA_FMA(X)
 #undef X
     default:
-      return fail(MBG_ERR_UNSUPPORTED, "no contraction kernel for fragments of %d atoms", na);
+      return fail(MBG_ERR_UNSUPPORTED, "no FMA-pipe contraction kernel for fragments of %d atoms (use MBG_CONTRACT_DMMA / AUTO)", na);
   }
 }
 
@@ -548,7 +551,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
                                                                          NA * 3, out.E, out.F);
       ctx->launches++;
     }
-    if (ctx->contraction != MBG_CONTRACT_FMA) {
+    if (ctx->contraction != MBG_CONTRACT_FMA) {  // AUTO = DMMA for every fragment size
       MaternMmaArgs a;
       a.sys = s;
       a.R = dR;
@@ -848,8 +851,8 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   {
     // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row 5|X'|^2 and X'.A_s,
     // packed per tile of 64 rows; side arrays in column order (column j of a block <-> row tau(j)).
-    static_assert(kTileRows % kMmaTileRows == 0, "T_pad (multiple of kTileRows) must be whole DMMA tiles");
-    const int Dq = mma_row_pad(d->n_atoms), TILE = mma_tile_doubles(d->n_atoms), TRm = kMmaTileRows;
+    static_assert(kTileRows % 32 == 0, "T_pad (multiple of kTileRows) must be whole DMMA tiles of 16 or 32 rows");
+    const int Dq = mma_row_pad(d->n_atoms), TILE = mma_tile_doubles(d->n_atoms), TRm = mma_tile_rows(d->n_atoms);
     std::vector<double> mu(D, 0.0);
     for (int e = 0; e < D; ++e) {
       long double acc = 0;

@@ -38,26 +38,27 @@ template <int NA>
 struct MmaShape {
   static constexpr int D = NA * (NA - 1) / 2;
   static constexpr int KS = (D + 3) / 4;                      // k-steps of GEMM 1
-  static constexpr int NT = (D + 7) / 8;                      // n-tiles of GEMM 2
+  static constexpr int NT = (D + 8) / 8;                      // n-tiles of GEMM 2: D columns + the spare column D (s1)
   static constexpr int Dp = (D + 1 <= 4) ? 4 : ((D + 1 - 4 + 7) / 8 * 8 + 4);  // row length: > D and = 4 (mod 8)
-  static_assert(Dp >= 4 * KS && Dp > D && Dp % 8 == 4 && D % 8 != 0, "row padding / spare column");
+  static_assert(Dp >= 4 * KS && Dp > D && Dp % 8 == 4, "row padding / spare column");
 };
 
-constexpr int kMmaTileRows = 32;
 constexpr int kMmaStages = 3;  // tile buffers in flight
 constexpr int kMmaExpTable = 1024;  // entries of the 2^(j/1024) table (shared memory)
 __host__ __device__ constexpr int mma_row_pad(int na) {
   const int D = na * (na - 1) / 2;
   return (D + 1 <= 4) ? 4 : ((D + 1 - 4 + 7) / 8 * 8 + 4);
 }
+// training rows per TMA tile: 32, or 16 for the widest descriptors (three tiles in flight must fit shared memory)
+__host__ __device__ constexpr int mma_tile_rows(int na) { return mma_row_pad(na) <= 108 ? 32 : 16; }
 // doubles per packed tile: two planes, (xx5, xa) per row, alphas_E per row
-__host__ __device__ constexpr int mma_tile_doubles(int na) { return kMmaTileRows * (2 * mma_row_pad(na) + 3); }
+__host__ __device__ constexpr int mma_tile_doubles(int na) { return mma_tile_rows(na) * (2 * mma_row_pad(na) + 3); }
 __host__ __device__ constexpr int mma_tau(int j) { return j < 4 ? j : (j ^ 1); }  // {0,1,2,3,5,4,7,6}
 
 struct MaternMmaArgs {
   SysDev sys;
   const double* R;           // [n_frames][n_atoms][3]
-  const double* tiles;       // [T_pad/64][mma_tile_doubles]
+  const double* tiles;       // [T_pad / mma_tile_rows][mma_tile_doubles]
   const double* mu;          // [D] centre of the training descriptors
   const double* exp2_table;  // [1024] 2^(j/1024)
   const int* iperm;          // [P][D]: pi_p^-1
@@ -155,7 +156,7 @@ template <int NA, int MT, int NTHR, int MINB, bool USE_E>
 __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a) {
   using S = MmaShape<NA>;
   constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
-  constexpr int TR = kMmaTileRows, ST = kMmaStages, BPT = TR / 8;  // BPT: row blocks per tile
+  constexpr int TR = mma_tile_rows(NA), ST = kMmaStages, BPT = TR / 8;  // BPT: row blocks per tile
   constexpr int TILE = mma_tile_doubles(NA);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -417,6 +418,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a
 #pragma unroll
     for (int c = 0; c < NC; ++c) r_[c] = vfma(g_[c], k64, -t_[c]);
     G1(8);
+#pragma unroll
+    for (int k = 9; k < KS; ++k) G1(k);  // wide descriptors (D > 36): the remaining k-steps
     // exp(r c) - 1, c = ln2/1024, |r c| <= 3.4e-4: degree 3 (truncation 5.4e-16)
 #pragma unroll
     for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], 5.1692229383458926e-11, 2.2909784980688164e-07);
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a
   for (int i = 0; i < MT; ++i) {
     // s1 = sum_t w: column D of Gacc (the X' plane holds 1.0 there, the A_s plane 0.0), owned by lane 4 g + (D % 8) / 2
     double eq = Eacc[i], e2q = E2[i];
-    const double s1q = __shfl_sync(0xffffffffu, G[i][NT - 1][(D % 8) & 1], (lane & ~3) | ((D % 8) >> 1));
+    const double s1q = __shfl_sync(0xffffffffu, G[i][D / 8][(D % 8) & 1], (lane & ~3) | ((D % 8) >> 1));
     eq += __shfl_xor_sync(0xffffffffu, eq, 1);
     eq += __shfl_xor_sync(0xffffffffu, eq, 2);
     if (USE_E) {

@@ -190,19 +190,45 @@ def test_r_mic_operator():
         assert 0 < n_none < 40
 
 
-def test_mixed_water_methanol_small_fragments():
-    """Heterogeneous comp_ids; models of up to 9 atoms (larger fragments: see test_wide_fragments)."""
+def test_mixed_water_methanol(contraction):
+    """BASELINE config 5 shape: heterogeneous comp_ids, 8 models with fragments of 3..15 atoms (D up to 105),
+    alchemical 3-body factor; reference outputs from the golden fixture.  Fragments above 9 atoms exist on the
+    tensor-pipe kernel only: with the FMA-pipe kernel selected they must raise (no CPU fallback)."""
     g = load("mixed_h2o_meoh.npz")
-    mds = [m for m in unpack_models(g) if len(m["z"]) <= 9]
-    assert len(mds) == 5
+    mds = unpack_models(g)
+    assert sorted(len(m["z"]) for m in mds) == [3, 6, 6, 9, 9, 12, 12, 15]
     for tag in ("", "2"):
         Z, R, eids, cids = g["Z" + tag], g["R" + tag], g["entity_ids" + tag], g["comp_ids" + tag]
         al_rows = g["alch"] if tag == "" else []
-        E, F = mb.mbePredict(b200_models(mds, [None] * 5), mb.predict_gdml, alchemy_scalers=alch(al_rows)).predict(
-            Z, R, eids, cids)
-        Eo, Fo = orc.mbe_predict(oracle_models(mds, [None] * 5), Z, R, eids, cids,
-                                 alchemy_scalers=[orc.AlchemyScale(int(e), int(o), float(f)) for e, o, f in al_rows])
-        assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+        pred = mb.mbePredict(b200_models(mds, [None] * len(mds)), mb.predict_gdml, alchemy_scalers=alch(al_rows))
+        if contraction == "fma":
+            with pytest.raises(NotImplementedError):
+                pred.predict(Z, R, eids, cids)
+            small = [m for m in mds if len(m["z"]) <= 9]
+            E, F = mb.mbePredict(b200_models(small, [None] * 5), mb.predict_gdml, alchemy_scalers=alch(al_rows)).predict(
+                Z, R, eids, cids)
+            Eo, Fo = orc.mbe_predict(oracle_models(small, [None] * 5), Z, R, eids, cids,
+                                     alchemy_scalers=[orc.AlchemyScale(int(e), int(o), float(f)) for e, o, f in al_rows])
+            assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+            continue
+        E, F = pred.predict(Z, R, eids, cids)
+        assert relerr(E, g["E" + tag]) <= TOL and relerr(F, g["F" + tag]) <= TOL  # live reference outputs
+
+
+def test_widest_fragments_three_methanols(contraction):
+    """18-atom fragments (D = 153, P capped at 100 like _gdml/perm.py:275): the widest kernel instantiation."""
+    md = synthetic.make_model(["meoh", "meoh", "meoh"], n_train=21, sig=300.0, seed=12, c=0.7, std=1.3)
+    assert md["perms"].shape == (100, 18)
+    Z, R, eids, cids = synthetic.make_cluster(4, seed=3, spacing=4.2, comp=["meoh"] * 4)
+    pred = mb.mbePredict([mb.gdmlModel(dict(md))], mb.predict_gdml)
+    if contraction == "fma":
+        with pytest.raises(NotImplementedError):
+            pred.predict(Z, R, eids, cids)
+        return
+    E, F = pred.predict(Z, R, eids, cids)
+    Eo, Fo = orc.mbe_predict([orc.Model(dict(md))], Z, R[None], eids, cids)
+    assert pred.last_stats[0][2] == 4
+    assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
 
 
 def test_reference_known_answers_on_device():
@@ -364,9 +390,11 @@ def test_full_size_properties_140_h2o_periodic_box(contraction):
     (["hf"], 5), (["h2o"], 1), (["nh3"], 8), (["hf", "hf"], 9), (["ch4"], 31), (["hf", "h2o"], 33),
     (["meoh"], 64), (["h2o", "h2o"], 65), (["nh3", "h2o"], 7), (["nh3", "nh3"], 40), (["ch4", "h2o"], 17),
     (["h2o", "h2o", "h2o"], 100), (["hf", "hf", "ch4"], 23), (["h2o", "meoh"], 129),
+    (["ch4", "ch4"], 12), (["ch4", "meoh"], 19), (["meoh", "meoh"], 33), (["nh3", "nh3", "ch4"], 9),
+    (["nh3", "ch4", "ch4"], 26), (["ch4", "ch4", "ch4"], 8), (["ch4", "ch4", "meoh"], 41), (["ch4", "meoh", "meoh"], 15),
 ])
-def test_every_fragment_size_and_ragged_train_sizes(family, n_train):
-    """Fragments of 2..9 atoms (every kernel instantiation) with training-set sizes that are not multiples of
+def test_every_fragment_size_and_ragged_train_sizes(family, n_train, contraction):
+    """Fragments of 2..17 atoms (every kernel instantiation; 18 atoms: test_widest_fragments_three_methanols) with training-set sizes that are not multiples of
     the 8-row block / 32- and 64-row tiles, with and without alphas_E, against the NumPy oracle."""
     comps = list(dict.fromkeys(family))  # entity ids ascend in the model's component order (gen_combs keeps only ascending tuples)
     n_each = 4 if len(family) < 3 else 3
@@ -375,6 +403,10 @@ def test_every_fragment_size_and_ragged_train_sizes(family, n_train):
     for use_E in (False, True):
         md = synthetic.make_model(family, n_train=n_train, sig=37.0, seed=3, c=-1.5, std=2.25, use_E=use_E)
         pred = mb.mbePredict([mb.gdmlModel(dict(md))], mb.predict_gdml)
+        if contraction == "fma" and len(md["z"]) > 9:  # the FMA-pipe kernel exists for 2..9 atoms only
+            with pytest.raises(NotImplementedError):
+                pred.predict(Z, R, eids, cids)
+            continue
         E, F = pred.predict(Z, R, eids, cids)
         Eo, Fo = orc.mbe_predict([orc.Model(dict(md))], Z, R[None], eids, cids)
         assert pred.last_stats[0][2] > 0
