@@ -10,6 +10,7 @@ one batch of synthetic frames.  Workloads (BASELINE.json configs):
            scaling, n_train = 1000 models, --frames frames per GPU per step (config 4, weak scaling)
   trimers64  64-H2O cluster, 3-body model only, 41,664 trimers per frame (config 3)
   monomers   1-body water model on 100,000 monomer structures (config 2)
+  mixed140   100 H2O + 40 MeOH periodic box, 9 models with fragments of 3..18 atoms (config 5)
 
 `value` is measured with the inputs resident in HBM (device pointers through the C ABI, CUDA events);
 `e2e` goes through the public mbePredict.predict call with pinned HOST buffers (H2D + D2H inside the
@@ -52,6 +53,18 @@ def make_workload(name, n_frames, n_train=1000):
         w["alchemy"] = [(0, 3, 0.5), (0, 2, 0.5)]
         w["label"] = (f"140-H2O periodic box L=16.12 A, MIC cutoff L/2, 1+2+3-body MBE, criteria "
                       f"com_distance_sum None/6.0/10.0, alchemical factor 0.5, n_train={n_train}")
+    elif name == "mixed140":
+        comp = ["h2o"] * 100 + ["meoh"] * 40
+        Z, R, eids, cids, cell = syn.make_periodic_box(n_mol=140, box=17.8, n_frames=n_frames, seed=0, comp=comp,
+                                                       frame_sigma=0.1)
+        w.update(Z=Z, R=R, eids=eids, cids=cids, cell=cell)
+        w["families"] = [["h2o"], ["meoh"], ["h2o", "h2o"], ["h2o", "meoh"], ["meoh", "meoh"], ["h2o", "h2o", "h2o"],
+                         ["h2o", "h2o", "meoh"], ["h2o", "meoh", "meoh"], ["meoh", "meoh", "meoh"]]
+        w["sigs"] = [10.0, 20.0, 100.0, 120.0, 150.0, 400.0, 420.0, 450.0, 500.0]
+        w["cutoffs"] = [None, None, 6.0, 6.5, 7.0, 10.0, 10.5, 11.0, 11.5]
+        w["alchemy"] = [(100, 3, 0.5)]
+        w["label"] = (f"100 H2O + 40 MeOH periodic box L=17.8 A, 9 models (fragments of 3..18 atoms), MIC cutoff L/2, "
+                      f"criteria com_distance_sum, alchemical 3-body factor 0.5 on one methanol, n_train={n_train}")
     elif name == "trimers64":
         Z, R0, eids, cids = syn.make_cluster(64, seed=0)
         w.update(Z=Z, R=syn.jitter_frames(R0, n_frames, sigma=0.02, seed=0), eids=eids, cids=cids, cell=None)
@@ -184,7 +197,7 @@ def cpu_reference_pass(w, n_candidates, pool, cores):
 
 def cpu_sample_size(w):
     """Candidate tuples per CPU sample: ~10-20 s of work on 16 host cores (the GPU does all of them)."""
-    return {"box140": 200000, "trimers64": 6000, "monomers": 100000}[w["name"]]
+    return {"box140": 200000, "trimers64": 6000, "monomers": 100000, "mixed140": 60000}[w["name"]]
 
 
 def ncu_traffic(workload, n_frag_atoms, frames, use_dmma):
@@ -359,12 +372,16 @@ def run_gpu_arm(args):
         return
 
     # roofline of the dominant kernel (the contraction launch with the most work in the last step)
-    wfrag = {len(d["z"]): flops_per_fragment(d) for d in w["model_dicts"]}
-    best = max(recs, key=lambda r: r["n_fragments"] * wfrag[r["n_frag_atoms"]]) if recs else None
+    def rec_flops(r):  # W_frag = T * P * (9 D + 10) of the model this launch contracted against
+        n = r["n_frag_atoms"]
+        return args.n_train * r["n_perms"] * (9 * (n * (n - 1) // 2) + 10)
+
+    wfrag = {r["n_frag_atoms"]: rec_flops(r) for r in recs}
+    best = max(recs, key=lambda r: r["n_fragments"] * rec_flops(r)) if recs else None
     roofline = None
     if best and best["ms"] > 0:
-        dom = [r for r in recs if r["n_frag_atoms"] == best["n_frag_atoms"]]
-        flop = sum(r["n_fragments"] * wfrag[r["n_frag_atoms"]] for r in dom)
+        dom = [r for r in recs if (r["n_frag_atoms"], r["n_perms"]) == (best["n_frag_atoms"], best["n_perms"])]
+        flop = sum(r["n_fragments"] * rec_flops(r) for r in dom)
         ms = sum(r["ms"] for r in dom)
         achieved = flop / (ms * 1e-3) / 1e12
         kname = f"k_matern_mma<NA={best['n_frag_atoms']}>" if use_dmma else f"k_matern<NA={best['n_frag_atoms']}>"
@@ -373,7 +390,7 @@ def run_gpu_arm(args):
             "frac": achieved / peak_tflops if peak_tflops else None,
             "traffic": ncu_traffic(args.workload, best["n_frag_atoms"], args.frames, use_dmma),
             "kernel": kname, "launches_in_step": len(dom),
-            "avg_launch_ms": ms / len(dom), "alg_flop_per_fragment": wfrag[best["n_frag_atoms"]],
+            "avg_launch_ms": ms / len(dom), "alg_flop_per_fragment": rec_flops(best),
             "fragments_per_launch": sum(r["n_fragments"] for r in dom) / len(dom),
             "pipe": ("FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA.8x8x4)" if use_dmma else "FP64 FMA pipe (DFMA)"),
             "peak_source": "measured live on this GPU, CUDA events: back-to-back DMMA m8n8k4 on 8 independent accumulators "
@@ -421,6 +438,10 @@ def run_gpu_arm(args):
                 "h2d_bytes_per_step": int(R_host.nbytes), "d2h_bytes_per_step": int(8 * n_frames * (1 + 3 * n_atoms))},
         "gpu_launches": int(nl.item()), "clocks": clocks,
         "fp64_peak_tflops_measured": {"fma_pipe": peak_fma, "tensor_pipe": peak_dmma},
+        "contraction_launches": [
+            {"n_frag_atoms": r["n_frag_atoms"], "n_perms": r["n_perms"], "n_fragments": r["n_fragments"], "ms": round(r["ms"], 4),
+             "tflops": round(r["n_fragments"] * rec_flops(r) / (r["ms"] * 1e-3) / 1e12, 2) if r["ms"] > 0 else None}
+            for r in recs],
         "sm_clock_mhz_implied_by_fma_peak": clk_est, "contraction": "dmma" if use_dmma else "fma",
     }
     print(json.dumps(line))
@@ -434,7 +455,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="box140", choices=["box140", "trimers64", "monomers"])
+    ap.add_argument("--workload", default="box140", choices=["box140", "trimers64", "monomers", "mixed140"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--n-train", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -442,7 +463,7 @@ def main():
                     help="contraction kernel: FP64 tensor pipe (dmma, default) or FMA pipe (fma)")
     args = ap.parse_args()
     if args.frames is None:
-        args.frames = {"box140": 8, "trimers64": 4, "monomers": 1}[args.workload]
+        args.frames = {"box140": 8, "trimers64": 4, "monomers": 1, "mixed140": 4}[args.workload]
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -183,6 +183,8 @@ def make_periodic_box(n_mol=140, box=16.12, n_frames=1, seed=0, comp="h2o", fram
     a = box / side
     centres = (sites[pick] + 0.5) * a + rng.uniform(-0.15, 0.15, size=(n_mol, 3))
     comp_list = [comp] * n_mol if isinstance(comp, str) else list(comp)
+    if not isinstance(comp, str):  # mixtures: species are listed in blocks (entity ids), but mixed in space
+        centres = centres[rng.permutation(n_mol)]
     z, r0, eids, comp_ids = _place(rng, comp_list, centres)
     R = r0[None] + rng.normal(scale=frame_sigma, size=(n_frames,) + r0.shape)
     R = np.mod(R, box)
