@@ -428,6 +428,46 @@ def case_mbe_contrib():
     print("  mbe_contrib add x3 (known answer reproduced), remove with missing fragments, decomp_to_total: bit-exact")
 
 
+def case_train_kernel():
+    """analysis.models.gdml_mat52 (analysis/models.py:31-139) and the force-field kernel matrix
+    GDMLTrain._assemble_kernel_mat (_gdml/train.py:92-292, 1105-1337), outputs of the live reference."""
+    from mbgdml._gdml.train import GDMLTrain  # the reference
+    from mbgdml.analysis.models import gdml_mat52
+
+    trainer = GDMLTrain(max_processes=1)
+    out = {}
+    cases = [("h2o", ["h2o"], 14, 7.0, 0), ("h2o2", ["h2o", "h2o"], 9, 20.0, 1), ("h2o3", ["h2o", "h2o", "h2o"], 4, 35.0, 2),
+             ("meoh", ["meoh"], 6, 12.0, 3)]
+    for name, comp, T, sig, seed in cases:
+        rng = np.random.default_rng(100 + seed)
+        Rt = syn.fragment_geometries(rng, comp, T)
+        n = Rt.shape[1]
+        desc = Desc(n, max_processes=1)
+        R_desc, R_d_desc = desc.from_R(Rt.reshape(T, -1))
+        perms = syn.fragment_perms(comp)
+        tpl = orc.tril_perms_lin_from_perms(perms)
+        out.update({f"{name}_R": Rt, f"{name}_R_desc": R_desc, f"{name}_R_d_desc": R_d_desc, f"{name}_perms": perms,
+                    f"{name}_tril_perms_lin": tpl, f"{name}_sig": np.array(sig)})
+        for use_E in (False, True):
+            K_ref = np.array(trainer._assemble_kernel_mat(R_desc, R_d_desc, tpl, sig, desc, use_E_cstr=use_E))
+            K_orc = orc.assemble_kernel_mat(R_desc, R_d_desc, tpl, sig, use_E_cstr=use_E)
+            check(f"kernel_mat {name} use_E={use_E}", K_orc, K_ref, tol=1e-11)
+            out[f"{name}_K_E{int(use_E)}"] = K_ref
+    # covariances vs. the training set on the prediction models (monomer, dimer, trimer; 1 and 5 structures)
+    for k, comp in enumerate((["h2o"], ["h2o", "h2o"], ["h2o", "h2o", "h2o"])):
+        md = syn.make_model(comp, n_train=40, sig=[10.0, 100.0, 400.0][k], seed=20 + k)
+        rng = np.random.default_rng(300 + k)
+        Rq = syn.fragment_geometries(rng, comp, 5)
+        ref_m, orc_m = gdmlModel(dict(md)), orc.Model(dict(md))
+        for tag, R in (("1", Rq[0]), ("5", Rq)):
+            want = gdml_mat52(ref_m, md["z"], R)
+            check(f"mat52 {len(comp)}-body n_R={tag}", orc.gdml_mat52(orc_m, md["z"], R), want, tol=1e-13)
+            out[f"mat52_{k}_R{tag}"] = R
+            out[f"mat52_{k}_out{tag}"] = want
+        out.update({f"mat52_{k}_{kk}": v for kk, v in slim(md).items()})
+    np.savez_compressed(os.path.join(GOLD, "train_kernel.npz"), **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="raise", under="ignore")
     print("gen_combs"); case_gen_combs()
@@ -437,5 +477,6 @@ if __name__ == "__main__":
     print("mixed"); case_mixed()
     print("reference fixtures"); case_reference_fixtures()
     print("mbe_contrib"); case_mbe_contrib()
+    print("train kernel"); case_train_kernel()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden fixtures written: %.1f KB" % (total / 1024))

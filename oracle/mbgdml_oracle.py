@@ -593,3 +593,79 @@ def decomp_to_total(E_nbody, F_nbody, entity_ids, entity_combs):
     F_nbody = np.nan_to_num(F_nbody, copy=True, nan=0.0)
     return mbe_contrib(E, F, entity_ids, None, None, E_nbody, F_nbody, np.array(entity_ids_lower), {0: ""},
                        r_prov_specs_lower, operation="add")
+
+
+# --------------------------------------------------------------------------
+# Matern-5/2 covariance of structures vs. the training set, and the
+# force-field kernel matrix of the closed-form trainer
+# --------------------------------------------------------------------------
+def gdml_mat52(model, Z, R):
+    """analysis/models.py:31-139: k_5/2(x, x_j) = (1 + s d + 5 d^2 / (3 sig^2)) exp(-s d), s = sqrt(5)/sig,
+    d = |x - x_j| over the T*P rows of ``R_desc_perms``; (n_R, T*P), or (T*P,) for one structure."""
+    R = np.asarray(R, dtype=np.float64)
+    if R.ndim == 2:
+        R = R[None, ...]
+    sig = float(model.sig)
+    out = np.empty((R.shape[0], model.R_desc_perms.shape[0]))
+    for m in range(R.shape[0]):
+        x, _ = from_r(R[m].reshape(-1), model.lat_and_inv)
+        d = np.linalg.norm(x[None, :] - model.R_desc_perms, axis=1)
+        s = np.sqrt(5.0) / sig
+        out[m] = (1.0 + s * d + 5.0 / (3 * sig**2) * d**2) * np.exp(-s * d)
+    return out[0] if out.shape[0] == 1 else out
+
+
+def d_desc_from_comp(r_d_desc, n_atoms):
+    """desc.py:397-444: compressed Jacobian (D, 3) -> full (D, 3N); row k <-> (i>j): +g at atom j, -g at atom i."""
+    D = n_atoms * (n_atoms - 1) // 2
+    i, j = np.tril_indices(n_atoms, k=-1)
+    out = np.zeros((D, n_atoms, 3))
+    out[np.arange(D), j, :] = r_d_desc
+    out[np.arange(D), i, :] = -r_d_desc
+    return out.reshape(D, 3 * n_atoms)
+
+
+def assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, use_E_cstr=False):
+    """_gdml/train.py:92-292 (worker) and 1105-1337 (driver, ``col_idxs = np.s_[:]``): the Hessian-of-Matern
+    force-field kernel matrix, (T 3N [+T]) square.  R_desc (T, D); R_d_desc (T, D, 3) compressed.
+
+    Block (i, j), j < T (train.py:183-218), with pi_p(k) = tril_perms_lin[k P + p] mod D:
+        diff_p = X_i - X_j[pi_p],  n_p = sqrt(5)|diff_p|,  b_p = exp(-n_p/sig) 5/(3 sig^4),  Jj_p = J_j[pi_p, :]
+        K_ij = J_i^T sum_p [ 5 b_p diff_p (diff_p^T Jj_p) - (sig^2 + sig n_p) b_p Jj_p ]
+    Energy rows/columns (use_E_cstr, train.py:224-289) as written there."""
+    R_desc = np.asarray(R_desc, dtype=np.float64)
+    R_d_desc = np.asarray(R_d_desc, dtype=np.float64)
+    sig = float(sig)
+    T, D = R_desc.shape
+    n = int((1 + np.sqrt(8 * D + 1)) / 2)
+    dim_i = 3 * n
+    P = len(tril_perms_lin) // D
+    pi = (np.asarray(tril_perms_lin).reshape(D, P) % D).T  # pi[p][k]
+    J = np.stack([d_desc_from_comp(R_d_desc[t], n) for t in range(T)])  # (T, D, 3N)
+    rows = T * dim_i + (T if use_E_cstr else 0)
+    K = np.zeros((rows, rows))
+    sqrt5 = np.sqrt(5.0)
+    for j in range(T):
+        Xjp = R_desc[j][pi]  # (P, D)
+        Jjp = J[j][pi]  # (P, D, 3N)
+        for i in range(T):
+            diff = R_desc[i][None, :] - Xjp
+            nrm = sqrt5 * np.linalg.norm(diff, axis=1)
+            b = np.exp(-nrm / sig) / (3 * sig**4) * 5
+            M = np.einsum("pk,pc->kc", diff * (5 * b)[:, None], np.einsum("pk,pkc->pc", diff, Jjp))
+            M -= np.einsum("pkc,p->kc", Jjp, (sig**2 + sig * nrm) * b)
+            K[i * dim_i:(i + 1) * dim_i, j * dim_i:(j + 1) * dim_i] = J[i].T.dot(M)
+            if use_E_cstr:  # train.py:224-239
+                kfe = 5 * diff / (3 * sig**3) * (nrm[:, None] + sig) * np.exp(-nrm / sig)[:, None]
+                K[T * dim_i + i, j * dim_i:(j + 1) * dim_i] = -np.einsum("pk,pkc->c", kfe, Jjp)
+    if use_E_cstr:  # train.py:241-289: columns T 3N + j
+        for j in range(T):
+            for i in range(T):
+                Xip = R_desc[i][pi]
+                Jip = J[i][pi]
+                diff = R_desc[j][None, :] - Xip
+                nrm = sqrt5 * np.linalg.norm(diff, axis=1)
+                kfe = 5 * diff / (3 * sig**3) * (nrm[:, None] + sig) * np.exp(-nrm / sig)[:, None]
+                K[i * dim_i:(i + 1) * dim_i, T * dim_i + j] = -np.einsum("pk,pkc->c", kfe, Jip)
+                K[T * dim_i + i, T * dim_i + j] = -(1 + (nrm / sig) * (1 + nrm / (3 * sig))).dot(np.exp(-nrm / sig))
+    return K
