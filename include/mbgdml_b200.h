@@ -194,6 +194,29 @@ int mbg_mbe_accumulate(mbg_context_t ctx, int64_t n_ref, const int64_t *ref_rows
                        const double *E_lower, const double *Deriv_lower, int64_t n_lower, double sign,
                        double *E, double *Deriv, int64_t n_total);
 
+/* ---- training-side reuse of the distance/exp engine ------------------------------------- */
+
+/* GDMLTrain._assemble_kernel_mat with col_idxs = np.s_[:] (reference mbgdml/_gdml/train.py:1105-1337; worker
+ * _assemble_kernel_mat_wkr, train.py:92-292): the Hessian-of-Matern force-field kernel matrix.
+ *   R_desc[n_train][D], R_d_desc[n_train][D][3] (compressed Jacobian, desc.py:448-480), D = n_atoms(n_atoms-1)/2,
+ *   tril_perms_lin[n_perms * D]  ->  K[rows][rows] row-major, rows = n_train*3*n_atoms (+ n_train with
+ *   use_E_cstr).  One CTA per ordered pair of training points.  Flags: MBG_FLAG_OUT_ON_DEVICE (K is a device
+ *   pointer; the call returns with the work enqueued). */
+int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double *R_desc,
+                   const double *R_d_desc, const int64_t *tril_perms_lin, double sig, int32_t use_E_cstr,
+                   uint32_t flags, double *K);
+
+/* analysis.models.gdml_mat52 (reference mbgdml/analysis/models.py:84-139): Matern-5/2 covariances between
+ * n_R structures R[n_R][model n_atoms][3] and the T*P permuted training descriptors of `model`, in the row
+ * order of gdmlModel.R_desc_perms (row t*P + p, gdml_model.py:109-113): out[n_R][T*P].
+ * Flags: MBG_FLAG_R_ON_DEVICE, MBG_FLAG_OUT_ON_DEVICE. */
+int mbg_mat52(mbg_context_t ctx, mbg_model_t model, const double *R, int64_t n_R, uint32_t flags, double *out);
+
+/* analysis.models.gdml_mat52_wrk (analysis/models.py:31-81) for n_q descriptors r_desc[n_q][dim_d] against
+ * explicit rows[n_rows][dim_d] (an expanded R_desc_perms): out[n_q][n_rows].  Host buffers. */
+int mbg_mat52_rows(mbg_context_t ctx, int32_t dim_d, const double *r_desc, int64_t n_q, double sig,
+                   const double *rows, int64_t n_rows, double *out);
+
 /* Measured FP64 FMA-pipe peak of this GPU (dependent-chain-free DFMA loop, CUDA-event timed),
  * in TFLOP/s: the roofline denominator bench.py reports against. */
 int mbg_measure_fp64_peak(mbg_context_t ctx, double *tflops, double *sm_clock_mhz_est);

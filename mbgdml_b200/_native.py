@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_enumerate",
     "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
+    "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -107,6 +108,10 @@ def load_library():
         lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
         lib.mbg_mbe_accumulate.argtypes = [C.c_void_p, C.c_int64, _lp, _lp, _lp, _ip, C.c_int32, C.c_int32, _ip, _ip,
                                            C.c_int32, _ip, _ip, _dp, _dp, C.c_int64, C.c_double, _dp, _dp, C.c_int64]
+        lib.mbg_kernel_mat.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _lp, C.c_double, C.c_int32,
+                                       C.c_uint32, C.c_void_p]
+        lib.mbg_mat52.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p]
+        lib.mbg_mat52_rows.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int64, C.c_double, _dp, C.c_int64, _dp]
         lib.mbg_measure_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
         lib.mbg_measure_fp64_tensor_peak.argtypes = [C.c_void_p, _dp]
         for name in EXPORTED_SYMBOLS:
@@ -275,6 +280,43 @@ class Context:
             ptr(slot_entity, _ip), n_slots, Deriv.shape[1], ptr(atom_entity, _ip), ptr(atom_rank, _ip), n_atoms_lower,
             ptr(lower_off, _ip), ptr(lower_atoms, _ip), ptr(E_lower, _dp), ptr(Deriv_lower, _dp), len(E_lower),
             float(sign), ptr(E, _dp), ptr(Deriv, _dp), len(E)))
+
+    # -- training-side kernels ---------------------------------------------
+    def kernel_mat(self, R_desc, R_d_desc, tril_perms_lin, sig, use_E_cstr=False, out=None):
+        """Force-field kernel matrix (train.py:1105-1337).  ``out``: optional device pointer (int) of a
+        [rows][rows] float64 buffer; otherwise a host array is returned."""
+        R_desc, R_d_desc = as_f64(R_desc), as_f64(R_d_desc)
+        tpl = np.ascontiguousarray(tril_perms_lin, dtype=np.int64)
+        T, D = R_desc.shape
+        n_atoms = int((1 + np.sqrt(8 * D + 1)) / 2)
+        if n_atoms * (n_atoms - 1) // 2 != D or R_d_desc.shape != (T, D, 3) or tpl.size % D:
+            raise ValueError("R_desc (T, D), R_d_desc (T, D, 3) and tril_perms_lin (P*D,) have inconsistent shapes")
+        P = tpl.size // D
+        rows = T * 3 * n_atoms + (T if use_E_cstr else 0)
+        if out is None:
+            K = np.empty((rows, rows))
+            dst, flags = K.ctypes.data, 0
+        else:
+            K, dst, flags = None, int(out), FLAG_OUT_ON_DEVICE
+        check(self.lib.mbg_kernel_mat(self.handle, n_atoms, T, P, ptr(R_desc, _dp), ptr(R_d_desc, _dp), ptr(tpl, _lp),
+                                      float(sig), int(bool(use_E_cstr)), flags, C.c_void_p(dst)))
+        return K
+
+    def mat52(self, model_handle, R, n_rows):
+        """Covariances of structures R (n_R, n_atoms, 3) vs. the T*P permuted training rows of a device model."""
+        R = as_f64(R)
+        out = np.empty((R.shape[0], n_rows))
+        check(self.lib.mbg_mat52(self.handle, model_handle, C.c_void_p(R.ctypes.data), R.shape[0], 0,
+                                 C.c_void_p(out.ctypes.data)))
+        return out
+
+    def mat52_rows(self, r_desc, sig, rows):
+        r_desc, rows = as_f64(r_desc), as_f64(rows)
+        q = r_desc.reshape(-1, rows.shape[1])
+        out = np.empty((q.shape[0], rows.shape[0]))
+        check(self.lib.mbg_mat52_rows(self.handle, rows.shape[1], ptr(q, _dp), q.shape[0], float(sig), ptr(rows, _dp),
+                                      rows.shape[0], ptr(out, _dp)))
+        return out
 
     def r_mic(self, cell, cutoff, r):
         r = as_f64(r)

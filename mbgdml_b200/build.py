@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmbgdml_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "geom.cuh", "enumerate.cuh", "matern.cuh", "hostmath.h", "matern_mma.cuh", "mbe_accum.cuh",
+HEADERS = ["common.cuh", "geom.cuh", "enumerate.cuh", "matern.cuh", "hostmath.h", "matern_mma.cuh", "mbe_accum.cuh", "kernel_mat.cuh",
            os.path.join("..", "..", "include", "mbgdml_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -15,6 +15,7 @@
 #include "matern.cuh"
 #include "matern_mma.cuh"
 #include "mbe_accum.cuh"
+#include "kernel_mat.cuh"
 
 using namespace mbg;
 
@@ -82,6 +83,7 @@ struct mbg_context_s {
   DevBuf sys_ints, sys_masses, R, outE, outF, outV;
   DevBuf job_ints, job_binom, flags, blk_acc, blk_enum, blk_off, totals;
   DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
+  DevBuf km_in, km_ints, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/1024), j = 0..1023  (DMMA kernel)
   long long* h_totals = nullptr;  // pinned [2]
@@ -739,7 +741,8 @@ int mbg_context_destroy(mbg_context_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints, &ctx->job_binom,
                     &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
-                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma})
+                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
+                    &ctx->km_ints, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_call0);
@@ -1300,6 +1303,156 @@ int mbg_mbe_accumulate(mbg_context_t ctx, int64_t n_ref, const int64_t* ref_rows
   CUDA_TRY(cudaMemcpyAsync(E, a.E, (size_t)n_total * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(Deriv, a.D, (size_t)n_total * n_atoms_ref * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MBG_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// training-side kernels (kernel_mat.cuh)
+// ------------------------------------------------------------------------------------
+// One timed launch record for mbg_context_last_launches (kind 2 = kernel matrix, 3 = covariance).
+static void record_aux_launch(mbg_context_t ctx, cudaEvent_t e0, cudaEvent_t e1, int na, long long units, int T, int P,
+                              int kind) {
+  (void)e0, (void)e1;
+  ctx->launch_recs.push_back({na, units, T, P, 0.f, kind});
+  ctx->n_contract++;
+  ctx->launches++;
+}
+
+int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double* R_desc,
+                   const double* R_d_desc, const int64_t* tril_perms_lin, double sig, int32_t use_E_cstr,
+                   uint32_t flags, double* K) {
+  if (!ctx || !R_desc || !R_d_desc || !tril_perms_lin || !K) return fail(MBG_ERR_ARG, "NULL argument");
+  if (n_atoms < 2 || n_atoms > 18) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: n_atoms=%d outside 2..18", n_atoms);
+  if (n_train < 1 || n_perms < 1) return fail(MBG_ERR_ARG, "n_train and n_perms must be positive");
+  if (n_train > 65535) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: n_train=%d > 65535", n_train);
+  if (!(sig > 0)) return fail(MBG_ERR_ARG, "sig must be positive");
+  if (flags & ~(uint32_t)MBG_FLAG_OUT_ON_DEVICE) return fail(MBG_ERR_UNSUPPORTED, "flag not supported by mbg_kernel_mat");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int N = n_atoms, D = N * (N - 1) / 2, T = n_train, P = n_perms, N3 = 3 * N;
+  // pi_p(k) = tril_perms_lin[k P + p] mod D (train.py:163-167); must be a permutation
+  std::vector<int> tab((size_t)2 * P * D);
+  int* pi = tab.data();
+  int* ipi = tab.data() + (size_t)P * D;
+  for (int p = 0; p < P; ++p) {
+    std::vector<char> seen(D, 0);
+    for (int k = 0; k < D; ++k) {
+      const int64_t lin = tril_perms_lin[(size_t)k * P + p];
+      if (lin < 0 || lin >= (int64_t)P * D) return fail(MBG_ERR_ARG, "tril_perms_lin[%d] out of range", k * P + p);
+      const int e = (int)(lin % D);
+      if (seen[e]) return fail(MBG_ERR_UNSUPPORTED, "tril_perms_lin column %d is not a permutation", p);
+      seen[e] = 1;
+      pi[(size_t)p * D + k] = e, ipi[(size_t)p * D + e] = k;
+    }
+  }
+  const size_t rows = (size_t)T * N3 + (use_E_cstr ? T : 0);
+  const size_t nX = (size_t)T * D, nG = (size_t)T * D * 3;
+  begin_call(ctx);
+  TRY(ctx->km_in.ensure((nX + nG) * sizeof(double)));
+  TRY(ctx->km_ints.ensure(tab.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->km_in.p, R_desc, nX * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->km_in.as<double>() + nX, R_d_desc, nG * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->km_ints.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  double* dK = K;
+  const bool out_dev = (flags & MBG_FLAG_OUT_ON_DEVICE) != 0;
+  if (!out_dev) {
+    TRY(ctx->km_out.ensure(rows * rows * sizeof(double)));
+    dK = ctx->km_out.as<double>();
+  }
+  KernelMatArgs a;
+  a.n_atoms = N, a.D = D, a.T = T, a.P = P, a.sig = sig, a.use_E = use_E_cstr ? 1 : 0;
+  a.X = ctx->km_in.as<double>(), a.G = ctx->km_in.as<double>() + nX;
+  a.pi = ctx->km_ints.as<int>(), a.ipi = ctx->km_ints.as<int>() + (size_t)P * D;
+  a.K = dK, a.ld = (long long)rows;
+  const size_t smem = kernel_mat_smem_bytes(N);
+  const int n_out = (N3 * N3 + kKmThreads - 1) / kKmThreads;
+  void (*kern)(KernelMatArgs) = n_out <= 3 ? k_kernel_mat<3> : (n_out <= 6 ? k_kernel_mat<6> : k_kernel_mat<kKmMaxOut>);
+  if (n_out > kKmMaxOut) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: block too large");
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+  kern<<<dim3(T, T), kKmThreads, smem, ctx->stream>>>(a);
+  cudaEventRecord(e1, ctx->stream);
+  CUDA_TRY(cudaGetLastError());
+  record_aux_launch(ctx, e0, e1, N, (long long)T * T, T, P, 2);
+  if (!out_dev) {
+    CUDA_TRY(cudaMemcpyAsync(K, dK, rows * rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  end_call_timing(ctx);
+  return MBG_OK;
+}
+
+static int launch_mat52(mbg_context_t ctx, Mat52Args a, int64_t n_q, int na_rec) {
+  if (n_q > 65535) return fail(MBG_ERR_UNSUPPORTED, "covariance: more than 65535 query structures per call");
+  const size_t smem = ((size_t)a.D + (size_t)kM52Rows * (a.D + 1)) * sizeof(double);
+  if (smem > 200 * 1024) return fail(MBG_ERR_UNSUPPORTED, "covariance: descriptor dimension %d too large", a.D);
+  CUDA_TRY(cudaFuncSetAttribute(k_mat52, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+  k_mat52<<<dim3((a.T + kM52Rows - 1) / kM52Rows, (unsigned)n_q), kM52Threads, smem, ctx->stream>>>(a);
+  cudaEventRecord(e1, ctx->stream);
+  CUDA_TRY(cudaGetLastError());
+  record_aux_launch(ctx, e0, e1, na_rec, (long long)n_q * a.T * a.P, a.T, a.P, 3);
+  return MBG_OK;
+}
+
+int mbg_mat52(mbg_context_t ctx, mbg_model_t m, const double* R, int64_t n_R, uint32_t flags, double* out) {
+  if (!ctx || !m || !R || !out) return fail(MBG_ERR_ARG, "NULL argument");
+  if (n_R < 0) return fail(MBG_ERR_ARG, "negative count");
+  if (flags & ~(uint32_t)(MBG_FLAG_R_ON_DEVICE | MBG_FLAG_OUT_ON_DEVICE))
+    return fail(MBG_ERR_UNSUPPORTED, "flag not supported by mbg_mat52");
+  if (n_R == 0) return MBG_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  const size_t nR = (size_t)n_R * m->n_atoms * 3, nOut = (size_t)n_R * m->T * m->P;
+  const double* dR = R;
+  if (!(flags & MBG_FLAG_R_ON_DEVICE)) {
+    TRY(ctx->km_in.ensure(nR * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->km_in.p, R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dR = ctx->km_in.as<double>();
+  }
+  double* dOut = out;
+  const bool out_dev = (flags & MBG_FLAG_OUT_ON_DEVICE) != 0;
+  if (!out_dev) {
+    TRY(ctx->km_out.ensure(nOut * sizeof(double)));
+    dOut = ctx->km_out.as<double>();
+  }
+  Mat52Args a;
+  a.n_atoms = m->n_atoms, a.D = m->D, a.T = m->T, a.P = m->P, a.sig = m->sig;
+  a.Q = dR, a.q_is_desc = 0;
+  a.X = reinterpret_cast<const double*>(m->XA), a.x_row_stride = 2ll * model_row_pad(m->n_atoms), a.x_elem_stride = 2;
+  a.iperm = m->iperm, a.out = dOut;
+  TRY(launch_mat52(ctx, a, n_R, m->n_atoms));
+  if (!out_dev) {
+    CUDA_TRY(cudaMemcpyAsync(out, dOut, nOut * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  end_call_timing(ctx);
+  return MBG_OK;
+}
+
+int mbg_mat52_rows(mbg_context_t ctx, int32_t dim_d, const double* r_desc, int64_t n_q, double sig, const double* rows,
+                   int64_t n_rows, double* out) {
+  if (!ctx || !r_desc || !rows || !out) return fail(MBG_ERR_ARG, "NULL argument");
+  if (dim_d < 1 || n_q < 0 || n_rows < 0 || n_rows > 0x7fffffff) return fail(MBG_ERR_ARG, "bad sizes");
+  if (!(sig > 0)) return fail(MBG_ERR_ARG, "sig must be positive");
+  if (n_q == 0 || n_rows == 0) return MBG_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  const size_t nQ = (size_t)n_q * dim_d, nX = (size_t)n_rows * dim_d, nOut = (size_t)n_q * n_rows;
+  TRY(ctx->km_in.ensure((nQ + nX) * sizeof(double)));
+  TRY(ctx->km_out.ensure(nOut * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->km_in.p, r_desc, nQ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->km_in.as<double>() + nQ, rows, nX * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  Mat52Args a;
+  a.n_atoms = 0, a.D = dim_d, a.T = (int)n_rows, a.P = 1, a.sig = sig;
+  a.Q = ctx->km_in.as<double>(), a.q_is_desc = 1;
+  a.X = ctx->km_in.as<double>() + nQ, a.x_row_stride = dim_d, a.x_elem_stride = 1;
+  a.iperm = nullptr, a.out = ctx->km_out.as<double>();
+  TRY(launch_mat52(ctx, a, n_q, 0));
+  CUDA_TRY(cudaMemcpyAsync(out, a.out, nOut * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  end_call_timing(ctx);
   return MBG_OK;
 }
 
