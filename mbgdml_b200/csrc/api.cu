@@ -85,7 +85,7 @@ struct mbg_context_s {
   DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
   DevBuf km_in, km_ints, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
-  DevBuf exp2_table_mma;  // 2^(j/1024), j = 0..1023  (DMMA kernel)
+  DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
   long long* h_totals = nullptr;  // pinned [2]
   // timing of the last call
   std::vector<cudaEvent_t> ev_pool;
@@ -180,14 +180,14 @@ static int launch_matern_t(mbg_context_t ctx, const MaternArgs& a) {
   return MBG_OK;
 }
 
-template <int NA, int MT, int NTHR, int MINB, bool USE_E>
+template <int NA, int MT, int NTHR, int MINB, bool USE_E, bool YS = false>
 static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a) {
   int dev_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   const int nt = NTHR;
-  const size_t smem = mma_smem_bytes<NA, MT>(nt, a.P);
+  const size_t smem = mma_smem_bytes<NA, MT, YS>(nt, a.P);
   if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
-  auto kern = k_matern_mma<NA, MT, NTHR, MINB, USE_E>;
+  auto kern = k_matern_mma<NA, MT, NTHR, MINB, USE_E, YS>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nq = a.n_frag * a.P;
   const int qc = mma_queries_per_cta<NA, MT>(nt);
@@ -216,8 +216,12 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
     }
   }
 #endif
-  // Shape per fragment size (measured on B200, profiles/r1_dmma_tuning.md): 8 warps per SM, as many m-tiles
-  // per warp as the register file allows without spilling (3 for D = 28, 36; 4 below).
+  // Shape per fragment size (measured on B200, profiles/r1_dmma_tuning.md): as many m-tiles per warp as the
+  // register file allows without spilling (3 for D = 28, 36; 4 below).  Trimers of 9 atoms (the headline shape)
+  // run 12 warps per SM with the GEMM-1 query operands in shared memory (168 registers): three warps per
+  // scheduler keep the FP64 pipe fed while one of them sits in its sqrt/exp chain.
+  // (models with alphas_E need more registers per thread and keep the 8-warp shape)
+  if (na == 9 && !use_E && ctx->mma_cfg != 1) return launch_matern_mma_t<9, 3, 384, 1, false, true>(ctx, a);
   switch (na) {
 #define X(N)                                                                                        \
   case N: {                                                                                         \
@@ -852,7 +856,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   CUDA_TRY(cudaMemcpy(m->XA, xa.data(), xa.size() * sizeof(double2), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(m->iperm, iperm.data(), iperm.size() * sizeof(int), cudaMemcpyHostToDevice));
   {
-    // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row 5|X'|^2 and X'.A_s,
+    // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row -|X'|^2/2 and -X'.A_s,
     // packed per tile of 64 rows; side arrays in column order (column j of a block <-> row tau(j)).
     static_assert(kTileRows % 32 == 0, "T_pad (multiple of kTileRows) must be whole DMMA tiles of 16 or 32 rows");
     const int Dq = mma_row_pad(d->n_atoms), TILE = mma_tile_doubles(d->n_atoms), TRm = mma_tile_rows(d->n_atoms);
@@ -880,7 +884,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
       // position of row r in column order: r = 8 b + tau(j)  ->  8 b + j  (tau is an involution)
       const int pos = (r / 8) * 8 + mma_tau(r % 8);
       double* side = tile + (size_t)2 * TRm * Dq;
-      side[2 * pos] = (double)(5.0L * xx), side[2 * pos + 1] = (double)xa;
+      side[2 * pos] = (double)(-0.5L * xx), side[2 * pos + 1] = (double)(-xa);  // seeds of the GEMM-1 accumulators
       if (d->alphas_E) side[2 * TRm + pos] = d->alphas_E[t];
     }
     if (cudaMalloc(&m->tiles_mma, tl.size() * sizeof(double)) != cudaSuccess ||
