@@ -34,7 +34,7 @@ __device__ __forceinline__ long long global_candidate(const CullArgs& a, int blo
 
 // One thread per candidate: decode -> gather -> MIC/cut-off -> criteria -> flag.
 template <int NA>
-__global__ void __launch_bounds__(kCullThreads) k_cull(const CullArgs a) {
+__global__ void __launch_bounds__(kCullThreads) k_cull(const __grid_constant__ CullArgs a) {
   const long long g = global_candidate(a, blockIdx.x, threadIdx.x);
   int flag = 0;
   if (g < a.n_cand_total) {
@@ -129,7 +129,7 @@ struct CompactArgs {
   long long* rec_slot;  // [n_rec] candidate index within the frame (row of the decomposed outputs)
 };
 
-__global__ void __launch_bounds__(kCullThreads) k_compact(const CompactArgs a) {
+__global__ void __launch_bounds__(kCullThreads) k_compact(const __grid_constant__ CompactArgs a) {
   __shared__ int warp_cnt[kCullThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool acc = a.flags[(long long)blockIdx.x * kCullThreads + tid] == 1;

@@ -162,7 +162,7 @@ __host__ __device__ constexpr size_t mma_smem_bytes(int nt, int P) {
 // YS: the loop-invariant A operands of GEMM 1 (the queries y') live in shared memory instead of 2 MT KS registers,
 // which lets 12 warps (3 per scheduler) fit the register file with MT = 3.
 template <int NA, int MT, int NTHR, int MINB, bool USE_E, bool YS = false>
-__global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a) {
+__global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant__ MaternMmaArgs a) {
   using S = MmaShape<NA>;
   constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
   constexpr int TR = mma_tile_rows(NA), ST = kMmaStages, BPT = TR / 8;  // BPT: row blocks per tile
@@ -267,20 +267,25 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a
   // ---- this thread's slices of the warp's queries: A fragments of y' (row g of each m-tile) ----
   double Y[YS ? 1 : MT][YS ? 1 : KS], yy5[MT];
   double* ysw = ysm + (size_t)warp * MT * KS * 32 + lane;  // this lane's column of the warp's query operands
-  bool active[MT];
-  int fl_q[MT];
-  const int* ip[MT];
+  // query bookkeeping (active, fragment slot, permutation row); recomputed in the epilogue rather than kept in
+  // registers across the main loop
+  auto query_info = [&](const int wq, const int i, bool& act, int& flq, const int*& ipp) {
+    const long long q = q0 + (long long)wq * (8 * MT) + 8 * i + g;
+    act = q < nq;
+    flq = act ? (int)(q / P - f_lo) : 0;
+    ipp = a.iperm + (act ? (int)(q % P) : 0) * D;
+  };
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
-    const long long q = q0 + (long long)warp * (8 * MT) + 8 * i + g;
-    active[i] = q < nq;
-    fl_q[i] = active[i] ? (int)(q / P - f_lo) : 0;
-    ip[i] = a.iperm + (active[i] ? (int)(q % P) : 0) * D;
+    bool act;
+    int flq;
+    const int* ipp;
+    query_info(warp, i, act, flq, ipp);
     double part = 0.0;
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       const int e = 4 * k + l;
-      const double v = (e < D && active[i]) ? xs[fl_q[i] * D + ip[i][e]] - mus[e] : 0.0;
+      const double v = (e < D && act) ? xs[flq * D + ipp[e]] - mus[e] : 0.0;
       if (YS) ysw[(i * KS + k) * 32] = v;
       else Y[YS ? 0 : i][YS ? 0 : k] = v;
       part = fma(v, v, part);
@@ -517,24 +522,47 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a
     for (int c = 0; c < NC; ++c) Eacc[c >> 1] = vfma(as[c], sq[c], Eacc[c >> 1]);
 #pragma unroll
     for (int c = 0; c < NC; ++c) wp[c >> 1][c & 1] = r_[c], up[c >> 1][c & 1] = sq[c];
+#ifndef EXP_G2_FIRST
     if (G1MODE == 1) {
 #pragma unroll
       for (int k = 0; k < KS; ++k) G1x(k);
     }
+#endif
     G2x();
+#ifdef EXP_G2_FIRST
+    if (G1MODE == 1) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) G1x(k);
+    }
+#endif
     if (b == BPT - 1 || gb == NB - 1) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[ST + s]);  // this warp is done with stage s
     }
   }
   __syncthreads();  // all warps have left the main loop: the tile buffers are free (no TMA is in flight)
+#ifdef EXP_SKIP_EPI  // (experiment) cost of the epilogue
+  if (a.n_frag > 0) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) sacc += Eacc[i] + G[i][0][0] + G[i][NT - 1][1];
+    if (sacc == 123.456) a.E[0] = sacc;
+    return;
+  }
+#endif
 
   // ---- epilogue: G = base (s1 y' - Gacc), un-permute, reduce over permutations, project, scatter ----
   double* Gs = tiles;                // [qc][D]
   double* Es = Gs + (size_t)qc * D;  // [qc]
   const double base = 5.0 / (3.0 * sig * sig * sig);
+  int warp_e;  // == warp, hidden from the optimiser so that query_info is re-evaluated here
+  asm volatile("mov.u32 %0, %1;" : "=r"(warp_e) : "r"(warp));
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
+    bool act;
+    int flq;
+    const int* ipp;
+    query_info(warp_e, i, act, flq, ipp);
     // s1 = sum_t w: column D of Gacc (the X' plane holds 1.0 there, the A_s plane 0.0), owned by lane 4 g + (D % 8) / 2
     double eq = Eacc[i], e2q = E2[i];
     const double s1q = __shfl_sync(0xffffffffu, G[i][D / 8][(D % 8) & 1], (lane & ~3) | ((D % 8) >> 1));
@@ -551,12 +579,12 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const MaternMmaArgs a
       for (int cc = 0; cc < 2; ++cc) {
         const int e = 8 * n + 2 * l + cc;
         if (e < D) {
-          const int d = ip[i][e];
-          const double yv = xs[fl_q[i] * D + d] - mus[e];
-          Gs[ql * D + d] = active[i] ? base * fma(s1q, yv, -G[i][n][cc]) : 0.0;
+          const int d = ipp[e];
+          const double yv = xs[flq * D + d] - mus[e];
+          Gs[ql * D + d] = act ? base * fma(s1q, yv, -G[i][n][cc]) : 0.0;
         }
       }
-    if (l == 0) Es[ql] = active[i] ? fma(base, eq, e2q) : 0.0;
+    if (l == 0) Es[ql] = act ? fma(base, eq, e2q) : 0.0;
   }
   __syncthreads();
 
