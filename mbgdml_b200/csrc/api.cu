@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -181,21 +182,60 @@ static int launch_matern_t(mbg_context_t ctx, const MaternArgs& a) {
 }
 
 template <int NA, int MT, int NTHR, int MINB, bool USE_E, bool YS = false>
-static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a) {
+static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a_in) {
+  MaternMmaArgs a = a_in;
   int dev_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-  const int nt = NTHR;
-  const size_t smem = mma_smem_bytes<NA, MT, YS>(nt, a.P);
-  if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
-  auto kern = k_matern_mma<NA, MT, NTHR, MINB, USE_E, YS>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nq = a.n_frag * a.P;
+  // Launch shape.  Large launches: NTHR threads per CTA, one row slice.  Small launches (single MD frames, small
+  // clusters, the minor models of a mixed system) would leave SMs idle and pay the full latency of a T-row loop:
+  // pick the CTA size (the kernel reads its shape from blockDim/gridDim; NTHR is only the launch bound) and the
+  // number of training-row slices (gridDim.y; partial sums meet in the output atomics) that minimise a simple
+  // cost model -- waves x row blocks per slice x max(latency floor, resident warps per SM) + a per-wave overhead.
+  auto kern = k_matern_mma<NA, MT, NTHR, MINB, USE_E, YS>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::min<size_t>(mma_smem_bytes<NA, MT, YS>(NTHR, a.P), (size_t)dev_smem)));
+  const int n_tiles = a.T_pad / mma_tile_rows(NA), bpt = mma_tile_rows(NA) / 8;
+  int nt = NTHR, slices = 1;
+  {
+    double best = 1e300;
+    const int min_nt = ctx->mma_cfg == 2 ? NTHR : 32;  // MBG_MMA_CFG=2 (developer): always the full-size shape
+    for (int cand_nt = NTHR; cand_nt >= min_nt; cand_nt -= 32) {
+      const size_t sm = mma_smem_bytes<NA, MT, YS>(cand_nt, a.P);
+      if (sm > (size_t)dev_smem) continue;
+      static thread_local std::map<std::pair<int, size_t>, int> occ_cache;  // per instantiation: (threads, smem) -> CTAs/SM
+      int occ = 0;
+      auto hit = occ_cache.find({cand_nt, sm});
+      if (hit != occ_cache.end()) {
+        occ = hit->second;
+      } else {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cand_nt, sm) != cudaSuccess) occ = 0;
+        occ_cache[{cand_nt, sm}] = occ;
+      }
+      if (occ < 1) continue;
+      const int qc_c = mma_queries_per_cta<NA, MT>(cand_nt);
+      const long long g = (nq + qc_c - 1) / qc_c;
+      for (int sl = 1; sl <= (ctx->mma_cfg == 2 ? 1 : std::max(1, n_tiles / 2)); sl *= 2) {
+        const int tps = (n_tiles + sl - 1) / sl;
+        const int sl_eff = std::min((n_tiles + tps - 1) / tps, (a.n_row_blocks + tps * bpt - 1) / (tps * bpt));
+        const long long ctas = g * sl_eff;
+        const long long waves = (ctas + (long long)ctx->sm_count * occ - 1) / ((long long)ctx->sm_count * occ);
+        const double resident = (double)std::min<long long>(occ, (ctas + ctx->sm_count - 1) / ctx->sm_count) * (cand_nt / 32);
+        const double cost = (double)waves * ((double)std::min(a.n_row_blocks, tps * bpt) * std::max(5.0, resident) + 40.0);
+        if (cost < best * 0.97) best = cost, nt = cand_nt, slices = sl_eff, a.tiles_per_slice = tps;
+        if (ctas >= 4ll * ctx->sm_count * occ) break;  // more slices only add waves
+      }
+      if (g >= 4ll * ctx->sm_count) break;  // large launch: keep the full-size CTA
+    }
+    if (best == 1e300) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
+  }
   const int qc = mma_queries_per_cta<NA, MT>(nt);
   const long long grid = (nq + qc - 1) / qc;
   if (grid > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "too many fragments in one launch");
+  const size_t smem = mma_smem_bytes<NA, MT, YS>(nt, a.P);
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
-  kern<<<(unsigned)grid, nt, smem, ctx->stream>>>(a);
+  kern<<<dim3((unsigned)grid, (unsigned)slices), nt, smem, ctx->stream>>>(a);
   cudaEventRecord(e1, ctx->stream);
   ctx->launches++;
   ctx->n_contract++;

@@ -65,6 +65,7 @@ struct MaternMmaArgs {
   const int* iperm;          // [P][D]: pi_p^-1
   int T_pad, P;
   int n_row_blocks;  // ceil(T / 8): blocks of 8 training rows that hold data (the rest of the last tile is padding)
+  int tiles_per_slice;  // training-row tiles per CTA row slice (gridDim.y slices; partial sums meet in the atomics)
   double sig, c, std;
   long long n_frag;
   const int* rec_frame;
@@ -188,7 +189,11 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
   const long long q_end = (q0 + qc < nq) ? q0 + qc : nq;
   const long long f_lo = q0 / P;
   const int nf = (int)((q_end - 1) / P - f_lo) + 1;
-  const int n_tiles = a.T_pad / TR;
+  // Row slice of this CTA (blockIdx.y): small launches are split over the training rows so that every SM gets
+  // work; E and F are linear in the per-row terms, so each slice projects and scatters its own partial sums.
+  const int tile0 = blockIdx.y * a.tiles_per_slice;
+  const int n_tiles = min(a.tiles_per_slice, a.T_pad / TR - tile0);
+  const double* __restrict__ gtiles = a.tiles + (size_t)tile0 * TILE;
   constexpr uint32_t kTileBytes = TILE * 8;
 
   // bars[0..ST): "full" (TMA landed a tile in stage s); bars[ST..2ST): "empty" (every warp is done with stage s).
@@ -207,12 +212,12 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
     for (int s = 0; s < ST; ++s)
       if (s < n_tiles) {
         mbar_expect_tx(&bars[s], kTileBytes);
-        tma_load_1d(tiles + (size_t)s * TILE, a.tiles + (size_t)s * TILE, kTileBytes, &bars[s]);
+        tma_load_1d(tiles + (size_t)s * TILE, gtiles + (size_t)s * TILE, kTileBytes, &bars[s]);
       }
     mbar_expect_tx(&bars[2 * ST], kMmaExpTable * 8);
     tma_load_1d(etab, a.exp2_table, kMmaExpTable * 8, &bars[2 * ST]);
   }
-  if (tid < D) mus[tid] = a.mu[tid];
+  for (int k = tid; k < D; k += nt) mus[k] = a.mu[k];
 
   // ---- prologue: geometry + descriptor of this CTA's fragments (periodic.py:61-107, desc.py:79-158) ----
   // One thread per (fragment, atom), then one per (fragment, atom pair): a single thread per fragment would
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
   const uint32_t tiles_s = smem_u32(tiles);
   const uint32_t ys_s = smem_u32(ysw);
   double yb[2][MT];  // YS: operand double buffer
-  const int NB = a.n_row_blocks;
+  const int NB = min(a.n_row_blocks - tile0 * BPT, n_tiles * BPT);  // row blocks of this slice that hold data
   constexpr uint32_t kPlane = TR * Dp * 8;  // bytes from a row of the X' plane to the same row of the A_s plane
   auto block_base = [&](int gb) -> uint32_t {  // shared address of row 0 of block gb in the X' plane
     return tiles_s + (uint32_t)(((gb / BPT) % ST) * TILE + (gb % BPT) * 8 * Dp) * 8u;
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
         mbar_wait(&bars[ST + su], (u / ST) & 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&bars[su], kTileBytes);
-        tma_load_1d(tiles + (size_t)su * TILE, a.tiles + (size_t)(u + ST) * TILE, kTileBytes, &bars[su]);
+        tma_load_1d(tiles + (size_t)su * TILE, gtiles + (size_t)(u + ST) * TILE, kTileBytes, &bars[su]);
       }
       __syncwarp();
       mbar_wait(&bars[tn % ST], (tn / ST) & 1);
@@ -615,7 +620,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
     const double* rf = rs + fl * NA * 3;
     const double* xf = xs + fl * D;
     if (rem == NA * 3) {
-      const double e = (Es[t_lo] * a.std + (fq0 >= q0 ? a.c : 0.0)) * lam;
+      const double e = (Es[t_lo] * a.std + ((fq0 >= q0 && blockIdx.y == 0) ? a.c : 0.0)) * lam;
       double* dst = a.decomp ? a.E + ((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag])
                              : a.E + a.rec_frame[frag];
       atomicAdd(dst, e);
