@@ -1368,7 +1368,6 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
   if (!ctx || !R_desc || !R_d_desc || !tril_perms_lin || !K) return fail(MBG_ERR_ARG, "NULL argument");
   if (n_atoms < 2 || n_atoms > 18) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: n_atoms=%d outside 2..18", n_atoms);
   if (n_train < 1 || n_perms < 1) return fail(MBG_ERR_ARG, "n_train and n_perms must be positive");
-  if (n_train > 65535) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: n_train=%d > 65535", n_train);
   if (!(sig > 0)) return fail(MBG_ERR_ARG, "sig must be positive");
   if (flags & ~(uint32_t)MBG_FLAG_OUT_ON_DEVICE) return fail(MBG_ERR_UNSUPPORTED, "flag not supported by mbg_kernel_mat");
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1402,19 +1401,32 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
     TRY(ctx->km_out.ensure(rows * rows * sizeof(double)));
     dK = ctx->km_out.as<double>();
   }
+  // closed under inversion?  (pi_q == pi_p^-1 for some q, for every p)
+  bool closed = true;
+  for (int p = 0; p < P && closed; ++p) {
+    bool found = false;
+    for (int q = 0; q < P && !found; ++q) found = std::equal(ipi + (size_t)p * D, ipi + (size_t)(p + 1) * D, pi + (size_t)q * D);
+    closed = found;
+  }
   KernelMatArgs a;
-  a.n_atoms = N, a.D = D, a.T = T, a.P = P, a.sig = sig, a.use_E = use_E_cstr ? 1 : 0;
+  a.T = T, a.P = P, a.sig = sig, a.use_E = use_E_cstr ? 1 : 0, a.symmetric = closed ? 1 : 0;
   a.X = ctx->km_in.as<double>(), a.G = ctx->km_in.as<double>() + nX;
   a.pi = ctx->km_ints.as<int>(), a.ipi = ctx->km_ints.as<int>() + (size_t)P * D;
   a.K = dK, a.ld = (long long)rows;
-  const size_t smem = kernel_mat_smem_bytes(N);
-  const int n_out = (N3 * N3 + kKmThreads - 1) / kKmThreads;
-  void (*kern)(KernelMatArgs) = n_out <= 3 ? k_kernel_mat<3> : (n_out <= 6 ? k_kernel_mat<6> : k_kernel_mat<kKmMaxOut>);
-  if (n_out > kKmMaxOut) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: block too large");
+  const long long n_blocks = closed ? (long long)T * (T + 1) / 2 : (long long)T * T;
+  if (n_blocks > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: too many blocks for one launch");
+  void (*kern)(KernelMatArgs) = nullptr;
+  size_t smem = 0;
+  switch (N) {
+#define X(NA_) case NA_: kern = k_kernel_mat<NA_>, smem = KmShape<NA_>::kBytes; break;
+    MBG_FOR_EACH_NA(X)
+#undef X
+    default: return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: no kernel for %d atoms", N);
+  }
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
-  kern<<<dim3(T, T), kKmThreads, smem, ctx->stream>>>(a);
+  kern<<<(unsigned)n_blocks, kKmThreads, smem, ctx->stream>>>(a);
   cudaEventRecord(e1, ctx->stream);
   CUDA_TRY(cudaGetLastError());
   record_aux_launch(ctx, e0, e1, N, (long long)T * T, T, P, 2);

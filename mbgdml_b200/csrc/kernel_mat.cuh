@@ -15,7 +15,9 @@
 // (the reference forms M = sum_p 5 b_p diff_p v_p^T - W and then J_i^T M; pulling J_i^T through the rank-1
 // term makes it P outer products of 3N-vectors instead of D x 3N ones).  Energy constraints (train.py:224-289):
 //     K[E+i][blk_j] = K[blk_j][E+i] = -sum_p c_p v_p          K[E+j][E+i] = -sum_p (1 + (n/sig)(1 + n/(3 sig))) e^{-n/sig}
-// Permutations are processed in chunks of kKmPC so that shared memory does not grow with P.
+// Permutations are processed in chunks of kKmPC so that shared memory does not grow with P.  When the permutation
+// set is closed under inversion (always, for symmetry groups; checked on the host) K_ji = K_ij^T and the energy
+// entries of the swapped pair follow from u_p, so only the pairs i >= j are computed (the reference's exploit_sym).
 #pragma once
 #include "common.cuh"
 
@@ -23,12 +25,12 @@ namespace mbg {
 
 constexpr int kKmPC = 16;        // permutations per chunk
 constexpr int kKmThreads = 256;  // threads per CTA
-constexpr int kKmMaxOut = 12;    // outputs per thread: ceil((3 * 18)^2 / 256)
 
 struct KernelMatArgs {
-  int n_atoms, D, T, P;
+  int T, P;
   double sig;
   int use_E;
+  int symmetric;     // 1: the permutation set is closed under inversion -> K_ji = K_ij^T; one CTA per pair i >= j
   const double* X;   // [T][D]      R_desc
   const double* G;   // [T][D][3]   compressed Jacobian (desc.py:448-480)
   const int* pi;     // [P][D]      pi_p(k)
@@ -37,68 +39,80 @@ struct KernelMatArgs {
   long long ld;      // rows
 };
 
-__host__ __device__ inline size_t kernel_mat_smem_bytes(int n_atoms) {
-  const int D = n_atoms * (n_atoms - 1) / 2, N3 = 3 * n_atoms;
-  size_t doubles = 2 * (size_t)D            // Xi, Xj
-                   + 2 * (size_t)D * 3      // gi, gj
-                   + (size_t)kKmPC * D      // diff
-                   + 4 * (size_t)kKmPC      // fb, c, kee, pad
-                   + 2 * (size_t)kKmPC * N3 // u, v
-                   + (size_t)D * N3;        // W
-  return doubles * 8 + (size_t)D * 2 * sizeof(int);  // + pair table
-}
+template <int NA>
+struct KmShape {
+  static constexpr int N = NA, D = NA * (NA - 1) / 2, N3 = 3 * NA;
+  static constexpr int NOUT = (N3 * N3 + kKmThreads - 1) / kKmThreads;  // outputs per thread
+  // doubles: Xi, Xj, gi, gj, diff, (fb, cc, kee, pad), u, fu, v, W, out block; ints: pi/ipi chunk
+  static constexpr size_t kDoubles = 2 * D + 6 * D + (size_t)kKmPC * D + 4 * kKmPC + 3 * (size_t)kKmPC * N3 +
+                                     (size_t)D * N3 + (size_t)N3 * (N3 + 1);
+  static constexpr size_t kBytes = kDoubles * 8 + (2 * (size_t)kKmPC * D + 2 * D) * sizeof(int);  // + pair table
+};
 
-template <int MAXOUT>
-__global__ void __launch_bounds__(kKmThreads) k_kernel_mat(const KernelMatArgs a) {
+// pair index k of atoms (a, x), a != x, in np.tril_indices(n, -1) order, and the sign of J[k] at atom a
+__device__ __forceinline__ int km_pair(int a, int x) { return a > x ? a * (a - 1) / 2 + x : x * (x - 1) / 2 + a; }
+
+template <int NA>
+__global__ void __launch_bounds__(kKmThreads) k_kernel_mat(const __grid_constant__ KernelMatArgs a) {
+  using S = KmShape<NA>;
+  constexpr int N = S::N, D = S::D, N3 = S::N3, NOUT = S::NOUT, PC = kKmPC, NT = kKmThreads;
   extern __shared__ __align__(16) unsigned char km_smem[];
-  const int N = a.n_atoms, D = a.D, P = a.P, N3 = 3 * N;
-  const int i = blockIdx.x, j = blockIdx.y;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  int i, j;
+  if (a.symmetric) {  // blockIdx.x = i (i + 1) / 2 + j, j <= i
+    const long long b = blockIdx.x;
+    i = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= b) ++i;
+    while ((long long)i * (i + 1) / 2 > b) --i;
+    j = (int)(b - (long long)i * (i + 1) / 2);
+  } else {
+    i = blockIdx.x % a.T, j = blockIdx.x / a.T;
+  }
+  const int P = a.P;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* Xi = reinterpret_cast<double*>(km_smem);
   double* Xj = Xi + D;
-  double* gi = Xj + D;            // [D][3]
-  double* gj = gi + 3 * D;        // [D][3]
-  double* diff = gj + 3 * D;      // [PC][D]
-  double* fb = diff + kKmPC * D;  // [PC] 5 b_p
-  double* cc = fb + kKmPC;        // [PC] c_p
-  double* kee = cc + kKmPC;       // [PC]
-  double* u = kee + 2 * kKmPC;    // [PC][3N]
-  double* v = u + kKmPC * N3;     // [PC][3N]
-  double* W = v + kKmPC * N3;     // [D][3N]
-  int* pa = reinterpret_cast<int*>(W + (size_t)D * N3);  // [D] larger atom of pair k
-  int* pb = pa + D;                                      // [D] smaller atom
+  double* gi = Xj + D;        // [D][3]
+  double* gj = gi + 3 * D;    // [D][3]
+  double* diff = gj + 3 * D;  // [PC][D]
+  double* fb = diff + PC * D; // [PC] 5 b_p
+  double* cc = fb + PC;       // [PC] c_p
+  double* kee = cc + PC;      // [PC]
+  double* u = kee + 2 * PC;   // [PC][3N]  J_i^T diff_p
+  double* fu = u + PC * N3;   // [PC][3N]  5 b_p u_p
+  double* v = fu + PC * N3;   // [PC][3N]  (J_j[pi_p])^T diff_p
+  double* W = v + PC * N3;    // [D][3N]
+  double* ob = W + D * N3;    // [3N][3N + 1] output block staging
+  int* pis = reinterpret_cast<int*>(ob + N3 * (N3 + 1));  // [PC][D]
+  int* ipis = pis + PC * D;                               // [PC][D]
+  int* pa = ipis + PC * D;                                // [D] larger atom of pair k
+  int* pb = pa + D;                                       // [D] smaller atom
 
-  for (int k = tid; k < D; k += nt) {
-    Xi[k] = a.X[(size_t)i * D + k];
-    Xj[k] = a.X[(size_t)j * D + k];
+  for (int k = tid; k < D; k += NT) {
+    Xi[k] = a.X[(size_t)i * D + k], Xj[k] = a.X[(size_t)j * D + k];
     int hi = 1;
     while ((hi + 1) * hi / 2 <= k) ++hi;  // k = hi (hi - 1) / 2 + lo, lo < hi  (np.tril_indices order)
     pa[k] = hi, pb[k] = k - hi * (hi - 1) / 2;
   }
-  for (int k = tid; k < 3 * D; k += nt) {
-    gi[k] = a.G[(size_t)i * 3 * D + k];
-    gj[k] = a.G[(size_t)j * 3 * D + k];
-  }
-  for (int k = tid; k < D * N3; k += nt) W[k] = 0.0;
-  __syncthreads();
+  for (int k = tid; k < 3 * D; k += NT) gi[k] = a.G[(size_t)i * 3 * D + k], gj[k] = a.G[(size_t)j * 3 * D + k];
+  for (int k = tid; k < D * N3; k += NT) W[k] = 0.0;
 
   const double sig = a.sig;
   const double sqrt5 = sqrt(5.0);
-  double acc[MAXOUT];
+  double acc[NOUT];
 #pragma unroll
-  for (int o = 0; o < MAXOUT; ++o) acc[o] = 0.0;
-  double erow = 0.0, eacc = 0.0;  // threads < 3N: -sum_p c_p v_p[tid]; thread 0: -sum_p kee_p
+  for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
+  double erow = 0.0, ecol = 0.0, eacc = 0.0;  // threads < 3N: -sum c_p v_p[tid], +sum c_p u_p[tid]; thread 0: -sum kee_p
 
-  for (int p0 = 0; p0 < P; p0 += kKmPC) {
-    const int pc = min(kKmPC, P - p0);
+  for (int p0 = 0; p0 < P; p0 += PC) {
+    const int pc = min(PC, P - p0);
+    __syncthreads();  // previous chunk fully consumed (and the loads above visible)
+    for (int idx = tid; idx < pc * D; idx += NT) pis[idx] = a.pi[(size_t)p0 * D + idx], ipis[idx] = a.ipi[(size_t)p0 * D + idx];
+    __syncthreads();
     // A1: diff_p[k] = X_i[k] - X_j[pi_p(k)]
-    for (int idx = tid; idx < pc * D; idx += nt) {
-      const int pl = idx / D, k = idx - pl * D;
-      diff[idx] = Xi[k] - Xj[a.pi[(size_t)(p0 + pl) * D + k]];
-    }
+    for (int idx = tid; idx < pc * D; idx += NT) diff[idx] = Xi[idx % D] - Xj[pis[idx]];
     __syncthreads();
     // A2: norms and radial factors, one warp per permutation
-    for (int pl = warp; pl < pc; pl += nw) {
+    for (int pl = warp; pl < pc; pl += NT / 32) {
       double s = 0.0;
       for (int k = lane; k < D; k += 32) s = fma(diff[pl * D + k], diff[pl * D + k], s);
 #pragma unroll
@@ -112,78 +126,93 @@ __global__ void __launch_bounds__(kKmThreads) k_kernel_mat(const KernelMatArgs a
         kee[pl] = (1.0 + (n / sig) * (1.0 + n / (3.0 * sig))) * ex;
       }
     }
+    __syncthreads();
     // A3: u_p = J_i^T diff_p, v_p = (J_j[pi_p])^T diff_p  -- one thread per (p, atom, axis)
-    for (int idx = tid; idx < pc * N3; idx += nt) {
+    for (int idx = tid; idx < pc * N3; idx += NT) {
       const int pl = idx / N3, r = idx - pl * N3, at = r / 3, ax = r - at * 3;
-      const int* ipi = a.ipi + (size_t)(p0 + pl) * D;
+      const int* ipl = ipis + pl * D;
       const double* dp = diff + pl * D;
       double su = 0.0, sv = 0.0;
+#pragma unroll
       for (int x = 0; x < N; ++x) {
         if (x == at) continue;
-        const int hi = x > at ? x : at, lo = x > at ? at : x;
-        const int k = hi * (hi - 1) / 2 + lo;
-        const double sgn = (at == lo) ? 1.0 : -1.0;  // +g at the smaller atom of the pair, -g at the larger
+        const int k = km_pair(at, x);
+        const double sgn = at < x ? 1.0 : -1.0;  // +g at the smaller atom of the pair, -g at the larger
         su = fma(sgn * gi[k * 3 + ax], dp[k], su);
-        sv = fma(sgn * gj[k * 3 + ax], dp[ipi[k]], sv);  // row k of J_j sits at position pi_p^-1(k) of J_j[pi_p]
+        sv = fma(sgn * gj[k * 3 + ax], dp[ipl[k]], sv);  // row k of J_j sits at position pi_p^-1(k) of J_j[pi_p]
       }
-      u[idx] = su, v[idx] = sv;
+      u[idx] = su, fu[idx] = fb[pl] * su, v[idx] = sv;
     }
-    __syncthreads();
     // B1: W[k][c] += c_p J_j[pi_p(k)][c]  -- thread (k, axis) owns its row/axis: no conflicts
-    for (int idx = tid; idx < D * 3; idx += nt) {
+    for (int idx = tid; idx < D * 3; idx += NT) {
       const int k = idx / 3, ax = idx - k * 3;
       for (int pl = 0; pl < pc; ++pl) {
-        const int k2 = a.pi[(size_t)(p0 + pl) * D + k];
+        const int k2 = pis[pl * D + k];
         const double val = cc[pl] * gj[k2 * 3 + ax];
         W[k * N3 + pb[k2] * 3 + ax] += val;
         W[k * N3 + pa[k2] * 3 + ax] -= val;
       }
     }
+    __syncthreads();
     // B2: rank-1 part, outputs (r, c) strided over the CTA
 #pragma unroll
-    for (int o = 0; o < MAXOUT; ++o) {
-      const int e = tid + o * kKmThreads;
+    for (int o = 0; o < NOUT; ++o) {
+      const int e = tid + o * NT;
       if (e < N3 * N3) {
         const int r = e / N3, c = e - r * N3;
         double s = acc[o];
-        for (int pl = 0; pl < pc; ++pl) s = fma(fb[pl] * u[pl * N3 + r], v[pl * N3 + c], s);
+        for (int pl = 0; pl < pc; ++pl) s = fma(fu[pl * N3 + r], v[pl * N3 + c], s);
         acc[o] = s;
       }
     }
     if (a.use_E) {
       if (tid < N3)
-        for (int pl = 0; pl < pc; ++pl) erow = fma(-cc[pl], v[pl * N3 + tid], erow);
+        for (int pl = 0; pl < pc; ++pl) erow = fma(-cc[pl], v[pl * N3 + tid], erow), ecol = fma(cc[pl], u[pl * N3 + tid], ecol);
       if (tid == 0)
         for (int pl = 0; pl < pc; ++pl) eacc -= kee[pl];
     }
-    __syncthreads();
   }
 
-  // C: K_ij[r][c] = acc - sum_{k containing atom(r)} J_i[k][r] W[k][c]
-  double* Kb = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+  // C: K_ij[r][c] = acc - sum_{k containing atom(r)} J_i[k][r] W[k][c], staged so that the block and (symmetric mode)
+  // its transpose leave in coalesced rows
 #pragma unroll
-  for (int o = 0; o < MAXOUT; ++o) {
-    const int e = tid + o * kKmThreads;
+  for (int o = 0; o < NOUT; ++o) {
+    const int e = tid + o * NT;
     if (e < N3 * N3) {
       const int r = e / N3, c = e - r * N3, at = r / 3, ax = r - at * 3;
       double s = acc[o];
+#pragma unroll
       for (int x = 0; x < N; ++x) {
         if (x == at) continue;
-        const int hi = x > at ? x : at, lo = x > at ? at : x;
-        const int k = hi * (hi - 1) / 2 + lo;
-        const double sgn = (at == lo) ? 1.0 : -1.0;
+        const int k = km_pair(at, x);
+        const double sgn = at < x ? 1.0 : -1.0;
         s = fma(-sgn * gi[k * 3 + ax], W[k * N3 + c], s);
       }
-      Kb[(size_t)r * a.ld + c] = s;
+      ob[r * (N3 + 1) + c] = s;
     }
+  }
+  __syncthreads();
+  double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+  double* Kji = a.K + ((size_t)j * N3) * a.ld + (size_t)i * N3;
+  for (int e = tid; e < N3 * N3; e += NT) {
+    const int r = e / N3, c = e - r * N3;
+    Kij[(size_t)r * a.ld + c] = ob[r * (N3 + 1) + c];
+    if (a.symmetric && i != j) Kji[(size_t)r * a.ld + c] = ob[c * (N3 + 1) + r];
   }
   if (a.use_E) {
     const size_t E0 = (size_t)a.T * N3;
     if (tid < N3) {
-      a.K[(E0 + i) * a.ld + (size_t)j * N3 + tid] = erow;    // train.py:224-239
-      a.K[((size_t)j * N3 + tid) * a.ld + E0 + i] = erow;    // train.py:262-287 (worker j' = T + i, block j)
+      a.K[(E0 + i) * a.ld + (size_t)j * N3 + tid] = erow;  // train.py:224-239
+      a.K[((size_t)j * N3 + tid) * a.ld + E0 + i] = erow;  // train.py:262-287 (worker j' = T + i, block j)
+      if (a.symmetric && i != j) {  // the swapped pair: (J_i[pi_p])^T (X_j - X_i[pi_p]) = -u_q with pi_q = pi_p^-1
+        a.K[(E0 + j) * a.ld + (size_t)i * N3 + tid] = ecol;
+        a.K[((size_t)i * N3 + tid) * a.ld + E0 + j] = ecol;
+      }
     }
-    if (tid == 0) a.K[(E0 + j) * a.ld + E0 + i] = eacc;      // train.py:287-289
+    if (tid == 0) {
+      a.K[(E0 + j) * a.ld + E0 + i] = eacc;  // train.py:287-289
+      if (a.symmetric && i != j) a.K[(E0 + i) * a.ld + E0 + j] = eacc;
+    }
   }
 }
 

@@ -162,3 +162,25 @@ def test_gpu_mat52_golden_and_oracle():
     R = synthetic.fragment_geometries(np.random.default_rng(4), ["meoh", "meoh", "h2o"], 19)
     got = gdml_mat52(mb.gdmlModel(dict(md)), md["z"], R)
     assert relerr(got, orc.gdml_mat52(orc.Model(dict(md)), md["z"], R)) <= TOL
+
+
+@pytest.mark.gpu
+def test_gpu_kernel_mat_permutation_set_not_closed_under_inversion():
+    """A permutation list that is not a group (identity + one 3-cycle of the molecules, without its inverse): K is
+    no longer symmetric and the kernel must take the all-ordered-pairs path instead of mirroring blocks."""
+    from mbgdml_b200._gdml.train import assemble_kernel_mat
+
+    comp, T, sig = ["h2o", "h2o", "h2o"], 5, 60.0
+    _, X, G, perms, _ = _train_inputs(comp, T, 31)
+    ident = np.arange(9)
+    cyc = next(p for p in perms if not np.array_equal(p[p], ident) and not np.array_equal(p, ident))
+    tpl = orc.tril_perms_lin_from_perms(np.array([ident, cyc]))
+    for use_E in (False, True):
+        K = assemble_kernel_mat(X, G, tpl, sig, use_E_cstr=use_E)
+        ref = orc.assemble_kernel_mat(X, G, tpl, sig, use_E_cstr=use_E)
+        n3 = T * 27
+        assert relerr(ref[:n3, :n3], ref[:n3, :n3].T) > 1e-6  # the case really is asymmetric
+        assert relerr(K[:n3, :n3], ref[:n3, :n3]) <= TOL
+        if use_E:
+            assert relerr(K[n3:, :n3], ref[n3:, :n3]) <= TOL and relerr(K[:n3, n3:], ref[:n3, n3:]) <= TOL
+            assert relerr(K[n3:, n3:], ref[n3:, n3:]) <= TOL
