@@ -88,11 +88,6 @@ __device__ __forceinline__ double2 lds_row(uint32_t addr) {
 // Arithmetic wrapped in `asm volatile`: the compiler keeps volatile asm statements in program order, so
 // the stages of the scalar chain stay interleaved with the (volatile) shared-memory loads of the other
 // two streams exactly as written, instead of being re-serialised into one latency-bound run.
-#ifdef EXP_FREECHAIN  // (experiment) let the compiler schedule the chains
-__device__ __forceinline__ double vfma(double a, double b, double c) { return fma(a, b, c); }
-__device__ __forceinline__ double vmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double vadd(double a, double b) { return __dadd_rn(a, b); }
-#else
 __device__ __forceinline__ double vfma(double a, double b, double c) {
   double r;
   asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c));
@@ -108,7 +103,6 @@ __device__ __forceinline__ double vadd(double a, double b) {
   asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
   return r;
 }
-#endif
 __device__ __forceinline__ double vmax(double a, double b) {
   double r;
   asm volatile("max.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));

@@ -43,15 +43,30 @@ struct MmaShape {
   static_assert(Dp >= 4 * KS && Dp > D && Dp % 8 == 4, "row padding / spare column");
 };
 
-constexpr int kMmaStages = 3;  // tile buffers in flight
-constexpr int kMmaExpTable = 4096;  // entries of the 2^(j/4096) table (shared memory, 32 KB)
-constexpr int kMmaExpBits = 12;
+// Tuning knobs (defaults = the shipped configuration; overridden with -D in tools/mma_harness.cu builds only)
+#ifndef MBG_MMA_STAGES
+#define MBG_MMA_STAGES 3
+#endif
+#ifndef MBG_MMA_EXP_BITS
+#define MBG_MMA_EXP_BITS 12
+#endif
+constexpr int kMmaStages = MBG_MMA_STAGES;  // tile buffers in flight
+constexpr int kMmaExpBits = MBG_MMA_EXP_BITS;
+constexpr int kMmaExpTable = 1 << kMmaExpBits;  // entries of the 2^(j/4096) table (shared memory, 32 KB)
+// exp(r c) - 1 = r (c + r (c^2/2 + r c^3/6)), c = ln2 / table size, |r| <= 1/2
+constexpr double kMmaExpC1 = 0.6931471805599453 / kMmaExpTable;
+constexpr double kMmaExpC2 = kMmaExpC1 * kMmaExpC1 / 2;
+constexpr double kMmaExpC3 = kMmaExpC1 * kMmaExpC1 * kMmaExpC1 / 6;
 __host__ __device__ constexpr int mma_row_pad(int na) {
   const int D = na * (na - 1) / 2;
   return (D + 1 <= 4) ? 4 : ((D + 1 - 4 + 7) / 8 * 8 + 4);
 }
 // training rows per TMA tile: 32, or 16 for the widest descriptors (three tiles in flight must fit shared memory)
+#ifdef MBG_MMA_TILE_ROWS
+__host__ __device__ constexpr int mma_tile_rows(int) { return MBG_MMA_TILE_ROWS; }
+#else
 __host__ __device__ constexpr int mma_tile_rows(int na) { return mma_row_pad(na) <= 108 ? 32 : 16; }
+#endif
 // doubles per packed tile: two planes, (xx5, xa) per row, alphas_E per row
 __host__ __device__ constexpr int mma_tile_doubles(int na) { return mma_tile_rows(na) * (2 * mma_row_pad(na) + 3); }
 __host__ __device__ constexpr int mma_tau(int j) { return j < 4 ? j : (j ^ 1); }  // {0,1,2,3,5,4,7,6}
@@ -498,11 +513,11 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
     // per pair, even Chebyshev-economised) is NOT enough: trained models are ill-conditioned and amplify it past the
     // reference's own tolerance (tests/test_gpu_parity.py::test_reference_16mer_and_6mer_with_trained_models).
 #pragma unroll
-    for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], 8.076910841165456e-13, 1.43186156129301e-08);
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], kMmaExpC3, kMmaExpC2);
 #pragma unroll
     for (int c = 0; c < NC; ++c) t_[c] = etab[kk[c] & (kMmaExpTable - 1)];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], 0.0001692253858788929);
+    for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], kMmaExpC1);
 #pragma unroll
     for (int c = 0; c < NC; ++c) h_[c] = vmul(h_[c], r_[c]);
 #pragma unroll
@@ -527,34 +542,17 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
     for (int c = 0; c < NC; ++c) Eacc[c >> 1] = vfma(as[c], sq[c], Eacc[c >> 1]);
 #pragma unroll
     for (int c = 0; c < NC; ++c) wp[c >> 1][c & 1] = r_[c], up[c >> 1][c & 1] = sq[c];
-#ifndef EXP_G2_FIRST
     if (G1MODE == 1) {
 #pragma unroll
       for (int k = 0; k < KS; ++k) G1x(k);
     }
-#endif
     G2x();
-#ifdef EXP_G2_FIRST
-    if (G1MODE == 1) {
-#pragma unroll
-      for (int k = 0; k < KS; ++k) G1x(k);
-    }
-#endif
     if (b == BPT - 1 || gb == NB - 1) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[ST + s]);  // this warp is done with stage s
     }
   }
   __syncthreads();  // all warps have left the main loop: the tile buffers are free (no TMA is in flight)
-#ifdef EXP_SKIP_EPI  // (experiment) cost of the epilogue
-  if (a.n_frag > 0) {
-    double sacc = 0.0;
-#pragma unroll
-    for (int i = 0; i < MT; ++i) sacc += Eacc[i] + G[i][0][0] + G[i][NT - 1][1];
-    if (sacc == 123.456) a.E[0] = sacc;
-    return;
-  }
-#endif
 
   // ---- epilogue: G = base (s1 y' - Gacc), un-permute, reduce over permutations, project, scatter ----
   double* Gs = tiles;                // [qc][D]

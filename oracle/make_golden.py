@@ -465,6 +465,21 @@ def case_train_kernel():
             out[f"mat52_{k}_R{tag}"] = R
             out[f"mat52_{k}_out{tag}"] = want
         out.update({f"mat52_{k}_{kk}": v for kk, v in slim(md).items()})
+    # the reference's own kernel-matrix fixture (tests/data/train/1h2o/K.npy with R_desc.npy, tril_perms_lin.npy,
+    # train_idxs.npy; sigma = 42, tests/test_train.py:51-88): the blocks of the first 20 training points
+    tdir = os.path.join(REF, "tests/data/train/1h2o")
+    K_fix = np.load(os.path.join(tdir, "K.npy"))
+    idx = np.load(os.path.join(tdir, "train_idxs.npy"))
+    tpl = np.load(os.path.join(tdir, "tril_perms_lin.npy"))
+    dset = dict(np.load(os.path.join(REF, "tests/data/datasets/1h2o/140h2o.sphere.gfn2.md.500k.prod1.3h2o.dset.1h2o-dset.npz"),
+                        allow_pickle=True))
+    Rt = dset["R"][idx]
+    R_desc, R_d_desc = Desc(3, max_processes=1).from_R(Rt.reshape(len(idx), -1))
+    assert np.array_equal(R_desc.T, np.load(os.path.join(tdir, "R_desc.npy")))
+    check("kernel_mat reference fixture 1h2o/K.npy", orc.assemble_kernel_mat(R_desc, R_d_desc, tpl, 42), K_fix, tol=1e-13)
+    nk = 20
+    out.update({"fix1h2o_R": Rt[:nk], "fix1h2o_R_desc": R_desc[:nk], "fix1h2o_R_d_desc": R_d_desc[:nk],
+                "fix1h2o_tril_perms_lin": tpl, "fix1h2o_sig": np.array(42.0), "fix1h2o_K": K_fix[:nk * 9, :nk * 9].copy()})
     np.savez_compressed(os.path.join(GOLD, "train_kernel.npz"), **out)
 
 

@@ -44,6 +44,16 @@ def test_oracle_kernel_mat_matches_reference(name):
         assert relerr(K, ref) <= 1e-11
 
 
+def test_oracle_kernel_mat_reference_fixture():
+    """The reference's own known answer: tests/data/train/1h2o/K.npy (sigma 42, first 20 training points)."""
+    g = load("train_kernel.npz")
+    K = orc.assemble_kernel_mat(g["fix1h2o_R_desc"], g["fix1h2o_R_d_desc"], g["fix1h2o_tril_perms_lin"], 42.0)
+    assert K.shape == g["fix1h2o_K"].shape == (180, 180)
+    assert relerr(K, g["fix1h2o_K"]) <= 1e-13
+    x, gj = orc.from_r(g["fix1h2o_R"][3].reshape(-1))  # descriptors of the fixture come from its geometries
+    assert np.array_equal(x, g["fix1h2o_R_desc"][3]) and np.array_equal(gj, g["fix1h2o_R_d_desc"][3])
+
+
 def test_oracle_mat52_matches_reference():
     g = load("train_kernel.npz")
     for k in range(3):
@@ -97,6 +107,16 @@ def test_gpu_kernel_mat_golden(name):
             assert relerr(K[n3:, n3:], ref[n3:, n3:]) <= TOL
     K2 = GDMLTrain()._assemble_kernel_mat(*args, None, use_E_cstr=False, alloc_extra_rows=3)
     assert K2.shape == (n3 + 3, n3) and np.array_equal(K2[:n3], assemble_kernel_mat(*args))
+
+
+@pytest.mark.gpu
+def test_gpu_kernel_mat_reference_fixture():
+    """CUDA path vs. the reference's own tests/data/train/1h2o/K.npy."""
+    from mbgdml_b200._gdml.train import assemble_kernel_mat
+
+    g = load("train_kernel.npz")
+    K = assemble_kernel_mat(g["fix1h2o_R_desc"], g["fix1h2o_R_d_desc"], g["fix1h2o_tril_perms_lin"], 42.0)
+    assert relerr(K, g["fix1h2o_K"]) <= TOL
 
 
 @pytest.mark.gpu

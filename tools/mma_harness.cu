@@ -26,15 +26,18 @@ using namespace mbg;
 
 static double frand() { return rand() / (double)RAND_MAX; }
 
-template <int MT, int NTHR, bool YS>
+template <int MT, int NTHR, bool YS, int MINB = 1>
 static int run(const char* name, MaternMmaArgs a, int reps) {
   constexpr int NA = 9;
-  auto kern = k_matern_mma<NA, MT, NTHR, 1, false, YS>;
+  auto kern = k_matern_mma<NA, MT, NTHR, MINB, false, YS>;
   const size_t smem = mma_smem_bytes<NA, MT, YS>(NTHR, a.P);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nq = a.n_frag * a.P;
   const int qc = mma_queries_per_cta<NA, MT>(NTHR);
   const unsigned grid = (unsigned)((nq + qc - 1) / qc);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHR, smem);
+  printf("[occupancy %d CTA/SM] ", occ);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0), cudaEventCreate(&e1);
   kern<<<grid, NTHR, smem>>>(a);
@@ -130,8 +133,12 @@ int main(int argc, char** argv) {
 #ifdef EXP_NAME
   printf("experiment: %s\n", EXP_NAME);
 #endif
+#ifdef EXP_TWO_CTAS
+  if (run<3, 192, true, 2>("MT=3 192 thr x 2 CTA/SM, y' smem", a, 5)) return 1;
+#else
   if (run<3, 256, false>("MT=3 256 thr", a, 5)) return 1;
   if (run<3, 384, true>("MT=3 384 thr, y' in smem", a, 5)) return 1;
+#endif
   double E;
   CK(cudaMemcpy(&E, dE, 8, cudaMemcpyDeviceToHost));
   printf("E (sum over all launches) = %.6e\n", E);
