@@ -261,6 +261,8 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
   // run 12 warps per SM with the GEMM-1 query operands in shared memory (168 registers): three warps per
   // scheduler keep the FP64 pipe fed while one of them sits in its sqrt/exp chain.
   // (models with alphas_E need more registers per thread and keep the 8-warp shape)
+  // Measured and rejected for the other sizes: 12 warps + smem operands for 6-atom fragments (0.95 vs 0.85 ms on
+  // the box140 dimers), two 8-warp CTAs per SM for 3-atom fragments (0.83 vs 0.80 ms on 100 000 monomers).
   if (na == 9 && !use_E && ctx->mma_cfg != 1) return launch_matern_mma_t<9, 3, 384, 1, false, true>(ctx, a);
   switch (na) {
 #define X(N)                                                                                        \
