@@ -267,7 +267,9 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    n_frames = args.frames * world  # weak scaling: fixed frames per GPU
+    # weak scaling (default, the driver's contract): fixed frames per GPU; strong: --frames is the whole job and the
+    # fragments of every frame are sharded over the ranks (BASELINE config 3: one 64-H2O structure on 1/2/4/8 GPUs)
+    n_frames = args.frames * world if args.scaling == "weak" else args.frames
     w = make_workload(args.workload, n_frames, args.n_train)
     ctx = _native.get_context(local)
     # a dedicated (non-default) torch stream: the library launches on it, the CUDA events that time the
@@ -424,10 +426,11 @@ def run_gpu_arm(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": w["label"], "frames_per_step": n_frames, "frames_per_gpu": args.frames,
+            "workload": w["label"], "frames_per_step": n_frames,
+            "frames_per_gpu": args.frames if args.scaling == "weak" else n_frames / world,
             "fragments_enumerated_per_step": [int(x) for x in enum], "fragments_accepted_per_step": [int(x) for x in acc],
             "structures_per_s": n_frames * args.steps / (ms_dev * 1e-3),
             "parallelism": f"fragment-sharded x{world}, one all-reduce" if world > 1 else "single GPU",
@@ -457,6 +460,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="box140", choices=["box140", "trimers64", "monomers", "mixed140"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --frames per GPU (default); strong: --frames in total, fragments sharded over the GPUs")
     ap.add_argument("--n-train", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--contraction", default="auto", choices=["auto", "fma", "dmma"],
