@@ -103,3 +103,22 @@ def test_model_container_attributes():
     assert m.type == "gdml" and m.nbody_order == 2 and m.n_atoms == 6 and m.n_train == 12 and m.n_perms == 8
     assert m.sig == 55.0 and m.integ_c == 1.5 and m.stdev == 2.0 and list(m.comp_ids) == ["h2o", "h2o"]
     assert mb.gdmlModel(md, comp_ids=["a", "b"]).comp_ids == ["a", "b"]
+
+
+def test_cached_system_reuse_and_invalidation():
+    """_engine.cached_system: same (Z, entity_ids, cell) -> the same System object; any change -> a new one."""
+    from mbgdml_b200 import _engine
+    from mbgdml_b200.periodic import Cell
+
+    Z = np.array([8, 1, 1, 8, 1, 1])
+    eids = np.array([0, 0, 0, 1, 1, 1])
+    s1 = _engine.cached_system(Z, eids, None, False)
+    assert _engine.cached_system(Z.copy(), eids.copy(), None, False) is s1
+    assert _engine.cached_system(Z, np.array([0, 0, 0, 1, 1, 2]), None, False) is not s1
+    s2 = _engine.cached_system(Z, eids, None, True)  # masses become mandatory
+    assert s2 is not s1
+    cell = Cell(np.eye(3) * 10.0, pbc=True)
+    s3 = _engine.cached_system(Z, eids, cell, True)
+    assert s3 is not s2 and _engine.cached_system(Z, eids, Cell(np.eye(3) * 10.0, pbc=True), True) is s3
+    assert _engine.cached_system(Z, eids, Cell(np.eye(3) * 11.0, pbc=True), True) is not s3
+    assert list(s3.entity_offsets) == [0, 3, 6]
