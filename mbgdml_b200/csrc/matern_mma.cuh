@@ -19,16 +19,22 @@
 // F_d[d] = sum_p G_p[pi_p(d)]  -- algebraically the reference's  F_d += w1 diff - c2 A_j,  E += a c2.
 //
 // Mapping.  One warp owns 8*MT queries (MT m-tiles).  For every block of 8 training rows:
-//   GEMM 1: A operand = y' (registers, loaded once), B operand = the X' / A_s rows (shared memory),
-//           C fragment: thread (g = lane/4, l = lane%4) holds columns 2l, 2l+1 of row g;
+//   GEMM 1: A operand = y' (registers, loaded once -- or, template flag YS, re-read from shared memory so that
+//           12 warps fit the register file), B operand = the X' / A_s rows (shared memory), accumulators seeded
+//           with the row side data (-|X'|^2/2, -X'.A_s); C fragment: thread (g = lane/4, l = lane%4) holds
+//           columns 2l, 2l+1 of row g;
 //   chain:  element-wise on the C fragments (2*MT pairs per thread);
 //   GEMM 2: the weights are already laid out as an A operand if the k index l of the two k-steps is taken
 //           to mean columns 2l (+0 / +1) -- the sum over rows does not care about their order -- so no
 //           shuffle is needed; B operand = the same rows read along e; accumulators G[q][e] in registers.
 // Column j of a block maps to physical row tau(j) = {0,1,2,3,5,4,7,6}[j]: with a row stride of 32 (mod 128)
 // bytes this makes every 8-byte shared-memory load of both GEMMs bank-conflict free.
-// Tiles of 64 rows ([X' plane | A_s plane | (5|X'|^2, X'.A_s) | alphas_E], packed per tile by the host) are
-// staged by one TMA bulk copy each, double buffered on mbarriers.
+// Tiles of 32 rows (16 for the widest descriptors: [X' plane | A_s plane | (-|X'|^2/2, -X'.A_s) | alphas_E], packed
+// per tile by the host) are staged by one TMA bulk copy each into a 3-stage ring with full/empty mbarriers; the
+// 2^(j/4096) table is a fourth bulk copy.  Schedule per block of 8 rows: the scalar chains of the block, then one
+// uninterrupted run of DMMAs (GEMM 1 of the next block, GEMM 2 of this one) -- see the loop comment and
+// profiles/r1_dmma_tuning.md section 6 for why the phases are kept whole.  gridDim.y slices the training rows for
+// small launches (launch_matern_mma_t in api.cu).
 #pragma once
 #include "matern.cuh"
 
