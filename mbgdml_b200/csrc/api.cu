@@ -231,11 +231,26 @@ static int launch_matern_mma_t(mbg_context_t ctx, const MaternMmaArgs& a_in) {
   }
   const int qc = mma_queries_per_cta<NA, MT>(nt);
   const long long grid = (nq + qc - 1) / qc;
-  if (grid > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "too many fragments in one launch");
   const size_t smem = mma_smem_bytes<NA, MT, YS>(nt, a.P);
+  // Tail splitting for launches of several waves whose last wave is less than half full (one MD frame of the
+  // 140-H2O box: 24.07 waves): the tail batches are cut into row slices that together fill the SMs once.
+  a.main_ctas = (int)std::min<long long>(grid, 0x7fffffffLL), a.tail_slices = 1, a.tail_tiles_per_slice = a.tiles_per_slice;
+  long long grid_x = grid;
+  if (slices == 1 && ctx->mma_cfg != 2) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem) != cudaSuccess || occ < 1) occ = 1;
+    const long long per_wave = (long long)ctx->sm_count * occ, rem = grid % per_wave;
+    if (grid > per_wave && rem > 0 && 2 * rem <= per_wave) {
+      int ts = (int)std::min<long long>(per_wave / rem, std::max(1, n_tiles / 2));
+      const int tps = (n_tiles + ts - 1) / ts;
+      ts = std::min((n_tiles + tps - 1) / tps, (a.n_row_blocks + tps * bpt - 1) / (tps * bpt));  // slices that hold data
+      if (ts > 1) a.main_ctas = (int)(grid - rem), a.tail_slices = ts, a.tail_tiles_per_slice = tps, grid_x = grid - rem + rem * ts;
+    }
+  }
+  if (grid_x > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "too many fragments in one launch");
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
-  kern<<<dim3((unsigned)grid, (unsigned)slices), nt, smem, ctx->stream>>>(a);
+  kern<<<dim3((unsigned)grid_x, (unsigned)slices), nt, smem, ctx->stream>>>(a);
   cudaEventRecord(e1, ctx->stream);
   ctx->launches++;
   ctx->n_contract++;

@@ -87,6 +87,10 @@ struct MaternMmaArgs {
   int T_pad, P;
   int n_row_blocks;  // ceil(T / 8): blocks of 8 training rows that hold data (the rest of the last tile is padding)
   int tiles_per_slice;  // training-row tiles per CTA row slice (gridDim.y slices; partial sums meet in the atomics)
+  // Tail splitting: query batches [0, main_ctas) run all their rows in one CTA each (blockIdx.x = batch); the
+  // remaining batches -- the last, partial wave of a launch -- are each split into tail_slices CTAs of
+  // tail_tiles_per_slice tiles, so the tail takes 1 / tail_slices of a wave.  tail_slices <= 1: no splitting.
+  int main_ctas, tail_slices, tail_tiles_per_slice;
   double sig, c, std;
   long long n_frag;
   const int* rec_frame;
@@ -206,14 +210,19 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
   double* mus = rs + (size_t)maxf * NA * 3;                                                                // [D] (+1 pad)
 
   const long long nq = a.n_frag * P;
-  const long long q0 = (long long)blockIdx.x * qc;
+  int batch = blockIdx.x, slice = blockIdx.y, tps = a.tiles_per_slice;
+  if (a.tail_slices > 1 && batch >= a.main_ctas) {  // tail CTA: (batch, slice) packed in blockIdx.x
+    const int t = batch - a.main_ctas;
+    batch = a.main_ctas + t / a.tail_slices, slice = t - (t / a.tail_slices) * a.tail_slices, tps = a.tail_tiles_per_slice;
+  }
+  const long long q0 = (long long)batch * qc;
   const long long q_end = (q0 + qc < nq) ? q0 + qc : nq;
   const long long f_lo = q0 / P;
   const int nf = (int)((q_end - 1) / P - f_lo) + 1;
-  // Row slice of this CTA (blockIdx.y): small launches are split over the training rows so that every SM gets
+  // Row slice of this CTA: small launches (and the tail of large ones) are split over the training rows so that every SM gets
   // work; E and F are linear in the per-row terms, so each slice projects and scatters its own partial sums.
-  const int tile0 = blockIdx.y * a.tiles_per_slice;
-  const int n_tiles = min(a.tiles_per_slice, a.T_pad / TR - tile0);
+  const int tile0 = slice * tps;
+  const int n_tiles = min(tps, a.T_pad / TR - tile0);
   const double* __restrict__ gtiles = a.tiles + (size_t)tile0 * TILE;
   constexpr uint32_t kTileBytes = TILE * 8;
 
@@ -624,7 +633,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
     const double* rf = rs + fl * NA * 3;
     const double* xf = xs + fl * D;
     if (rem == NA * 3) {
-      const double e = (Es[t_lo] * a.std + ((fq0 >= q0 && blockIdx.y == 0) ? a.c : 0.0)) * lam;
+      const double e = (Es[t_lo] * a.std + ((fq0 >= q0 && slice == 0) ? a.c : 0.0)) * lam;
       double* dst = a.decomp ? a.E + ((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag])
                              : a.E + a.rec_frame[frag];
       atomicAdd(dst, e);

@@ -82,3 +82,16 @@ def test_tiny_training_sets(T):
     E, F = mb.mbePredict(b200_models(mds, [None] * 3), mb.predict_gdml).predict(Z, R, eids, cids)
     Eo, Fo = orc.mbe_predict(oracle_models(mds, [None] * 3), Z, R, eids, cids)
     assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+
+
+def test_tail_split_launch_shape():
+    """A launch of a little more than one wave: 969 water trimers x 48 permutations = 162 CTAs of 288 queries on
+    148 SMs.  The 14 CTAs of the last wave are cut into training-row slices (api.cu, tail splitting); the result
+    must not change.  Oracle on the same inputs (3-body model only, T = 250: 8 row tiles -> 4 tail slices)."""
+    md = synthetic.make_model(["h2o"] * 3, n_train=250, sig=150.0, seed=5)
+    Z, R, eids, cids = synthetic.make_cluster(19, seed=4)
+    pred = mb.mbePredict(b200_models([md], [None]), mb.predict_gdml)
+    E, F = pred.predict(Z, R, eids, cids)
+    assert pred.last_stats[0][2] == 969
+    Eo, Fo = orc.mbe_predict(oracle_models([md], [None]), Z, R, eids, cids)
+    assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL

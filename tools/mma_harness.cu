@@ -125,7 +125,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dSl, rec_slot.data(), n_frag * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(dE, 0, 8)); CK(cudaMemset(dF, 0, R.size() * 8));
   a.R = dR, a.tiles = dT, a.mu = dMu, a.exp2_table = dTab, a.iperm = dIp;
-  a.T_pad = T_pad, a.P = P, a.n_row_blocks = (T + 7) / 8, a.tiles_per_slice = T_pad / TR;
+  a.T_pad = T_pad, a.P = P, a.n_row_blocks = (T + 7) / 8, a.tiles_per_slice = T_pad / TR, a.main_ctas = 0x7fffffff, a.tail_slices = 1, a.tail_tiles_per_slice = T_pad / TR;
   a.sig = 100.0, a.c = 0.0, a.std = 1.0, a.n_frag = n_frag;
   a.rec_frame = dFr, a.rec_atoms = dAt, a.rec_lambda = dLam, a.rec_slot = dSl;
   a.n_slots_per_frame = (int)n_frag, a.decomp = 0, a.want_virial = 0;
