@@ -1,0 +1,80 @@
+"""``GDMLTorchPredict`` on the device kernels (reference mbgdml/_gdml/torchtools.py:401-1063).
+
+The reference class is a ``torch.nn.Module`` that evaluates an sGDML model with einsum-based PyTorch code; here the
+same interface -- ``forward(Rs, return_E=True)`` with ``Rs`` a (M, N, 3) tensor, returning ``(Es, Fs)`` tensors on
+the device of ``Rs`` -- runs through the Matern contraction kernels of the prediction path.  CUDA tensors are
+consumed and produced in place (no host round trip); the call is ordered on torch's current stream.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _engine, _native
+from ..models import gdmlModel
+from ..utils import gen_combs
+
+
+class GDMLTorchPredict(nn.Module):
+    """PyTorch front-end of ``GDMLPredict``; holds no trainable parameters (torchtools.py:401-405)."""
+
+    def __init__(self, model, lat_and_inv=None, batch_size=None, n_perm_batches=1, max_memory=None,
+                 max_processes=None, log_level=None):  # pylint: disable=unused-argument
+        super().__init__()
+        if lat_and_inv is not None:
+            raise NotImplementedError("sGDML periodic descriptors (lat_and_inv) have no device implementation")
+        model = dict(model)
+        model.setdefault("r_unit", np.array("Angstrom"))
+        self.dim_d, self.n_train = model["R_desc"].shape[:2]
+        self.n_perms, self.n_atoms = model["perms"].shape
+        self.dim_i = 3 * self.n_atoms
+        self._model = gdmlModel(model, comp_ids=np.array(["mol"]))
+        self._std = float(self._model.stdev)
+        self._c = float(self._model.integ_c)
+        self._Z = np.asarray(self._model.Z)
+        self._eids = np.zeros(self.n_atoms, dtype=np.int64)
+
+    def get_n_perm_batches(self):  # memory knobs of the reference: nothing to tune here (torchtools.py:584-605)
+        return 1
+
+    def set_n_perm_batches(self, n_perm_batches):  # pylint: disable=unused-argument
+        return None
+
+    def forward(self, Rs_or_train_idxs, return_E=True):
+        """(M, N, 3) coordinates -> ``(Es (M,), Fs (M, N, 3))``, or ``(Fs,)`` when ``return_E`` is False
+        (torchtools.py:999-1063).  Evaluating training points by index (a 1-D tensor) is training-side."""
+        Rs = Rs_or_train_idxs
+        if Rs.dim() == 1:
+            raise NotImplementedError("prediction by training index needs set_R_d_desc(), which is training-side")
+        if Rs.dim() != 3 or Rs.shape[1] != self.n_atoms or Rs.shape[2] != 3:
+            raise ValueError(f"Rs must be (M, {self.n_atoms}, 3)")
+        M = int(Rs.shape[0])
+        src = [gen_combs([np.array([0])])]
+        if Rs.is_cuda:
+            dev = Rs.device
+            R = Rs.detach().to(torch.float64).contiguous()
+            ctx = _native.get_context(dev.index if dev.index is not None else torch.cuda.current_device())
+            Es = torch.empty(M, dtype=torch.float64, device=dev)
+            Fs = torch.empty((M, self.n_atoms, 3), dtype=torch.float64, device=dev)
+            if M:
+                ts = torch.cuda.current_stream(dev)
+                if ts.cuda_stream == 0:
+                    # legacy default stream: the library's own (non-blocking) stream is not ordered against it
+                    ts.synchronize()
+                    ctx.set_stream(0)
+                else:
+                    ctx.set_stream(ts.cuda_stream)  # stream-ordered with the producer of Rs and the consumer of (Es, Fs)
+                try:
+                    _engine.predict_total(ctx, self._Z, R, self._eids, [self._model], src, [[]], None,
+                                          device_out=(Es, Fs, None))
+                    if ts.cuda_stream == 0:
+                        ctx.synchronize()
+                finally:
+                    ctx.set_stream(0)
+        else:
+            ctx = _native.get_context()
+            E, F, _, _ = _engine.predict_total(ctx, self._Z, Rs.detach().to(torch.float64).numpy(), self._eids,
+                                               [self._model], src, [[]], None)
+            Es, Fs = torch.from_numpy(E), torch.from_numpy(F)
+        return (Es, Fs) if return_E else (Fs,)

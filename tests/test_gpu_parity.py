@@ -509,3 +509,32 @@ def _single_entity(om):
     om.nbody_order = 1
     om.comp_ids = np.array(["mol"])
     return om
+
+
+def test_sgdml_torch_predictor():
+    """GDMLTorchPredict.forward (torchtools.py:999-1063): CUDA tensors in and out, CPU tensors in and out, both
+    equal to the bulk predictor and the oracle."""
+    import torch
+
+    from mbgdml_b200._gdml.torchtools import GDMLTorchPredict
+    from mbgdml_b200.gdml_predict import GDMLPredict
+
+    md = synthetic.make_model(["h2o", "h2o"], n_train=50, sig=25.0, seed=13, c=-3.5, std=2.25)
+    R = synthetic.fragment_geometries(np.random.default_rng(14), ["h2o", "h2o"], 9)
+    om = orc.Model(dict(md))
+    E_o = np.zeros(9)
+    F_o = np.zeros((9, 6, 3))
+    for k in range(9):
+        x, J = orc.from_r(R[k].reshape(-1))
+        out = orc.predict_gdml_wkr(x, J, 6, om.sig, om.n_perms, om.R_desc_perms, om.R_d_desc_alpha_perms)
+        E_o[k], F_o[k] = out[0] * md["std"] + md["c"], out[1:].reshape(6, 3) * md["std"]
+    net = GDMLTorchPredict(md)
+    Es, Fs = net(torch.from_numpy(R).cuda())
+    assert Es.is_cuda and Fs.shape == (9, 6, 3)
+    assert relerr(Es.cpu().numpy(), E_o) <= TOL and relerr(Fs.cpu().numpy(), F_o) <= TOL
+    (Fc,) = net(torch.from_numpy(R), return_E=False)
+    assert not Fc.is_cuda and relerr(Fc.numpy(), F_o) <= TOL
+    E_b, F_b = GDMLPredict(md).predict(R.reshape(9, -1))
+    assert relerr(E_b, E_o) <= TOL and relerr(F_b.reshape(9, 6, 3), F_o) <= TOL
+    with pytest.raises(NotImplementedError):
+        net(torch.arange(3))
