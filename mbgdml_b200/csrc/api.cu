@@ -1457,7 +1457,8 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
 
 static int launch_mat52(mbg_context_t ctx, Mat52Args a, int64_t n_q, int na_rec) {
   if (n_q > 65535) return fail(MBG_ERR_UNSUPPORTED, "covariance: more than 65535 query structures per call");
-  const size_t smem = ((size_t)a.D + (size_t)kM52Rows * (a.D + 1)) * sizeof(double);
+  a.stage_perms = mat52_smem_bytes(a.D, a.P, true) <= 96 * 1024 ? 1 : 0;  // two CTAs per SM at least
+  const size_t smem = mat52_smem_bytes(a.D, a.P, a.stage_perms != 0);
   if (smem > 200 * 1024) return fail(MBG_ERR_UNSUPPORTED, "covariance: descriptor dimension %d too large", a.D);
   CUDA_TRY(cudaFuncSetAttribute(k_mat52, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);

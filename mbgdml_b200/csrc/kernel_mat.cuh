@@ -233,17 +233,25 @@ struct Mat52Args {
   long long x_row_stride;
   int x_elem_stride;
   const int* iperm;       // [P][D] pi_p^-1, or NULL for the identity (P must be 1)
+  int stage_perms;        // 1: the P permuted copies of the query fit shared memory (mat52_smem_bytes)
   double* out;            // [n_q][T * P]
 };
 
-__global__ void __launch_bounds__(kM52Threads) k_mat52(const Mat52Args a) {
+// bytes of shared memory: query descriptor, row tile, and (when it fits) the P permuted copies of the query
+__host__ __device__ inline size_t mat52_smem_bytes(int D, int P, bool stage_perms) {
+  return ((size_t)D + (size_t)kM52Rows * (D + 1) + (stage_perms ? (size_t)P * (D | 1) : 0)) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(kM52Threads) k_mat52(const __grid_constant__ Mat52Args a) {
   extern __shared__ __align__(16) unsigned char m52_smem[];
   const int D = a.D, P = a.P, N = a.n_atoms;
   const int m = blockIdx.y, t0 = blockIdx.x * kM52Rows;
   const int nrow = min(kM52Rows, a.T - t0);
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int DQ = D | 1;                              // odd pitch: lanes with consecutive p hit different banks
   double* xq = reinterpret_cast<double*>(m52_smem);  // [D]
   double* Xs = xq + D;                               // [kM52Rows][D + 1]
+  double* yq = Xs + kM52Rows * (D + 1);              // [P][DQ] permuted queries y_p[e] = x[pi_p^-1(e)] (stage_perms)
   for (int k = tid; k < D; k += nt) {
     if (a.q_is_desc) {
       xq[k] = a.Q[(size_t)m * D + k];
@@ -263,16 +271,31 @@ __global__ void __launch_bounds__(kM52Threads) k_mat52(const Mat52Args a) {
     Xs[tl * (D + 1) + e] = a.X[(size_t)(t0 + tl) * a.x_row_stride + (size_t)e * a.x_elem_stride];
   }
   __syncthreads();
+  if (a.stage_perms) {
+    for (int idx = tid; idx < P * D; idx += nt) {
+      const int p = idx / D, e = idx - p * D;
+      yq[p * DQ + e] = xq[a.iperm ? a.iperm[idx] : e];
+    }
+    __syncthreads();
+  }
   const double sig = a.sig;
   const double s5 = sqrt(5.0) / sig, q2 = 5.0 / (3.0 * sig * sig);
   for (int idx = tid; idx < nrow * P; idx += nt) {
     const int tl = idx / P, p = idx - tl * P;
-    const int* ip = a.iperm ? a.iperm + (size_t)p * D : nullptr;
     const double* xr = Xs + tl * (D + 1);
     double s = 0.0;
-    for (int e = 0; e < D; ++e) {
-      const double d = xq[ip ? ip[e] : e] - xr[e];
-      s = fma(d, d, s);
+    if (a.stage_perms) {
+      const double* yp = yq + p * DQ;
+      for (int e = 0; e < D; ++e) {
+        const double d = yp[e] - xr[e];
+        s = fma(d, d, s);
+      }
+    } else {
+      const int* ip = a.iperm ? a.iperm + (size_t)p * D : nullptr;
+      for (int e = 0; e < D; ++e) {
+        const double d = xq[ip ? ip[e] : e] - xr[e];
+        s = fma(d, d, s);
+      }
     }
     const double d = sqrt(s);
     a.out[(size_t)m * a.T * P + (size_t)(t0 + tl) * P + p] = (1.0 + s5 * d + q2 * s) * exp(-s5 * d);
