@@ -72,6 +72,9 @@ struct DevBuf {  // growable device allocation
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int kMaxDeferred = 64;            // small jobs per call whose counts are read back once, at the end
+constexpr long long kSmallJobCand = 65536;  // candidates (all frames) up to which a job is "small"
+
 struct mbg_context_s {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -87,7 +90,10 @@ struct mbg_context_s {
   DevBuf km_in, km_ints, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
-  long long* h_totals = nullptr;  // pinned [2]
+  long long* h_totals = nullptr;  // pinned [2 + 2 * kMaxDeferred]
+  DevBuf deferred_totals;         // [kMaxDeferred][2]: (accepted, enumerated) of jobs whose counts stay on the device
+  int n_deferred = 0;
+  int deferred_rec[64] = {0};     // launch record of each deferred job (its fragment count is patched at the end)
   // timing of the last call
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -596,7 +602,7 @@ struct Outputs {
 // Enumerate + cull + compact + contract one job over n_frames frames.
 static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
                    int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
-                   mbg_job_stats* stats) {
+                   mbg_job_stats* stats, int* deferred_slot = nullptr) {
   const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
   long long n_cand_shard = 0, n_enum = 0, n_acc = 0;
   const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads;
@@ -606,6 +612,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
   const int NA = j.n_frag_atoms;
 
   long long rec_pending = 0;
+  const long long* n_frag_dev = nullptr;  // set by the small-job path below
   auto flush = [&]() -> int {
     if (rec_pending == 0) return MBG_OK;
     if (decomp) {
@@ -623,7 +630,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
       a.T_pad = m->T_pad, a.P = m->P;
       a.n_row_blocks = (m->T + 7) / 8;
       a.sig = m->sig, a.c = m->c, a.std = m->std;
-      a.n_frag = rec_pending;
+      a.n_frag = rec_pending, a.n_frag_dev = n_frag_dev;
       a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
       a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
       a.n_slots_per_frame = (int)j.cand_per_frame;
@@ -641,7 +648,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     a.exp2_table = ctx->exp2_table.as<double>();
     a.T_pad = m->T_pad, a.P = m->P;
     a.sig = m->sig, a.c = m->c, a.std = m->std;
-    a.n_frag = rec_pending;
+    a.n_frag = rec_pending, a.n_frag_dev = n_frag_dev;
     a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
     a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
     a.n_slots_per_frame = (int)j.cand_per_frame;
@@ -653,6 +660,56 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     return MBG_OK;
   };
 
+  // Small jobs (single MD frames of small systems, the minor models of a mixed system): no host round trip for
+  // the accepted count.  Records and the contraction grid are sized for the upper bound (every candidate of this
+  // shard accepted); the kernels read the true count from the device and surplus CTAs exit at once.  The counts
+  // for `stats` are read back once, at the end of the call (mbg_predict).
+  if (deferred_slot && !decomp && my_granules > 0 && my_granules <= kChunk && n_cand_total <= kSmallJobCand &&
+      ctx->n_deferred < kMaxDeferred && ctx->mma_cfg != 3) {
+    const int blocks = (int)my_granules, slot = ctx->n_deferred++;
+    TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
+    TRY(ctx->blk_acc.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->blk_enum.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->blk_off.ensure((size_t)blocks * sizeof(long long)));
+    TRY(ctx->deferred_totals.ensure((size_t)kMaxDeferred * 2 * sizeof(long long)));
+    long long* totals = ctx->deferred_totals.as<long long>() + 2 * slot;
+    CullArgs ca;
+    ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
+    ca.n_cand_total = n_cand_total, ca.granule0 = 0;
+    ca.shard_rank = shard_rank, ca.shard_count = shard_count;
+    ca.flags = ctx->flags.as<unsigned char>();
+    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    TRY(launch_cull(ctx, NA, blocks, ca));
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk_acc.as<int>(), ctx->blk_enum.as<int>(), blocks,
+                                               ctx->blk_off.as<long long>(), totals);
+    ctx->launches++;
+    for (long long b = 0; b < blocks; ++b) {
+      const long long lo = (b * shard_count + shard_rank) * kCullThreads;
+      n_cand_shard += std::max(0ll, std::min<long long>(kCullThreads, n_cand_total - lo));
+    }
+    TRY(ctx->rec_frame.ensure((size_t)n_cand_shard * sizeof(int)));
+    TRY(ctx->rec_atoms.ensure((size_t)n_cand_shard * NA * sizeof(int)));
+    TRY(ctx->rec_lambda.ensure((size_t)n_cand_shard * sizeof(double)));
+    TRY(ctx->rec_slot.ensure((size_t)n_cand_shard * sizeof(long long)));
+    CompactArgs pa;
+    pa.sys = s, pa.job = j;
+    pa.n_cand_total = n_cand_total, pa.granule0 = 0;
+    pa.shard_rank = shard_rank, pa.shard_count = shard_count;
+    pa.flags = ctx->flags.as<unsigned char>();
+    pa.block_offsets = ctx->blk_off.as<long long>();
+    pa.rec_base = 0;
+    pa.rec_frame = ctx->rec_frame.as<int>(), pa.rec_atoms = ctx->rec_atoms.as<int>();
+    pa.rec_lambda = ctx->rec_lambda.as<double>(), pa.rec_slot = ctx->rec_slot.as<long long>();
+    k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    rec_pending = n_cand_shard, n_frag_dev = totals;
+    TRY(flush());
+    ctx->deferred_rec[slot] = (int)ctx->launch_recs.size() - 1;
+    *deferred_slot = slot;
+    if (stats) stats->n_candidates = n_cand_shard, stats->n_enumerated = 0, stats->n_accepted = 0;  // patched by the caller
+    return MBG_OK;
+  }
   for (long long g0 = 0; g0 < my_granules; g0 += kChunk) {
     const int blocks = (int)std::min(kChunk, my_granules - g0);
     TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
@@ -774,7 +831,7 @@ int mbg_context_create(int device, mbg_context_t* out) {
   ctx->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
-  CUDA_TRY(cudaMallocHost(&ctx->h_totals, 2 * sizeof(long long)));
+  CUDA_TRY(cudaMallocHost(&ctx->h_totals, (2 + 2 * kMaxDeferred) * sizeof(long long)));
   {
     double tab[1 << kExpTableBits];
     for (int j = 0; j < (1 << kExpTableBits); ++j) tab[j] = (double)exp2l((long double)j / (1 << kExpTableBits));
@@ -802,7 +859,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints, &ctx->job_binom,
                     &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
-                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
+                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in, &ctx->deferred_totals,
                     &ctx->km_ints, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1036,6 +1093,8 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
     if (want_virial) CUDA_TRY(cudaMemsetAsync(out.V, 0, (size_t)n_frames * 9 * sizeof(double), ctx->stream));
   }
   size_t ints_off = 0;
+  ctx->n_deferred = 0;
+  std::vector<std::pair<int, int>> deferred;  // (job, slot of its device-side counts)
   for (int k = 0; k < n_jobs && n_frames > 0; ++k) {
     JobDev j;
     size_t used = 0;
@@ -1055,17 +1114,31 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
     TRY(build_job(ctx, sys, &jobs[k], ints_off, j, &used));
     ints_off += (used + 15) / 16 * 16 + 16;  // keep slices 64-byte aligned
     mbg_job_stats st = {0, 0, 0};
+    int slot = -1;
     if (j.cand_per_frame > 0)
-      TRY(run_job(ctx, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, &st));
+      TRY(run_job(ctx, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, &st, &slot));
     if (stats) stats[k] = st;
+    if (slot >= 0) deferred.push_back({k, slot});
   }
+  if (!deferred.empty())  // counts of the small jobs: one copy, resolved by the synchronisation below
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_totals + 2, ctx->deferred_totals.p, (size_t)ctx->n_deferred * 2 * sizeof(long long),
+                             cudaMemcpyDeviceToHost, ctx->stream));
   if (!out_dev) {
     CUDA_TRY(cudaMemcpyAsync(E, out.E, (size_t)n_frames * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(F, out.F, nR * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (want_virial)
       CUDA_TRY(cudaMemcpyAsync(virial, out.V, (size_t)n_frames * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  } else if (!deferred.empty() && stats) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // device outputs stay enqueued otherwise; the caller asked for counts
   }
+  if (stats)
+    for (const auto& d : deferred) {
+      stats[d.first].n_accepted = ctx->h_totals[2 + 2 * d.second];
+      stats[d.first].n_enumerated = ctx->h_totals[2 + 2 * d.second + 1];
+      const int rec = ctx->deferred_rec[d.second];
+      if (rec >= 0 && rec < (int)ctx->launch_recs.size()) ctx->launch_recs[rec].n_frag = stats[d.first].n_accepted;
+    }
   end_call_timing(ctx);
   return MBG_OK;
 }

@@ -35,6 +35,7 @@ struct MaternArgs {
   int T_pad, P;
   double sig, c, std;
   long long n_frag;
+  const long long* n_frag_dev;  // optional: the accepted count still on the device (n_frag is then an upper bound)
   const int* rec_frame;
   const int* rec_atoms;
   const double* rec_lambda;
@@ -235,8 +236,10 @@ __global__ void __launch_bounds__(kMaternThreads, Blocking<NA>::MinCtas) k_mater
   double* etab = rs + (size_t)maxf * NA * 3;                     // [64] 2^(j/64)
   uint64_t* bars = reinterpret_cast<uint64_t*>(etab + (1 << kExpTableBits));
 
-  const long long nq = a.n_frag * P;
+  const long long n_frag = a.n_frag_dev ? min(a.n_frag, *a.n_frag_dev) : a.n_frag;
+  const long long nq = n_frag * P;
   const long long q0 = (long long)blockIdx.x * qc;
+  if (q0 >= nq) return;  // the grid was sized for an upper bound of the fragment count (whole CTA, before any barrier)
   const long long q_end = (q0 + qc < nq) ? q0 + qc : nq;  // exclusive
   const long long f_lo = q0 / P;
   const int nf = (int)((q_end - 1) / P - f_lo) + 1;

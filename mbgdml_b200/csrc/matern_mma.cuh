@@ -93,6 +93,7 @@ struct MaternMmaArgs {
   int main_ctas, tail_slices, tail_tiles_per_slice;
   double sig, c, std;
   long long n_frag;
+  const long long* n_frag_dev;  // optional: the accepted count still on the device (n_frag is then an upper bound)
   const int* rec_frame;
   const int* rec_atoms;
   const double* rec_lambda;
@@ -209,13 +210,15 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
   double* rs = xs + (size_t)maxf * D;                                                                      // [maxf][NA][3]
   double* mus = rs + (size_t)maxf * NA * 3;                                                                // [D] (+1 pad)
 
-  const long long nq = a.n_frag * P;
+  const long long n_frag = a.n_frag_dev ? min(a.n_frag, *a.n_frag_dev) : a.n_frag;
+  const long long nq = n_frag * P;
   int batch = blockIdx.x, slice = blockIdx.y, tps = a.tiles_per_slice;
   if (a.tail_slices > 1 && batch >= a.main_ctas) {  // tail CTA: (batch, slice) packed in blockIdx.x
     const int t = batch - a.main_ctas;
     batch = a.main_ctas + t / a.tail_slices, slice = t - (t / a.tail_slices) * a.tail_slices, tps = a.tail_tiles_per_slice;
   }
   const long long q0 = (long long)batch * qc;
+  if (q0 >= nq) return;  // the grid was sized for an upper bound of the fragment count (whole CTA, before any barrier)
   const long long q_end = (q0 + qc < nq) ? q0 + qc : nq;
   const long long f_lo = q0 / P;
   const int nf = (int)((q_end - 1) / P - f_lo) + 1;
