@@ -149,50 +149,96 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU reference arm: the oracle port (NumPy restatement of the reference) on the host cores
+# CPU arm: the reference's own predict_gdml (unmodified package from oracle/_ref, see oracle/fetch_ref.py) on the
+# host cores; the NumPy oracle port only when that install is absent.  Also the checker for `parity`.
 # ----------------------------------------------------------------------------------------------
 _CPU_W = None  # workload shared with forked workers (set before the pool is created)
+
+
+def cpu_kind():
+    from oracle import reference
+
+    return "reference" if reference.available() else "port"
+
+
+def _cpu_objects(model_idx):
+    """(predict function, model, cell, scalers) of the CPU implementation in this worker (cached)."""
+    hit = _cpu_objects.cache.get(model_idx)
+    if hit is not None:
+        return hit
+    w = _CPU_W
+    d = w["model_dicts"][model_idx]
+    order = len(d["comp_ids"])
+    if cpu_kind() == "reference":
+        from oracle import reference
+
+        ref = reference.load()
+        crit = ref.Criteria(ref.com_distance_sum, {"entity_ids": d["entity_ids"]}, w["cutoffs"][model_idx])
+        model = ref.gdmlModel(dict(d), criteria=crit)
+        cell = ref.Cell(w["cell"], pbc=True) if w["cell"] is not None else None
+        scalers = [ref.mbeAlchemyScale(e, o, ref.linear_switching, {"factor": f}) for e, o, f in w["alchemy"] if o == order]
+        fn = lambda Z, R, eids, combs: ref.predict_gdml(Z, R, eids, combs, model, cell, alchemy_scalers=scalers)[:2]
+    else:
+        from oracle import mbgdml_oracle as orc
+
+        crit = orc.Criteria(orc.com_distance_sum, {"entity_ids": d["entity_ids"]}, w["cutoffs"][model_idx])
+        model = orc.Model(dict(d), criteria=crit)
+        cell = orc.Cell(w["cell"]) if w["cell"] is not None else None
+        scalers = [orc.AlchemyScale(e, o, f) for e, o, f in w["alchemy"] if o == order]
+        fn = lambda Z, R, eids, combs: orc.predict_gdml(Z, R, eids, combs, model, cell, alchemy_scalers=scalers)[:2]
+    _cpu_objects.cache[model_idx] = fn
+    return fn
+
+
+_cpu_objects.cache = {}
 
 
 def _cpu_chunk(args):
     from threadpoolctl import threadpool_limits
 
-    from oracle import mbgdml_oracle as orc
-
     model_idx, combs = args
     w = _CPU_W
-    d = w["model_dicts"][model_idx]
-    crit = orc.Criteria(orc.com_distance_sum, {"entity_ids": d["entity_ids"]}, w["cutoffs"][model_idx])
-    model = _cpu_chunk.cache.get(model_idx)
-    if model is None:
-        model = _cpu_chunk.cache[model_idx] = orc.Model(dict(d), criteria=crit)
-    cell = orc.Cell(w["cell"]) if w["cell"] is not None else None
+    fn = _cpu_objects(model_idx)
     with threadpool_limits(limits=1):
-        orc.predict_gdml(w["Z"], w["R"][0], w["eids"], combs, model, cell)
-    return orc.predict_gdml.last_n_eval
+        E, F = fn(w["Z"], w["R"][0], w["eids"], [tuple(int(e) for e in c) for c in combs])
+    return float(E), F
 
 
-_cpu_chunk.cache = {}
-
-
-def cpu_reference_pass(w, n_candidates, pool, cores):
-    """One bounded sample of the workload on the host: the first `n_candidates` candidate tuples of the
-    highest-order model on frame 0 (culling included), fanned out over the cores in chunks as the
-    reference's ray branch does (mbe.py:823-868).  Returns (accepted fragments, seconds)."""
+def cpu_sample(w):
+    """The bounded sample of the workload the CPU arm evaluates: the first `cpu_sample_size` candidate tuples of the
+    highest-order model on frame 0, in gen_combs order (culling is part of the pass).  Returns (model index, combs)."""
     from oracle import mbgdml_oracle as orc
 
     k = len(w["model_dicts"]) - 1
     sets = orc.get_avail_entities(w["cids"], w["model_dicts"][k]["comp_ids"])
+    n_candidates = cpu_sample_size(w)
     combs = []
     for c in orc.gen_combs(sets):
         combs.append(c)
         if len(combs) >= n_candidates:
             break
+    return k, np.array(combs, dtype=np.int64).reshape(len(combs), -1)
+
+
+def cpu_sample_accepted(w, k, combs):
+    """Accept mask of the sample by the vectorised oracle culling (untimed; gives the fragment count of the metric)."""
+    from oracle import cull_vec
+    from oracle import mbgdml_oracle as orc
+
+    d = w["model_dicts"][k]
+    om = orc.Model(dict(d), criteria=orc.Criteria(orc.com_distance_sum, {"entity_ids": d["entity_ids"]}, w["cutoffs"][k]))
+    return cull_vec.accept_mask(w["Z"], w["R"][0], w["eids"], combs, om, orc.Cell(w["cell"]) if w["cell"] is not None else None)
+
+
+def cpu_reference_pass(k, combs, pool, cores):
+    """One pass over the sample, fanned out over the cores in chunks as the reference's ray branch does
+    (mbe.py:823-868).  Returns (E, F, seconds)."""
     chunk = max(1, len(combs) // (cores * 8))
     tasks = [(k, combs[i:i + chunk]) for i in range(0, len(combs), chunk)]
     t0 = time.perf_counter()
-    n_eval = sum(pool.map(_cpu_chunk, tasks))
-    return n_eval, time.perf_counter() - t0, len(combs)
+    parts = pool.map(_cpu_chunk, tasks)
+    dt = time.perf_counter() - t0
+    return sum(p[0] for p in parts), sum(p[1] for p in parts), dt
 
 
 def cpu_sample_size(w):
@@ -201,17 +247,23 @@ def cpu_sample_size(w):
 
 
 def ncu_traffic(workload, n_frag_atoms, frames, use_dmma):
-    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum from the
-    committed `ncu --set full` capture of the same command, profiles/ncu_traffic.json), else None."""
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
+    committed `ncu --set full` capture of the same command (profiles/ncu_traffic.json): a STATIC figure that names
+    the capture it came from -- (bytes, source) or (None, None)."""
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
-        return None
+        return None, None
     for row in table:
         if (row["workload"] == workload and row["n_frag_atoms"] == n_frag_atoms and row["frames"] == frames
                 and row["contraction"] == ("dmma" if use_dmma else "fma")):
-            return row["dram_bytes_per_launch"]
-    return None
+            return row["dram_bytes_per_launch"], "static: " + row.get("source", "ncu --set full capture, profiles/")
+    return None, None
+
+
+def sample_text(w, n_scanned, n_acc):
+    return (f"first {n_scanned} candidate tuples of the {len(w['families'][-1])}-body model on frame 0 in gen_combs order "
+            f"({n_acc} accepted), culling included")
 
 
 def run_reference_arm(args):
@@ -221,27 +273,28 @@ def run_reference_arm(args):
     if rank != 0:
         return
     global _CPU_W
-    w = make_workload(args.workload, 1, args.n_train)
-    w_small = _CPU_W = w
+    w = _CPU_W = make_workload(args.workload, 1, args.n_train)
     cores = os.cpu_count() or 1
-    n_cand = cpu_sample_size(w)
+    k, combs = cpu_sample(w)
+    n_acc = int(cpu_sample_accepted(w, k, combs).sum())
+    kind = cpu_kind()
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_reference_pass(w_small, max(cores * 8, n_cand // 8), pool, cores)
-        n_tot, t_tot = 0, 0.0
+            cpu_reference_pass(k, combs[:max(cores * 8, len(combs) // 8)], pool, cores)
+        t_tot = 0.0
         for _ in range(args.steps):
-            n, t, n_scanned = cpu_reference_pass(w_small, n_cand, pool, cores)
-            n_tot += n
-            t_tot += t
-    value = n_tot / t_tot
-    sample = (f"per step: first {n_scanned} candidate tuples of the {len(w['families'][-1])}-body model on frame 0 "
-              f"({n_tot // args.steps} accepted), culling included")
+            t_tot += cpu_reference_pass(k, combs, pool, cores)[2]
+    value = n_acc * args.steps / t_tot
+    impl_text = ("unmodified reference package (oracle/_ref): mbgdml.predictors.predict_gdml per chunk, one process per "
+                 "core, the multiprocessing mirror of the ray fan-out of mbe.py:823-868" if kind == "reference"
+                 else "NumPy oracle port (oracle/_ref absent), one process per core")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "parallelism": f"{cores} host processes"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": w["label"], "parallelism": f"{cores} host processes", "implementation": impl_text},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "per step: " + sample_text(w, len(combs), n_acc)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -284,6 +337,8 @@ def run_gpu_arm(args):
     scalers = [mb.mbeAlchemyScale(e, o, mb.linear_switching, {"factor": f}) for e, o, f in w["alchemy"]]
     cell = mb.Cell(w["cell"], pbc=True) if w["cell"] is not None else None
     pred = mb.mbePredict(models, mb.predict_gdml, alchemy_scalers=scalers, periodic_cell=cell)
+    if world > 1:
+        pred.shard_group = dist.group.WORLD  # opt-in fragment sharding + one all-reduce inside predict()
     Z, eids, cids = w["Z"], w["eids"], w["cids"]
     n_atoms = len(Z)
 
@@ -368,6 +423,50 @@ def run_gpu_arm(args):
     ms_e2e, _ = timed(step_e2e, args.steps)
     e2e_value = frag_per_step * args.steps / (ms_e2e * 1e-3)
 
+    # N > 1: the all-reduced result of frame 0 equals the un-sharded single-rank evaluation of the same frame
+    mg_check = None
+    if world > 1:
+        step_device()
+        torch.cuda.synchronize(dev)
+        E_all, F_all = buf[:1].cpu().numpy().copy(), buf[n_frames:n_frames + 3 * n_atoms].cpu().numpy().copy()
+        one = torch.zeros(1 + 3 * n_atoms, dtype=torch.float64, device=dev)
+        _engine.predict_total(ctx, Z, R_dev[:1].contiguous(), eids, models, sources(), [pred._scalers_for(m) for m in models],
+                              cell, shard=(0, 1), device_out=(one[:1], one[1:], None))
+        torch.cuda.synchronize(dev)
+        one = one.cpu().numpy()
+        err = torch.tensor([abs(E_all[0] - one[0]) / max(abs(one[0]), 1e-300),
+                            np.abs(F_all - one[1:]).max() / max(np.abs(one[1:]).max(), 1e-300)], dtype=torch.float64, device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        mg_check = {"what": "all-reduced [E|F] of frame 0 vs the same frame evaluated un-sharded on every rank (max over ranks)",
+                    "max_rel_err_E": float(err[0].item()), "max_rel_err_F": float(err[1].item()),
+                    "ok": bool(err.max().item() <= 1e-11)}
+
+    # strong-scaling sub-record (BASELINE config 3): ONE 64-H2O structure, its 41,664 trimers sharded over the ranks
+    strong = None
+    if not args.no_strong:
+        ws = make_workload("trimers64", 1, args.n_train)
+        ms_ = [mb.gdmlModel(dict(d)) for d in ws["model_dicts"]]
+        ps = mb.mbePredict(ms_, mb.predict_gdml)
+        Rs = torch.from_numpy(ws["R"]).to(dev)
+        na_s = len(ws["Z"])
+        bs = torch.zeros(1 + 3 * na_s, dtype=torch.float64, device=dev)
+
+        def step_strong():
+            _engine.predict_total(ctx, ws["Z"], Rs, ws["eids"], ms_, [mb.gen_combs(ps.get_avail_entities(ws["cids"], m.comp_ids)) for m in ms_],
+                                  [[]], None, shard=(rank, world), device_out=(bs[:1], bs[1:], None))
+            if world > 1:
+                dist.all_reduce(bs, op=dist.ReduceOp.SUM)
+
+        for _ in range(3):
+            step_strong()
+        n_s = 10
+        ms_s, _ = timed(step_strong, n_s)
+        kern_ms = sum(r["ms"] for r in ctx.last_launches())
+        strong = {"workload": ws["label"], "frames": 1, "fragments": 41664, "n_gpus": world, "steps": n_s,
+                  "ms_per_structure": ms_s / n_s, "structures_per_s": n_s / (ms_s * 1e-3),
+                  "contraction_ms_rank0": kern_ms, "scaling": "strong",
+                  "efficiency_inputs": "efficiency(N) = ms_per_structure(1) / (N * ms_per_structure(N)) across the --gpus lines"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -387,10 +486,11 @@ def run_gpu_arm(args):
         ms = sum(r["ms"] for r in dom)
         achieved = flop / (ms * 1e-3) / 1e12
         kname = f"k_matern_mma<NA={best['n_frag_atoms']}>" if use_dmma else f"k_matern<NA={best['n_frag_atoms']}>"
+        traffic, traffic_source = ncu_traffic(args.workload, best["n_frag_atoms"], args.frames, use_dmma)
         roofline = {
             "bound": "tensor" if use_dmma else "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops if peak_tflops else None,
-            "traffic": ncu_traffic(args.workload, best["n_frag_atoms"], args.frames, use_dmma),
+            "traffic": traffic, "traffic_source": traffic_source,
             "kernel": kname, "launches_in_step": len(dom),
             "avg_launch_ms": ms / len(dom), "alg_flop_per_fragment": rec_flops(best),
             "fragments_per_launch": sum(r["n_fragments"] for r in dom) / len(dom),
@@ -409,20 +509,39 @@ def run_gpu_arm(args):
         except Exception:
             pass
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp_
 
         global _CPU_W
         _CPU_W = w
         cores = os.cpu_count() or 1
+        k, combs = cpu_sample(w)
+        mask_cpu = cpu_sample_accepted(w, k, combs)
         with mp_.get_context("fork").Pool(cores) as pool:
-            n, t, n_scanned = cpu_reference_pass(w, cpu_sample_size(w), pool, cores)
+            E_cpu, F_cpu, t = cpu_reference_pass(k, combs, pool, cores)
+        n = int(mask_cpu.sum())
         cpu_baseline = {
-            "value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n_scanned} candidate tuples of the {len(w['families'][-1])}-body model on frame 0 "
-                      f"({n} accepted, {t:.1f} s), culling included; NumPy oracle port, one process per core",
+            "value": n / t, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+            "sample": sample_text(w, len(combs), n) + f"; {t:.1f} s; " +
+                      ("unmodified reference predict_gdml (oracle/_ref), one process per core" if cpu_kind() == "reference"
+                       else "NumPy oracle port, one process per core"),
         }
+        # parity on the benchmark workload itself: the same sampled tuples through the GPU path (explicit combs)
+        from mbgdml_b200.predictors import accept_mask
+
+        order = len(w["families"][k])
+        sc = [s_ for s_ in scalers if s_.order == order]
+        E_gpu, F_gpu = mb.predict_gdml(Z, w["R"][0], eids, combs, models[k], cell, alchemy_scalers=sc)
+        mask_gpu = accept_mask(Z, w["R"][0], eids, combs, models[k], cell)[0] == 1
+        parity = {
+            "checked_against": cpu_baseline["kind"], "n_candidates": int(len(combs)), "n_fragments": n,
+            "accept_mask_equal": bool(np.array_equal(mask_gpu, mask_cpu)),
+            "max_rel_err_E": float(abs(E_gpu - E_cpu) / max(abs(E_cpu), 1e-300)),
+            "max_rel_err_F": float(np.abs(F_gpu - F_cpu).max() / max(np.abs(F_cpu).max(), 1e-300)),
+            "tolerance": 1e-9,
+        }
+        parity["ok"] = bool(parity["accept_mask_equal"] and parity["max_rel_err_E"] <= 1e-9 and parity["max_rel_err_F"] <= 1e-9)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -436,7 +555,8 @@ def run_gpu_arm(args):
             "parallelism": f"fragment-sharded x{world}, one all-reduce" if world > 1 else "single GPU",
             "l2": "flushed between steps (256 MiB fill, untimed); model tables are L2-resident by design within a step",
         },
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "multi_gpu_check": mg_check,
+        "strong": strong,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(R_host.nbytes), "d2h_bytes_per_step": int(8 * n_frames * (1 + 3 * n_atoms))},
         "gpu_launches": int(nl.item()), "clocks": clocks,
@@ -464,6 +584,7 @@ def main():
                     help="weak: --frames per GPU (default); strong: --frames in total, fragments sharded over the GPUs")
     ap.add_argument("--n-train", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (one 64-H2O structure)")
     ap.add_argument("--contraction", default="auto", choices=["auto", "fma", "dmma"],
                     help="contraction kernel: FP64 tensor pipe (dmma, default) or FMA pipe (fma)")
     args = ap.parse_args()

@@ -164,6 +164,16 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc *sys, const double *R, 
 int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc *sys, const double *R,
                        const mbg_job *job, uint32_t flags, double *E, double *F, mbg_job_stats *stats);
 
+/* The accept decision predict_gdml takes for every candidate fragment before it evaluates the model
+ * (gdml_predict.py:214-235: slice -> Cell.r_mic, periodic.py:61-107 -> Criteria.accept, descriptors.py:65-103),
+ * for all frames of R[n_frames][n_atoms][3] and one job: mask[n_frames][candidates per frame], candidates in the
+ * job's own order (product order of the sets, or the explicit tuples); 0 = tuple not strictly ascending (gen_combs
+ * never yields it), 1 = accepted (the fragment is evaluated), 2 = yielded but rejected by the cell cut-off or the
+ * criteria.  *n_per_frame receives the candidates per frame; call with mask == NULL to size the buffer.
+ * Host buffers (R may be a device pointer with MBG_FLAG_R_ON_DEVICE). */
+int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc *sys, const double *R, int32_t n_frames,
+                    const mbg_job *job, uint32_t flags, uint8_t *mask, int64_t *n_per_frame);
+
 /* utils.gen_combs (utils.py:449-489) on device.  Call with combs == NULL to get the count,
  * then with a buffer of [*n_combs][order] int32. */
 int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t *set_offsets,

@@ -177,3 +177,24 @@ def predict_decomp(ctx, Z, R, entity_ids, model, entity_combs, alchemy_scalers=N
         _native.check(ctx.lib.mbg_predict_decomp(ctx.handle, C.byref(system.desc), R.ctypes.data, C.byref(job), 0,
                                                  E.ctypes.data, F.ctypes.data, C.byref(st)))
     return E, F
+
+
+def accept_mask(ctx, Z, R, entity_ids, model, entity_combs, periodic_cell=None):
+    """Accept decision of every candidate fragment (0 not ascending / 1 accepted / 2 rejected), all frames:
+    uint8 array (n_frames, candidates per frame) in the job's candidate order (gdml_predict.py:214-235)."""
+    R = _native.as_f64(R)
+    if R.ndim == 2:
+        R = R[None]
+    system = cached_system(Z, entity_ids, periodic_cell, _needs_masses([model]))
+    if system.n_atoms != R.shape[1]:
+        raise ValueError("R and Z disagree on the number of atoms")
+    keep = []
+    job = make_job(ctx, model, entity_combs, None, keep)
+    n = C.c_int64(0)
+    _native.check(ctx.lib.mbg_accept_mask(ctx.handle, C.byref(system.desc), R.ctypes.data, R.shape[0], C.byref(job), 0,
+                                          None, C.byref(n)))
+    mask = np.zeros((R.shape[0], n.value), dtype=np.uint8)
+    if mask.size:
+        _native.check(ctx.lib.mbg_accept_mask(ctx.handle, C.byref(system.desc), R.ctypes.data, R.shape[0], C.byref(job),
+                                              0, mask.ctypes.data, C.byref(n)))
+    return mask

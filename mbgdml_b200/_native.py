@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "mbg_last_error", "mbg_abi_version", "mbg_device_count", "mbg_context_create", "mbg_context_destroy",
     "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
-    "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_enumerate",
+    "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_accept_mask", "mbg_enumerate",
     "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
     "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
 ]
@@ -103,6 +103,8 @@ def load_library():
                                     C.POINTER(JobStats)]
         lib.mbg_predict_decomp.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.POINTER(Job), C.c_uint32,
                                            C.c_void_p, C.c_void_p, C.POINTER(JobStats)]
+        lib.mbg_accept_mask.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.c_int32, C.POINTER(Job), C.c_uint32,
+                                        C.c_void_p, _lp]
         lib.mbg_enumerate.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, _lp]
         lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
         lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
@@ -163,6 +165,7 @@ class Context:
         check(self.lib.mbg_context_create(self.device, C.byref(h)))
         self.handle = h
         self._models = {}
+        self._stream = 0  # 0 = the context's own stream
 
     def close(self):
         if getattr(self, "handle", None):
@@ -179,7 +182,15 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream):
-        check(self.lib.mbg_context_set_stream(self.handle, C.c_void_p(cuda_stream)))
+        """Run on an existing CUDA stream handle (0 / None: the context's own stream; 1: cudaStreamLegacy)."""
+        check(self.lib.mbg_context_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+        self._stream = int(cuda_stream or 0)
+
+    def swap_stream(self, cuda_stream):
+        """set_stream, returning the previous handle (so that a caller can restore it)."""
+        prev = self._stream
+        self.set_stream(cuda_stream)
+        return prev
 
     def set_contraction(self, kind):
         """'auto' | 'fma' | 'dmma': which kernel evaluates the Matern contraction."""

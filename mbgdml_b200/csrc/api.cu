@@ -1187,6 +1187,53 @@ int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc* sys, const doub
   return MBG_OK;
 }
 
+int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, int32_t n_frames, const mbg_job* job,
+                    uint32_t flags, uint8_t* mask, int64_t* n_per_frame) {
+  if (!ctx || !sys || !R || !job || !n_per_frame) return fail(MBG_ERR_ARG, "NULL argument");
+  if (n_frames < 0) return fail(MBG_ERR_ARG, "negative count");
+  if (flags & ~(uint32_t)MBG_FLAG_R_ON_DEVICE) return fail(MBG_ERR_UNSUPPORTED, "flag not supported by mbg_accept_mask");
+  if (!job->model) return fail(MBG_ERR_ARG, "job without model");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  SysDev s;
+  memset(&s, 0, sizeof(s));
+  TRY(upload_system(ctx, sys, s));
+  const mbg_model_t m = job->model;
+  const size_t n_ints = job->combs ? (size_t)std::max<int64_t>(job->n_combs, 0) * m->order
+                                   : (job->set_offsets ? (size_t)job->set_offsets[m->order] : 0);
+  TRY(ctx->job_ints.ensure((n_ints + 64) * sizeof(int)));
+  JobDev j;
+  size_t used = 0;
+  TRY(build_job(ctx, sys, job, 0, j, &used));
+  *n_per_frame = j.cand_per_frame;
+  if (!mask || n_frames == 0 || j.cand_per_frame == 0) return MBG_OK;
+  const size_t nR = (size_t)n_frames * sys->n_atoms * 3;
+  const double* dR = R;
+  if (!(flags & MBG_FLAG_R_ON_DEVICE)) {
+    TRY(ctx->R.ensure(nR * sizeof(double) + 8));
+    CUDA_TRY(cudaMemcpyAsync(ctx->R.p, R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dR = ctx->R.as<double>();
+  }
+  const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
+  const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads, kChunk = 1ll << 18;
+  for (long long g0 = 0; g0 < n_granules; g0 += kChunk) {
+    const int blocks = (int)std::min(kChunk, n_granules - g0);
+    TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
+    TRY(ctx->blk_acc.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->blk_enum.ensure((size_t)blocks * sizeof(int)));
+    CullArgs ca;
+    ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
+    ca.n_cand_total = n_cand_total, ca.granule0 = g0;
+    ca.shard_rank = 0, ca.shard_count = 1;
+    ca.flags = ctx->flags.as<unsigned char>();
+    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    TRY(launch_cull(ctx, m->n_atoms, blocks, ca));
+    const long long lo = g0 * kCullThreads, n = std::min<long long>((long long)blocks * kCullThreads, n_cand_total - lo);
+    CUDA_TRY(cudaMemcpyAsync(mask + lo, ctx->flags.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return MBG_OK;
+}
+
 int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t* set_offsets, const int32_t* set_entities,
                   int32_t* combs, int64_t* n_combs) {
   if (!ctx || !set_offsets || !set_entities || !n_combs) return fail(MBG_ERR_ARG, "NULL argument");

@@ -6,9 +6,9 @@ whole ``R`` batch x all models goes to the GPU in ONE native call (fragment
 enumeration, culling, contraction and scatter all on device); any other callable is
 driven per frame x model exactly as the reference does (mbe.py:1048-1058).
 
-Multi-GPU: one process per GPU.  With ``torch.distributed`` initialised (NCCL), every
-rank evaluates its block-cyclic share of the fragments and the per-atom forces,
-energies and virials are summed with a single all-reduce.
+Multi-GPU: one process per GPU, opt-in (``pred.shard_group = torch.distributed.group.WORLD``):
+every rank of the NCCL group evaluates its block-cyclic share of the fragments and the per-atom
+forces, energies and virials are summed with a single all-reduce.
 """
 from __future__ import annotations
 
@@ -153,15 +153,27 @@ def decomp_to_total(E_nbody, F_nbody, entity_ids, entity_combs, use_ray=False, n
                        operation="add", use_ray=use_ray, n_workers=n_workers, ray_address=ray_address)
 
 
-def _dist():
-    try:
-        import torch.distributed as dist
+def _shard_group(requested):
+    """The process group a prediction is sharded over, or None for a purely local evaluation (the default, like
+    the reference's ``mbePredict.predict``).  Sharding is OPT-IN -- ``pred.shard_group = dist.group.WORLD`` (or the
+    environment variable MBGDML_B200_SHARD=1 for the default group) -- because it is an SPMD contract: every rank of
+    the group must call ``predict`` with the same (Z, R, entity_ids, comp_ids) the same number of times."""
+    import os
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return dist
-    except Exception:  # pragma: no cover
-        pass
-    return None
+    if requested is None and os.environ.get("MBGDML_B200_SHARD", "0") not in ("1", "true", "True"):
+        return None
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        if requested is not None:
+            raise RuntimeError("shard_group is set but torch.distributed is not initialised")
+        return None
+    group = dist.group.WORLD if requested is None or requested is True else requested
+    if dist.get_world_size(group) <= 1:
+        return None
+    if dist.get_backend(group) != "nccl":
+        raise RuntimeError("fragment sharding all-reduces a CUDA buffer: the process group must use the NCCL backend")
+    return group
 
 
 class mbePredict:  # pylint: disable=invalid-name
@@ -199,6 +211,7 @@ class mbePredict:  # pylint: disable=invalid-name
         self.only_normal_stress = False
         self.box_scaling_type = "anisotropic"
         self.last_stats = None
+        self.shard_group = None  # opt-in multi-GPU fragment sharding (see _shard_group)
 
     @property
     def periodic_cell(self):
@@ -257,30 +270,35 @@ class mbePredict:  # pylint: disable=invalid-name
         ctx = _native.get_context()
         sources = [gen_combs(self.get_avail_entities(comp_ids, m.comp_ids)) for m in self.models]
         scalers = [self._scalers_for(m) for m in self.models]
-        dist = _dist()
-        if dist is None:
+        group = _shard_group(self.shard_group)
+        if group is None:
             E, F, V, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
                                                    self.periodic_cell, compute_virial=want_virial)
             self.last_stats = stats
             return E, F, V
         import torch
+        import torch.distributed as dist
 
         dev = torch.device("cuda", ctx.device)
         n_frames, n_atoms = R.shape[0], R.shape[1]
-        # one flat buffer [E | F | virial] so that a single all-reduce carries everything
+        # one flat buffer [E | F | virial] so that a single all-reduce carries everything; mbg_predict zeroes it on
+        # the stream it runs on (torch.empty: no fill kernel of ours on a stream the library does not order against)
         n_E, n_F, n_V = n_frames, n_frames * n_atoms * 3, n_frames * 9 if want_virial else 0
-        buf = torch.zeros(n_E + n_F + n_V, dtype=torch.float64, device=dev)
+        buf = torch.empty(n_E + n_F + n_V, dtype=torch.float64, device=dev)
         E_t, F_t = buf[:n_E], buf[n_E:n_E + n_F]
         V_t = buf[n_E + n_F:] if want_virial else None
+        # run the library on torch's current stream (NCCL orders the all-reduce after it); the legacy default stream
+        # is addressed by its explicit handle cudaStreamLegacy = 0x1, a NULL handle would select the context's own
         cur = torch.cuda.current_stream(dev).cuda_stream
-        if cur != 0:  # a NULL handle would select the context's own stream, which torch does not order against
-            ctx.set_stream(cur)
-        _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
-                                               self.periodic_cell, compute_virial=want_virial,
-                                               shard=(dist.get_rank(), dist.get_world_size()),
-                                               device_out=(E_t, F_t, V_t))
-        ctx.synchronize()  # the library's stream is idle before NCCL reads the partial sums
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        prev = ctx.swap_stream(cur if cur != 0 else 1)
+        try:
+            _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
+                                                   self.periodic_cell, compute_virial=want_virial,
+                                                   shard=(dist.get_rank(group), dist.get_world_size(group)),
+                                                   device_out=(E_t, F_t, V_t))
+        finally:
+            ctx.swap_stream(prev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         host = buf.cpu().numpy()
         self.last_stats = stats
         E = host[:n_E].copy()

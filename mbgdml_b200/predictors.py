@@ -44,3 +44,12 @@ def predict_gdml_decomp(Z, R, entity_ids, entity_combs, model, **kwargs):
     E, F = _engine.predict_decomp(ctx, Z, R, entity_ids, model, entity_combs_2d,
                                   alchemy_scalers=kwargs.get("alchemy_scalers", None))
     return E, F, entity_combs
+
+
+def accept_mask(Z, R, entity_ids, entity_combs, model, periodic_cell=None):
+    """Which candidate fragments ``predict_gdml`` evaluates (gdml_predict.py:214-235: slice -> ``Cell.r_mic`` ->
+    ``Criteria.accept``), decided on device for one or several frames: uint8 (n_frames, n_candidates) with
+    0 = tuple not ascending (never yielded by ``gen_combs``), 1 = accepted, 2 = rejected.  ``entity_combs`` is a
+    ``gen_combs`` generator (candidates = the product space of its sets) or explicit tuples."""
+    return _engine.accept_mask(_native.get_context(), Z, R, entity_ids, model, entity_combs,
+                               periodic_cell if periodic_cell else None)

@@ -1,0 +1,118 @@
+"""Minimum-image edge stress (the periodic path rests on a restated third-party ``find_mic``).
+
+Two-atom fragments whose separation vector sits a few ulp either side of every discrete decision of
+``Cell.r_mic`` (periodic.py:61-107 -> ase.geometry.find_mic): the fractional coordinate at +-1/2 (the image flips),
+the naive-branch validity test |v| < L_min/2, and the pair cut-off |v| >= cutoff.  The device decision (culling
+kernel, with its first-atom pre-filter and fast-reject shortcut) and the standalone ``mbg_r_mic`` operator must
+equal the oracle's.
+
+* Orthorhombic cells: the device arithmetic is operation-for-operation what NumPy/LAPACK execute for a diagonal
+  cell (f = v * (1/L); v' = f * L), so equality is required at EVERY offset, including 0 and +-1 ulp.
+* Triclinic cells: ``solve(cell.T, v.T)`` runs LAPACK's LU with whatever FMA kernels OpenBLAS picks for the host
+  CPU, the device multiplies by the inverse cell; results differ in the last bit for ~1/4 of the vectors, so the
+  two can only be required to agree outside a band of a few ulp around each threshold (asserted: |k| >= 16 ulp);
+  inside the band the number of disagreements is reported, not asserted.
+"""
+import numpy as np
+import pytest
+
+import mbgdml_b200 as mb
+from mbgdml_b200 import synthetic
+from mbgdml_b200.predictors import accept_mask
+from oracle import cull_vec
+from oracle import mbgdml_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CELLS = {
+    "cubic": np.eye(3) * 16.12,
+    "ortho": np.diag([16.12, 17.3, 19.9]),
+    "triclinic": np.array([[12.6, 0.0, 0.0], [2.8, 12.1, 0.0], [-1.9, 3.1, 11.8]]),
+}
+KS = np.arange(-24, 25)
+
+
+def _step(x, k):
+    """x moved by k ulp (element-wise)."""
+    x = np.array(x, dtype=np.float64)
+    for _ in range(abs(int(k))):
+        x = np.nextafter(x, np.inf if k > 0 else -np.inf)
+    return x
+
+
+def _edge_vectors(cell, cutoff, rng):
+    """Separation vectors around the decision thresholds, with the ulp offset of each (None = generic)."""
+    vecs, ks = [], []
+    lat = [np.zeros(3)] + [cell.T @ np.array(s, dtype=float) for s in ((1, 0, 0), (0, -1, 0), (1, 1, -1), (-2, 0, 1))]
+    # (1) fractional coordinate at +-1/2 along every axis (image flip), other two fractions generic / zero
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            for other in (np.zeros(3), rng.uniform(-0.2, 0.2, 3)):
+                f0 = other.copy()
+                f0[axis] = 0.5 * sign
+                v0 = f0 @ cell
+                for k in KS:
+                    v = v0.copy()
+                    j = int(np.argmax(np.abs(cell[axis])))  # move the component that carries this axis
+                    v[j] = _step(v[j], k)
+                    for s in lat[:3]:
+                        vecs.append(v + s), ks.append(k)
+    # (2) |v| at the pair cut-off and at L_min/2 in generic directions
+    half = 0.5 * np.min(np.linalg.norm(cell, axis=1))
+    for target in (cutoff, half):
+        for _ in range(12):
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            v0 = u * target
+            for k in KS:
+                v = v0.copy()
+                j = int(np.argmax(np.abs(u)))
+                v[j] = _step(v[j], 3 * k)  # the norm moves by about |u_j| ulp per step
+                for s in lat:
+                    vecs.append(v + s), ks.append(3 * k)
+    # (3) generic vectors all over a 3x3x3 block of cells
+    for _ in range(4000):
+        vecs.append(rng.uniform(-1.5, 1.5, 3) @ cell), ks.append(10 ** 6)
+    return np.array(vecs), np.array(ks)
+
+
+@pytest.mark.parametrize("cell_name", ["cubic", "ortho", "triclinic"])
+@pytest.mark.parametrize("cutoff_frac", [1.0, 0.85, 1.2])
+def test_mic_decisions_at_ulp_edges(cell_name, cutoff_frac):
+    cell_v = CELLS[cell_name]
+    half = 0.5 * np.min(np.linalg.norm(cell_v, axis=1))
+    cutoff = None if cutoff_frac == 1.0 else cutoff_frac * half
+    rng = np.random.default_rng(7)
+    d, ks = _edge_vectors(cell_v, half if cutoff is None else cutoff, rng)
+    n = len(d)
+    # system: n two-atom entities; atom 0 of half of them at the origin (d exact), the rest anywhere in the cell
+    p0 = np.where((np.arange(n) % 2 == 0)[:, None], 0.0, rng.uniform(0, 1, (n, 3)) @ cell_v)
+    R = np.stack([p0, p0 + d], axis=1).reshape(2 * n, 3)
+    Z, eids = np.tile(synthetic.HF_Z, n), np.repeat(np.arange(n), 2)
+    md = synthetic.make_model(["hf"], n_train=4, sig=10.0, seed=0)
+    model, om = mb.gdmlModel(dict(md)), orc.Model(dict(md))
+    cell, ocell = mb.Cell(cell_v, cutoff=cutoff, pbc=True), orc.Cell(cell_v, cutoff=cutoff)
+    combs = np.arange(n).reshape(-1, 1)
+    got = accept_mask(Z, R, eids, combs, model, cell)[0] == 1
+    want, _, r_want = cull_vec.accept_mask(Z, R, eids, combs, om, ocell, return_coords=True)
+    # the vectorised oracle is itself the scalar oracle (spot check here, full check in test_oracle_cull_vec.py)
+    for i in rng.choice(n, 300, replace=False):
+        assert (ocell.r_mic(R[2 * i:2 * i + 2]) is not None) == bool(want[i])
+    diff = got != want
+    print(f"{cell_name} cutoff x{cutoff_frac}: {n} edge fragments, {int(want.sum())} accepted, "
+          f"{int(diff.sum())} decisions differ (|ulp offset| of those: {sorted(set(np.abs(ks[diff]).tolist()))})")
+    if cell_name == "triclinic":
+        assert not diff[np.abs(ks) >= 16].any()
+    else:
+        assert not diff.any()
+    # standalone operator: same decision and, when accepted, the same coordinates (bit for bit on diagonal cells)
+    ctx_sel = rng.choice(n, 400, replace=False)
+    for i in ctx_sel:
+        out = cell.r_mic(R[2 * i:2 * i + 2])
+        if cell_name != "triclinic" or abs(ks[i]) >= 16:
+            assert (out is not None) == bool(want[i])
+        if out is not None and want[i]:
+            if cell_name == "triclinic":
+                assert np.abs(out - r_want[i]).max() <= 1e-13 * np.abs(cell_v).max()
+            else:
+                assert np.array_equal(out, r_want[i])

@@ -35,6 +35,16 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the product's sharding switch: local by default although a process group exists (the reference's predict is a
+    # local call); an explicit group must be NCCL (the all-reduce runs on a CUDA buffer)
+    from mbgdml_b200 import mbe as _mbe
+
+    assert _mbe._shard_group(None) is None
+    try:
+        _mbe._shard_group(dist.group.WORLD)
+        raise AssertionError("a gloo group must be refused")
+    except RuntimeError:
+        pass
     g = load("cluster_6h2o.npz")
     mds = unpack_models(g)
     Z, R, eids, cids = g["Z"], g["R"], g["entity_ids"], g["comp_ids"]

@@ -28,6 +28,7 @@ def main():
     al = [mb.mbeAlchemyScale(int(e), int(o), mb.linear_switching, {"factor": float(f)}) for e, o, f in g["alch"]]
     pred = mb.mbePredict(models, mb.predict_gdml, alchemy_scalers=al, periodic_cell=mb.Cell(g["cub_cell"], pbc=True),
                          compute_stress=True)
+    pred.shard_group = dist.group.WORLD  # sharding is opt-in
     E, F, S = pred.predict(g["cub_Z"], g["cub_R"], g["cub_eids"], g["cub_cids"])
     errs = (relerr(E, g["cub_E"]), relerr(F, g["cub_F"]), relerr(S, g["cub_stress"]))
     acc = torch.tensor([s[2] for s in pred.last_stats], dtype=torch.float64, device="cuda")
