@@ -12,6 +12,10 @@
 
 namespace mbg {
 
+// Relative guard band of the exact early-outs: a shortcut may only decide when the quantity is beyond its
+// threshold by more than any rounding difference between the shortcut's arithmetic and the full evaluation.
+constexpr double kGuard = 1.0 + 1e-9;
+
 __device__ __forceinline__ double norm3_rn(double x, double y, double z) {
   // sqrt((x*x + y*y) + z*z) with each operation rounded (scipy pdist / np.linalg.norm over 3 components)
   return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
@@ -141,18 +145,22 @@ __device__ __forceinline__ bool fragment_coords(const SysDev& s, const double* _
   }
   if (!s.periodic) return true;
   const double r0[3] = {r[0][0], r[0][1], r[0][2]};
-  bool naive_ok = true;
+  bool naive_ok = true, naive_far = false;
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
     const double d[3] = {__dsub_rn(r[a][0], r0[0]), __dsub_rn(r[a][1], r0[1]), __dsub_rn(r[a][2], r0[2])};
     double v[3];
     const double len = mic_naive(s, d, v);
     naive_ok = naive_ok && (len < s.half_min_len);
+    naive_far = naive_far || (len >= s.half_min_len * kGuard);
     r[a][0] = v[0], r[a][1] = v[1], r[a][2] = v[2];
   }
   if (!naive_ok) {
-    // find_mic falls back to the general algorithm for the whole set of vectors.
-    if (s.fast_reject) return false;  // some |d_0k| >= L_min/2 >= cutoff: pdist test below must fail
+    // find_mic falls back to the general algorithm for the whole set of vectors.  Shortcut (orthorhombic cell,
+    // cutoff <= L_min/2): some |d_0k| is beyond L_min/2 by more than the rounding differences between the naive and
+    // the general image (a few ulp; the guard is 1e-9), so the general image of that atom is >= cutoff from atom 0
+    // and the pair test below must fail.  Inside the guard band the general branch decides, as in find_mic.
+    if (s.fast_reject && naive_far) return false;
     for (int a = 0; a < NA; ++a) {
       const double* p = Rf + 3 * (long long)atoms[a];
       const double d[3] = {__dsub_rn(p[0], r0[0]), __dsub_rn(p[1], r0[1]), __dsub_rn(p[2], r0[2])};
@@ -227,26 +235,31 @@ __device__ __forceinline__ bool criteria_accept(const CritDev& c, double v) {
 }
 
 // Cheap exact pre-filter for the culling kernel: the subset of fragment_coords' rejection tests that only
-// involves the FIRST atom of every entity (under an orthorhombic cell with cutoff <= L_min/2, where a failed
-// naive minimum image already implies rejection).  Every test here is evaluated by fragment_coords with
-// bit-identical arithmetic, and any single failing test rejects the fragment, so returning false early
-// never changes the accept mask.  Consecutive candidates share their leading entities, so warps exit together.
+// involves the FIRST atom of every entity (under an orthorhombic cell with cutoff <= L_min/2, where a naive
+// minimum image beyond L_min/2 already implies rejection).  It rejects only when a distance is beyond its
+// threshold by the guard band (the fragment's final coordinates may come from the general branch, whose
+// rounding differs from the naive image by a few ulp); everything closer goes to the full evaluation, so
+// returning false early never changes the accept mask.  Consecutive candidates share their leading entities,
+// so warps exit together.
 __device__ __forceinline__ bool first_atoms_may_pass(const SysDev& s, const JobDev& j, const double* __restrict__ Rf,
                                                      const int ent[kMaxOrder]) {
   if (!(s.periodic && s.fast_reject)) return true;
   double v[kMaxOrder][3];
+  bool safe[kMaxOrder];  // the naive image is the unique minimum image, whatever branch find_mic ends up taking
   const double* p0 = Rf + 3ll * s.ent_atoms[s.ent_off[ent[0]]];
 #pragma unroll
   for (int k = 0; k < kMaxOrder; ++k) {
     if (k >= j.order) break;
     const double* p = Rf + 3ll * s.ent_atoms[s.ent_off[ent[k]]];
     const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
-    if (!(mic_naive(s, d, v[k]) < s.half_min_len)) return false;
+    const double len = mic_naive(s, d, v[k]);
+    if (len >= s.half_min_len * kGuard) return false;
+    safe[k] = len * kGuard < s.half_min_len;
 #pragma unroll
     for (int i = 0; i < kMaxOrder; ++i) {
       if (i >= k) break;
       const double dist = norm3_rn(__dsub_rn(v[i][0], v[k][0]), __dsub_rn(v[i][1], v[k][1]), __dsub_rn(v[i][2], v[k][2]));
-      if (dist >= s.cutoff) return false;
+      if (safe[i] && safe[k] && dist >= s.cutoff * kGuard) return false;
     }
   }
   return true;

@@ -1,0 +1,616 @@
+// K3 + K4, persistent form of the tensor-pipe contraction (matern_mma.cuh): one resident CTA per SM whose WARPS
+// are independent workers.  Same arithmetic per (query, training row) pair, same operand layouts and the same
+// whole-phase inner loop as k_matern_mma; what changes is everything around that loop:
+//
+//   * Work item = one group of 8*MT consecutive queries (24 for water trimers: half a fragment) for one warp.
+//     A warp builds the descriptors of its own item, runs all training rows, reduces and scatters its own
+//     partial forces -- no CTA-wide barrier anywhere.  The first item of every warp is assigned statically
+//     (group i -> CTA i mod n, warp i / n, so a small job spreads evenly over the SMs), the following ones come
+//     from a device counter (atomicAdd), so there are no waves and no tail.
+//   * The fragment count is read on the device (n_frag_dev, written by k_scan_blocks): the launch shape is
+//     always "one CTA per SM" and never depends on how many fragments were accepted -> no host round trip,
+//     and a whole MBE step is capturable in a CUDA graph.
+//   * The model tiles are ONE cyclic TMA stream per CTA shared by all its warps (the sum over training rows
+//     is order-free, so a warp may start its batch at whatever tile is current and stop after one lap).  Any
+//     warp refills a stage once every active warp has released it (per-warp progress words in shared memory).
+//   * The warps of a CTA start their first batch staggered by 1/NW of a lap, so that from then on at most one
+//     warp per scheduler is in its prologue / epilogue at any time while the others keep the FP64 pipe busy:
+//     the ~13 us of fixed cost per 430 us CTA of the wave-launched kernel overlap with DMMA work.
+//   * Small launches are split over the training rows on the DEVICE (row slices chosen from the fragment
+//     count; CTA c works on slice c mod S; partial sums meet in the output atomics).
+//
+// Reference: mbgdml/predictors/gdml_predict.py:94-142 (contraction), 151-163 (J^T F_d), 251-267 (scale, scatter,
+//            virial); mbgdml/_gdml/desc.py:79-233 (descriptor, Jacobian); mbgdml/periodic.py:61-107 (minimum image).
+#pragma once
+#include "matern_mma.cuh"
+
+namespace mbg {
+
+constexpr int kPwMaxSlices = 32;  // row slices a launch can be cut into (device counters per launch)
+
+struct MaternPwArgs {
+  SysDev sys;
+  const double* R;           // [n_frames][n_atoms][3]
+  const double* tiles;       // packed model tiles (mbg_model_create, layout of matern_mma.cuh)
+  const double* mu;          // [D]
+  const double* exp2_table;  // [kMmaExpTable]
+  const int* iperm;          // [P][D]
+  int P;
+  int n_row_blocks;  // ceil(T / 8)
+  int max_slices;    // upper bound of the device-side row-slice choice (power of two, <= kPwMaxSlices)
+  double sig, c, std;
+  long long n_frag;             // fragment records (an upper bound when n_frag_dev is set)
+  const long long* n_frag_dev;  // optional: the accepted count on the device
+  const int* rec_frame;
+  const int* rec_atoms;
+  const double* rec_lambda;
+  const long long* rec_slot;
+  int n_slots_per_frame;
+  int decomp;
+  int want_virial;
+  double* E;
+  double* F;
+  double* virial;
+  unsigned int* work_counters;  // [kPwMaxSlices], zero before the launch: dynamic work counter per row slice
+};
+
+// rows of an m-tile staged per pass of the epilogue's un-permute (8, or fewer for wide descriptors)
+__host__ __device__ constexpr int pw_stage_rows(int na) { return na * (na - 1) / 2 + 1 <= 80 ? 8 : (na * (na - 1) / 2 + 1 <= 128 ? 4 : 2); }
+
+template <int NA, int MT>
+__host__ __device__ constexpr int pw_max_frag(int P) {
+  return (8 * MT + P - 1) / P + 1;
+}
+
+// doubles of one warp's private shared-memory region
+template <int NA, int MT, bool YS>
+__host__ __device__ constexpr int pw_warp_doubles(int P) {
+  constexpr int D = NA * (NA - 1) / 2, KS = (D + 3) / 4;
+  const int maxf = pw_max_frag<NA, MT>(P);
+  const int stage = pw_stage_rows(NA) * (D + 1);
+  const int ys = YS ? MT * KS * 32 : 0;
+  return maxf * D + maxf * NA * 3 + maxf * (D + 1) + ((maxf + 1) / 2) + (ys > stage ? ys : stage);
+}
+
+template <int NA, int MT, int NW, bool YS>
+__host__ __device__ constexpr size_t pw_smem_bytes(int P) {
+  constexpr int D = NA * (NA - 1) / 2;
+  return (size_t)kMmaStages * mma_tile_doubles(NA) * 8 + (size_t)kMmaExpTable * 8 + (kMmaStages + 1) * 8 +
+         (size_t)(NW + 4) * 4 + 8 + (size_t)(D + 1) * 8 + (size_t)NW * pw_warp_doubles<NA, MT, YS>(P) * 8 + 64;
+}
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+
+template <int NA, int MT, int NW, bool USE_E, bool YS>
+__global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant__ MaternPwArgs a) {
+  using S = MmaShape<NA>;
+  constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
+  constexpr int TR = mma_tile_rows(NA), ST = kMmaStages, BPT = TR / 8;
+  constexpr int TILE = mma_tile_doubles(NA);
+  constexpr int QW = 8 * MT;  // queries per work item
+  constexpr int RP = pw_stage_rows(NA);
+  constexpr uint32_t kTileBytes = TILE * 8;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, l = lane & 3;
+  const int P = a.P;
+  const int maxf = pw_max_frag<NA, MT>(P);
+
+  // ---- launch-wide work description, derived identically by every thread -----------------------------------
+  const long long n_frag = a.n_frag_dev ? min(a.n_frag, *a.n_frag_dev) : a.n_frag;
+  const long long nq = n_frag * P;
+  const long long n_groups = (nq + QW - 1) / QW;
+  const int n_tiles_data = (a.n_row_blocks + BPT - 1) / BPT;  // tiles that hold training rows
+  int n_sl = 1;
+  {
+    const long long slots = (long long)gridDim.x * NW;
+    while (n_sl * 2 <= a.max_slices && n_groups * n_sl < slots) n_sl *= 2;
+  }
+  const int tps = (n_tiles_data + n_sl - 1) / n_sl;  // tiles per row slice
+  n_sl = (n_tiles_data + tps - 1) / tps;             // slices that hold data
+  const int slice = (int)(blockIdx.x % n_sl), rank = (int)(blockIdx.x / n_sl);
+  const int n_cta_sl = ((int)gridDim.x - slice + n_sl - 1) / n_sl;  // CTAs working on this slice
+  if (rank >= n_groups) return;  // no work can reach this CTA (whole CTA, before any barrier or copy)
+  const int tile0 = slice * tps;
+  const int nts = min(tps, n_tiles_data - tile0);                 // tiles of this slice (one lap of the stream)
+  const int NBs = min(a.n_row_blocks - tile0 * BPT, nts * BPT);   // row blocks of this slice that hold data
+  const double* __restrict__ gtiles = a.tiles + (size_t)tile0 * TILE;
+  // staggered start only pays when every warp runs several batches
+  const bool stagger = n_groups >= 4ll * n_cta_sl * NW;
+
+  // ---- shared memory ------------------------------------------------------------------------------------------
+  double* tiles = reinterpret_cast<double*>(smem_raw);                  // [ST][TILE]
+  double* etab = tiles + (size_t)ST * TILE;                             // [4096]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(etab + kMmaExpTable);    // full[ST], table
+  int* ctl = reinterpret_cast<int*>(bars + ST + 1);                     // next_issue, n_retired, pad, pad, progress[NW]
+  int* next_issue = ctl;
+  int* n_retired = ctl + 1;
+  int* progress = ctl + 4;
+  double* mus = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(progress + NW + 1) + 7 & ~(uintptr_t)7);  // [D + 1]
+  double* wbase = mus + D + 1 + ((D + 1) & 1);
+  double* xs = wbase + (size_t)warp * pw_warp_doubles<NA, MT, YS>(P);   // [maxf][D]
+  double* rs = xs + (size_t)maxf * D;                                   // [maxf][NA][3]
+  double* Fd = rs + (size_t)maxf * NA * 3;                              // [maxf][D + 1]: F_d and E_raw per fragment
+  int* bad = reinterpret_cast<int*>(Fd + (size_t)maxf * (D + 1));       // [maxf]
+  double* ysw = reinterpret_cast<double*>(bad) + (maxf + 1) / 2;        // YS: [MT][KS][32]; epilogue: [RP][D + 1]
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < ST; ++s) mbar_init(&bars[s], 1);
+    mbar_init(&bars[ST], 1);
+    *next_issue = 0, *n_retired = 0;
+    for (int w = 0; w < NW; ++w) progress[w] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = tid; k < D; k += NW * 32) mus[k] = a.mu[k];
+  __syncthreads();  // the only CTA-wide barrier of the kernel
+  if (tid == 0) {
+    mbar_expect_tx(&bars[ST], kMmaExpTable * 8);
+    tma_load_1d(etab, a.exp2_table, kMmaExpTable * 8, &bars[ST]);
+  }
+
+  const uint32_t tiles_s = smem_u32(tiles);
+  // Refill duty, shared by all warps (warp-collective): issue every tile whose stage all active warps have
+  // released; block only for a tile this warp needs now (k_need).
+  auto produce = [&](const int k_need) {
+    for (;;) {
+      const int ni = ld_volatile_s32(next_issue);
+      const bool must = ni <= k_need;
+      if (ni >= ST) {
+        int pr = lane < NW ? ld_volatile_s32(progress + lane) : 0x7fffffff;
+        pr = __reduce_min_sync(0xffffffffu, pr);
+        if (pr < ni - ST + 1) {  // someone still reads the tile in that stage
+          if (!must) break;
+          __nanosleep(64);
+          continue;
+        }
+      }
+      int won = 0;
+      if (lane == 0) {
+        won = atomicCAS(next_issue, ni, ni + 1) == ni;
+        if (won) {
+          const int s = ni % ST;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&bars[s], kTileBytes);
+          tma_load_1d(tiles + (size_t)s * TILE, gtiles + (size_t)(ni % nts) * TILE, kTileBytes, &bars[s]);
+        }
+      }
+      (void)__shfl_sync(0xffffffffu, won, 0);
+    }
+  };
+  auto acquire = [&](const int k) {  // tile k is in shared memory when this returns
+    produce(k);
+    mbar_wait(&bars[k % ST], (k / ST) & 1);
+  };
+  auto release = [&](const int k) {  // this warp will not read tile k again
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      st_volatile_s32(progress + warp, k + 1);
+    }
+  };
+
+  int kt = 0;  // sequence number of the next tile this warp consumes (tile index = tile0 + kt mod nts)
+  if (stagger) {
+    const int skip = (int)((long long)warp * nts / NW);
+    for (; kt < skip; ++kt) {
+      acquire(kt);
+      release(kt);
+    }
+  }
+
+  const double sig = a.sig;
+  const double k64 = -(double)kMmaExpTable * 1.4426950408889634 / sig;
+  const double kc1 = sig / 5.0, kc0 = sig * sig / 5.0;
+  const double s_max = (3900000.0 / k64) * (3900000.0 / k64);
+  const int hi_max = __double2hiint(s_max);
+  const int offB1 = mma_tau(g) * Dp + l;
+  const int offB2[2] = {mma_tau(2 * l) * Dp + g, mma_tau(2 * l + 1) * Dp + g};
+  constexpr uint32_t kPlane = TR * Dp * 8;
+  const uint32_t ys_s = smem_u32(ysw + lane);
+  const double kMagic = 6755399441055744.0;
+  bool table_ready = false;
+
+  long long grp = (long long)warp * n_cta_sl + rank;  // static first item
+  const unsigned dyn0 = (unsigned)n_cta_sl * NW;
+
+  while (grp < n_groups) {
+    // prefetch the id of the next item (dynamic part of the schedule)
+    unsigned nxt_dyn = 0;
+    if (lane == 0) nxt_dyn = atomicAdd(a.work_counters + slice, 1u);
+
+    // ---- prologue: geometry + descriptors of this item's fragments, query operands ----------------------------
+    const long long q0 = grp * QW;
+    const long long q_end = (q0 + QW < nq) ? q0 + QW : nq;
+    const long long f_lo = q0 / P;
+    const int nf = (int)((q_end - 1) / P - f_lo) + 1;
+    for (int fl = lane; fl < nf; fl += 32) bad[fl] = 0;
+    for (int idx = lane; idx < nf * (D + 1); idx += 32) Fd[idx] = 0.0;
+    __syncwarp();
+    for (int idx = lane; idx < nf * NA; idx += 32) {
+      const int fl = idx / NA, k = idx - fl * NA;
+      const long long frag = f_lo + fl;
+      const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
+      const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
+      double v[3] = {p[0], p[1], p[2]};
+      if (a.sys.periodic) {
+        const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
+        const double d[3] = {__dsub_rn(v[0], p0[0]), __dsub_rn(v[1], p0[1]), __dsub_rn(v[2], p0[2])};
+        if (!(mic_naive(a.sys, d, v) < a.sys.half_min_len)) bad[fl] = 1;
+      }
+      rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
+    }
+    __syncwarp();
+    if (a.sys.periodic) {  // find_mic falls back to the general algorithm for the whole fragment
+      for (int idx = lane; idx < nf * NA; idx += 32) {
+        const int fl = idx / NA, k = idx - fl * NA;
+        if (!bad[fl]) continue;
+        const long long frag = f_lo + fl;
+        const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
+        const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
+        const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
+        const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
+        double v[3];
+        mic_general(a.sys, d, v);
+        rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
+      }
+      __syncwarp();
+    }
+    for (int idx = lane; idx < nf * D; idx += 32) {  // x_k = 1 / |r_i - r_j|, np.tril_indices(n, -1) order
+      const int fl = idx / D, k = idx - fl * D;
+      int i = 1;
+#pragma unroll
+      for (int ii = 1; ii < NA; ++ii)
+        if (k >= ii * (ii + 1) / 2) i = ii + 1;
+      const int j = k - i * (i - 1) / 2;
+      const double* ri = rs + (fl * NA + i) * 3;
+      const double* rj = rs + (fl * NA + j) * 3;
+      xs[idx] = __ddiv_rn(1.0, norm3_rn(__dsub_rn(ri[0], rj[0]), __dsub_rn(ri[1], rj[1]), __dsub_rn(ri[2], rj[2])));
+    }
+    __syncwarp();
+
+    double Y[YS ? 1 : MT][YS ? 1 : KS], yy5[MT];
+    auto query_info = [&](const long long q0_, const int i, bool& act, int& flq, const int*& ipp) {
+      const long long q = q0_ + 8 * i + g;
+      act = q < nq;
+      flq = act ? (int)(q / P - q0_ / P) : 0;
+      ipp = a.iperm + (act ? (int)(q % P) : 0) * D;
+    };
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      bool act;
+      int flq;
+      const int* ipp;
+      query_info(q0, i, act, flq, ipp);
+      double part = 0.0;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int e = 4 * k + l;
+        const double v = (e < D && act) ? xs[flq * D + ipp[e]] - mus[e] : 0.0;
+        if (YS) ysw[(i * KS + k) * 32 + lane] = v;
+        else Y[YS ? 0 : i][YS ? 0 : k] = v;
+        part = fma(v, v, part);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      yy5[i] = 5.0 * part;
+    }
+    __syncwarp();
+    double G[MT][NT][2];
+    double Eacc[MT], E2[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      Eacc[i] = 0.0, E2[i] = 0.0;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) G[i][n][0] = 0.0, G[i][n][1] = 0.0;
+    }
+    if (!table_ready) {
+      mbar_wait(&bars[ST], 0);
+      table_ready = true;
+    }
+
+    // ---- main loop: one lap over the row blocks of this slice, starting at the current tile ------------------
+    double yb[2][MT];
+    double c1[MT][2], c2[MT][2];
+    double bxr[2], bar[2];
+    int tcy = kt % nts;                                     // position of tile kt in the lap
+    int nbt = min(BPT, NBs - tcy * BPT);                    // row blocks of the current tile that hold data
+    int b = 0;                                              // row block inside the current tile
+    acquire(kt);
+    uint32_t tb = tiles_s + (uint32_t)((kt % ST) * TILE) * 8u;  // shared address of the current tile
+    {  // GEMM 1 of the first block
+      const uint32_t x0 = tb + offB1 * 8;
+      const uint32_t sa = tb + (uint32_t)(2 * TR * Dp) * 8u + (uint32_t)(2 * l) * 16u;
+      const double2 sd0 = lds128v(sa), sd1 = lds128v(sa + 16);
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const double bx = lds64v(x0 + k * 32), ba = lds64v(x0 + kPlane + k * 32);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const double yv = YS ? lds64v(ys_s + (i * KS + k) * 256) : Y[YS ? 0 : i][YS ? 0 : k];
+          if (k == 0) {
+            dmma884_cv(c1[i][0], c1[i][1], yv, bx, sd0.x, sd1.x);
+            dmma884_cv(c2[i][0], c2[i][1], yv, ba, sd0.y, sd1.y);
+          } else {
+            dmma884_v(c1[i][0], c1[i][1], yv, bx);
+            dmma884_v(c2[i][0], c2[i][1], yv, ba);
+          }
+        }
+      }
+    }
+    constexpr int NI = 4 * NT;
+    constexpr int NC = 2 * MT;
+    double wp[MT][2], up[MT][2];
+    double b2r[2];
+#pragma unroll 1
+    for (int it = 0; it < NBs; ++it) {
+      // the block GEMM 1 runs ahead on: next block of this tile, first block of the next tile, or (last iteration)
+      // the current block again, unused
+      const bool last = it == NBs - 1;
+      const bool new_tile = !last && (b + 1 == nbt);
+      uint32_t tbn = tb;
+      int bn = last ? b : b + 1;
+      if (new_tile) {
+        acquire(kt + 1);
+        tbn = tiles_s + (uint32_t)(((kt + 1) % ST) * TILE) * 8u;
+        bn = 0;
+      }
+      const uint32_t xcur = tb + (uint32_t)(b * 8 * Dp) * 8u;
+      const uint32_t xnxt = tbn + (uint32_t)(bn * 8 * Dp + offB1) * 8u;
+      const uint32_t san = tbn + (uint32_t)(2 * TR * Dp) * 8u + (uint32_t)(bn * 8 + 2 * l) * 16u;
+      const double2 sn0 = lds128v(san), sn1 = lds128v(san + 16);  // seeds of the next block
+      double aE0 = 0.0, aE1 = 0.0;
+      if (USE_E) {
+        const uint32_t ae = tb + (uint32_t)(2 * TR * Dp + 2 * TR + b * 8 + 2 * l) * 8u;
+        aE0 = lds64v(ae), aE1 = lds64v(ae + 8);
+      }
+      bxr[0] = lds64v(xnxt), bar[0] = lds64v(xnxt + kPlane);
+      if (YS) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) yb[0][i] = lds64v(ys_s + (i * KS) * 256);
+      }
+      auto G1x = [&](const int k) {
+        if (k < KS) {
+          if (k + 1 < KS) {
+            bxr[(k + 1) & 1] = lds64v(xnxt + (k + 1) * 32), bar[(k + 1) & 1] = lds64v(xnxt + kPlane + (k + 1) * 32);
+            if (YS) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) yb[(k + 1) & 1][i] = lds64v(ys_s + (i * KS + k + 1) * 256);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < MT; ++i) {
+            const double yv = YS ? yb[k & 1][i] : Y[YS ? 0 : i][YS ? 0 : (k < KS ? k : 0)];
+            if (k == 0) {
+              dmma884_cv(c1[i][0], c1[i][1], yv, bxr[0], sn0.x, sn1.x);
+              dmma884_cv(c2[i][0], c2[i][1], yv, bar[0], sn0.y, sn1.y);
+            } else {
+              dmma884_v(c1[i][0], c1[i][1], yv, bxr[k & 1]);
+              dmma884_v(c2[i][0], c2[i][1], yv, bar[k & 1]);
+            }
+          }
+        }
+      };
+      const uint32_t x2[2] = {xcur + offB2[0] * 8, xcur + offB2[1] * 8};
+      auto item_addr = [&](const int q) -> uint32_t {
+        const int par = q / (2 * NT), plane = (q / NT) & 1, n = q % NT;
+        return x2[par] + plane * kPlane + n * 64;
+      };
+      b2r[0] = lds64v(item_addr(0));
+      auto G2x = [&]() {
+#pragma unroll
+        for (int q = 0; q < NI; ++q) {
+          const int par = q / (2 * NT), plane = (q / NT) & 1, n = q % NT;
+          if (q + 1 < NI) b2r[(q + 1) & 1] = lds64v(item_addr(q + 1));
+#pragma unroll
+          for (int i = 0; i < MT; ++i) dmma884_v(G[i][n][0], G[i][n][1], plane ? up[i][par] : wp[i][par], b2r[q & 1]);
+        }
+      };
+      // scalar chains of this block (see matern_mma.cuh for the derivation of every step)
+      double sq[NC], as[NC], g_[NC], h_[NC], r_[NC], t_[NC];
+      int kk[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sq[c] = vfma(c1[c >> 1][c & 1], -10.0, yy5[c >> 1]);  // 5|diff|^2
+#pragma unroll
+      for (int c = 0; c < NC; ++c) as[c] = c2[c >> 1][c & 1];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int hi = min(max(__double2hiint(sq[c]), 0x01A56E1F), hi_max);
+        sq[c] = __hiloint2double(hi, __double2loint(sq[c]));
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(t_[c]) : "d"(sq[c]));
+#pragma unroll
+      for (int c = 0; c < NC; ++c) g_[c] = vmul(sq[c], t_[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) h_[c] = __hiloint2double(__double2hiint(t_[c]) - 0x00100000, 0);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], h_[c], 0.5);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) g_[c] = vfma(g_[c], r_[c], g_[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r_[c] = vfma(-g_[c], g_[c], sq[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) g_[c] = vfma(r_[c], h_[c], g_[c]);  // sqrt(5)|diff|
+#pragma unroll
+      for (int c = 0; c < NC; ++c) t_[c] = vfma(g_[c], k64, kMagic);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sq[c] = vfma(g_[c], kc1, kc0);  // (n + sig) sig/5
+#pragma unroll
+      for (int c = 0; c < NC; ++c) kk[c] = __double2loint(t_[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) t_[c] = vadd(t_[c], -kMagic);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r_[c] = vfma(g_[c], k64, -t_[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) h_[c] = vfma(r_[c], kMmaExpC3, kMmaExpC2);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) t_[c] = etab[kk[c] & (kMmaExpTable - 1)];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) h_[c] = vfma(h_[c], r_[c], kMmaExpC1);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) h_[c] = vmul(h_[c], r_[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) h_[c] = vfma(t_[c], h_[c], t_[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        h_[c] = __hiloint2double(__double2hiint(h_[c]) + ((kk[c] >> kMmaExpBits) << 20), __double2loint(h_[c]));  // ex
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r_[c] = vmul(as[c], h_[c]);  // w
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sq[c] = vmul(sq[c], h_[c]);  // u = c2s
+      if (USE_E) {  // gdml_predict.py:132-140
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const double aE = (c & 1) ? aE1 : aE0;
+          const double nos = g_[c] / sig;
+          r_[c] = fma(aE * (5.0 / sig), sq[c], r_[c]);
+          E2[c >> 1] = fma(aE * h_[c], 1.0 + nos * (1.0 + nos * (1.0 / 3.0)), E2[c >> 1]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) Eacc[c >> 1] = vfma(as[c], sq[c], Eacc[c >> 1]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) wp[c >> 1][c & 1] = r_[c], up[c >> 1][c & 1] = sq[c];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) G1x(k);
+      G2x();
+      if (new_tile || last) {  // this warp is done with the current tile
+        release(kt);
+        ++kt;
+        if (++tcy == nts) tcy = 0;
+        nbt = min(BPT, NBs - tcy * BPT);
+      }
+      tb = tbn, b = bn;
+    }
+
+    // ---- epilogue: G = base (s1 y' - Gacc), un-permute, reduce over this item's queries, project, scatter ----
+    const double base = 5.0 / (3.0 * sig * sig * sig);
+    long long grp_e;  // == grp, hidden from the optimiser so that the item bookkeeping is re-derived here
+    asm volatile("mov.b64 %0, %1;" : "=l"(grp_e) : "l"(grp));
+    const long long q0e = grp_e * QW;
+    const long long q_ende = (q0e + QW < nq) ? q0e + QW : nq;
+    const long long f_loe = q0e / P;
+    const int nfe = (int)((q_ende - 1) / P - f_loe) + 1;
+    double* stg = ysw;  // [RP][D + 1]
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      bool act;
+      int flq;
+      const int* ipp;
+      query_info(q0e, i, act, flq, ipp);
+      double eq = Eacc[i], e2q = E2[i];
+      const double s1q = __shfl_sync(0xffffffffu, G[i][D / 8][(D % 8) & 1], (lane & ~3) | ((D % 8) >> 1));
+      eq += __shfl_xor_sync(0xffffffffu, eq, 1);
+      eq += __shfl_xor_sync(0xffffffffu, eq, 2);
+      if (USE_E) {
+        e2q += __shfl_xor_sync(0xffffffffu, e2q, 1);
+        e2q += __shfl_xor_sync(0xffffffffu, e2q, 2);
+      }
+#pragma unroll
+      for (int pass = 0; pass < 8 / RP; ++pass) {
+        __syncwarp();  // the staging rows (and, first time, the query operands) are no longer read
+        if (g / RP == pass) {
+          double* row = stg + (g % RP) * (D + 1);
+#pragma unroll
+          for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int e = 8 * n + 2 * l + cc;
+              if (e < D) {
+                const int d = ipp[e];
+                const double yv = xs[flq * D + d] - mus[e];
+                row[d] = act ? base * fma(s1q, yv, -G[i][n][cc]) : 0.0;
+              }
+            }
+          if (l == 0) row[D] = act ? fma(base, eq, e2q) : 0.0;
+        }
+        __syncwarp();
+        // rows of this pass: queries q0e + 8 i + pass RP + [0, RP); those of fragment fl are contiguous
+        const long long qa = q0e + 8 * i + pass * RP;
+        for (int idx = lane; idx < nfe * (D + 1); idx += 32) {
+          const int fl = idx / (D + 1), d = idx - fl * (D + 1);
+          const long long fq0 = (f_loe + fl) * P, fq1 = fq0 + P;
+          const int r_lo = (int)(max(fq0, qa) - qa);
+          const int r_hi = (int)(min(min(fq1, q_ende), qa + RP) - qa);
+          double sum = 0.0;
+          for (int r = r_lo; r < r_hi; ++r) sum += stg[r * (D + 1) + d];
+          if (r_hi > r_lo) Fd[idx] += sum;
+        }
+      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < nfe * (NA * 3 + 1); idx += 32) {
+      const int fl = idx / (NA * 3 + 1), rem = idx - fl * (NA * 3 + 1);
+      const long long frag = f_loe + fl;
+      const long long fq0 = frag * P;
+      const double lam = a.rec_lambda[frag];
+      const double* Fdf = Fd + fl * (D + 1);
+      const double* rf = rs + fl * NA * 3;
+      const double* xf = xs + fl * D;
+      if (rem == NA * 3) {
+        const double e = (Fdf[D] * a.std + ((fq0 >= q0e && slice == 0) ? a.c : 0.0)) * lam;
+        double* dst = a.decomp ? a.E + ((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag])
+                               : a.E + a.rec_frame[frag];
+        atomicAdd(dst, e);
+      } else {
+        const int m = rem / 3, c = rem - m * 3;
+        double f = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < NA; ++bb) {
+          if (bb == m) continue;
+          const int i = bb > m ? bb : m, j = bb > m ? m : bb;
+          const double inv = xf[i * (i - 1) / 2 + j];
+          f = fma((rf[bb * 3 + c] - rf[m * 3 + c]) * (inv * inv * inv), Fdf[i * (i - 1) / 2 + j], f);
+        }
+        f *= a.std * lam;
+        double* dst =
+            a.decomp
+                ? a.F + (((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag]) * NA + m) * 3 + c
+                : a.F + ((long long)a.rec_frame[frag] * a.sys.n_atoms + a.rec_atoms[frag * NA + m]) * 3 + c;
+        atomicAdd(dst, f);
+      }
+    }
+    if (a.want_virial) {  // stress.virial_atom_loop on the minimum-image coordinates (gdml_predict.py:266-267)
+      for (int idx = lane; idx < nfe * 9; idx += 32) {
+        const int fl = idx / 9, ij = idx - fl * 9, vi = ij / 3, vj = ij - vi * 3;
+        const long long frag = f_loe + fl;
+        const double* Fdf = Fd + fl * (D + 1);
+        const double* rf = rs + fl * NA * 3;
+        const double* xf = xs + fl * D;
+        double wv = 0.0;
+        for (int m = 0; m < NA; ++m) {
+          double f = 0.0;
+          for (int bb = 0; bb < NA; ++bb) {
+            if (bb == m) continue;
+            const int i = bb > m ? bb : m, j = bb > m ? m : bb;
+            const double inv = xf[i * (i - 1) / 2 + j];
+            f = fma((rf[bb * 3 + vj] - rf[m * 3 + vj]) * (inv * inv * inv), Fdf[i * (i - 1) / 2 + j], f);
+          }
+          wv = fma(rf[m * 3 + vi], f, wv);
+        }
+        atomicAdd(a.virial + (long long)a.rec_frame[frag] * 9 + ij, wv * a.std * a.rec_lambda[frag]);
+      }
+    }
+    __syncwarp();
+    grp = (long long)dyn0 + __shfl_sync(0xffffffffu, nxt_dyn, 0);
+  }
+
+  // ---- retire: stop holding stages; the last warp out waits for the copies still in flight ---------------------
+  __syncwarp();
+  int last_out = 0;
+  if (lane == 0) {
+    st_volatile_s32(progress + warp, 0x7fffffff);
+    __threadfence_block();
+    last_out = atomicAdd(n_retired, 1) == NW - 1;
+  }
+  last_out = __shfl_sync(0xffffffffu, last_out, 0);
+  if (last_out) {
+    const int ni = ld_volatile_s32(next_issue);
+    for (int t = max(kt, ni - ST); t < ni; ++t) mbar_wait(&bars[t % ST], (t / ST) & 1);
+    if (!table_ready) mbar_wait(&bars[ST], 0);
+  }
+}
+
+}  // namespace mbg

@@ -34,13 +34,14 @@ def plugin(ref):
     return mod
 
 
-def _ref_models(ref, dicts, cutoffs, desc="com"):
+def _ref_models(ref, dicts, cutoffs, desc="com", bounds=None):
     out = []
-    for d, cut in zip(dicts, cutoffs):
+    for k, (d, cut) in enumerate(zip(dicts, cutoffs)):
+        bound = "upper" if bounds is None else bounds[k]
         if desc == "com":
-            crit = ref.Criteria(ref.com_distance_sum, {"entity_ids": np.asarray(d["entity_ids"])}, cut)
+            crit = ref.Criteria(ref.com_distance_sum, {"entity_ids": np.asarray(d["entity_ids"])}, cut, bound=bound)
         else:
-            crit = ref.Criteria(ref.max_atom_pair_dist, {}, cut)
+            crit = ref.Criteria(ref.max_atom_pair_dist, {}, cut, bound=bound)
         out.append(ref.gdmlModel(dict(d), criteria=crit))
     return out
 
@@ -58,7 +59,8 @@ def test_reference_driver_with_b200_plugin_cluster(ref, plugin):
     al = [ref.mbeAlchemyScale(int(e), int(o), ref.linear_switching, {"factor": float(f)}) for e, o, f in g["alch"]]
     E, F = ref.mbePredict(_ref_models(ref, mds, cuts), plugin.predict_gdml_b200, alchemy_scalers=al).predict(Z, R, eids, cids)
     assert relerr(E, g["alch_E"]) <= TOL and relerr(F, g["alch_F"]) <= TOL
-    E, F = ref.mbePredict(_ref_models(ref, mds, cuts, desc="pair"), plugin.predict_gdml_b200).predict(Z, R, eids, cids)
+    pair = _ref_models(ref, mds, [None, (3.0, 6.0), 5.5], desc="pair", bounds=["upper", "upper", "lower"])  # make_golden (e)
+    E, F = ref.mbePredict(pair, plugin.predict_gdml_b200).predict(Z, R, eids, cids)
     assert relerr(E, g["pair_E"]) <= TOL and relerr(F, g["pair_F"]) <= TOL
     # and live, side by side with the reference's own predictor on a perturbed geometry
     R2 = R + np.random.default_rng(0).normal(scale=0.03, size=R.shape)
