@@ -485,7 +485,8 @@ def run_gpu_arm(args):
         flop = sum(r["n_fragments"] * rec_flops(r) for r in dom)
         ms = sum(r["ms"] for r in dom)
         achieved = flop / (ms * 1e-3) / 1e12
-        kname = f"k_matern_mma<NA={best['n_frag_atoms']}>" if use_dmma else f"k_matern<NA={best['n_frag_atoms']}>"
+        kname = (f"k_matern_pw<NA={best['n_frag_atoms']}>" if args.contraction in ("auto", "dmma") else
+                 f"k_matern_mma<NA={best['n_frag_atoms']}>" if use_dmma else f"k_matern<NA={best['n_frag_atoms']}>")
         traffic, traffic_source = ncu_traffic(args.workload, best["n_frag_atoms"], args.frames, use_dmma)
         roofline = {
             "bound": "tensor" if use_dmma else "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
@@ -565,7 +566,7 @@ def run_gpu_arm(args):
             {"n_frag_atoms": r["n_frag_atoms"], "n_perms": r["n_perms"], "n_fragments": r["n_fragments"], "ms": round(r["ms"], 4),
              "tflops": round(r["n_fragments"] * rec_flops(r) / (r["ms"] * 1e-3) / 1e12, 2) if r["ms"] > 0 else None}
             for r in recs],
-        "sm_clock_mhz_implied_by_fma_peak": clk_est, "contraction": "dmma" if use_dmma else "fma",
+        "sm_clock_mhz_implied_by_fma_peak": clk_est, "contraction": {"auto": "dmma"}.get(args.contraction, args.contraction),
     }
     print(json.dumps(line))
     if world > 1:
@@ -585,8 +586,9 @@ def main():
     ap.add_argument("--n-train", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (one 64-H2O structure)")
-    ap.add_argument("--contraction", default="auto", choices=["auto", "fma", "dmma"],
-                    help="contraction kernel: FP64 tensor pipe (dmma, default) or FMA pipe (fma)")
+    ap.add_argument("--contraction", default="auto", choices=["auto", "fma", "dmma", "dmma_wave"],
+                    help="contraction kernel: FP64 tensor pipe, persistent per-warp workers (dmma, default), the same "
+                         "arithmetic wave-launched (dmma_wave), or the FMA pipe (fma)")
     args = ap.parse_args()
     if args.frames is None:
         args.frames = {"box140": 8, "trimers64": 4, "monomers": 1, "mixed140": 4}[args.workload]

@@ -36,9 +36,11 @@ extern "C" {
 #define MBG_ERR_NOMEM (-4)
 
 /* Contraction kernel selection (mbg_context_set_contraction). */
-#define MBG_CONTRACT_AUTO 0 /* the faster one for the fragment size (DMMA in this build)                     */
+#define MBG_CONTRACT_AUTO 0 /* = MBG_CONTRACT_DMMA in this build                                              */
 #define MBG_CONTRACT_FMA 1  /* difference form on the FP64 FMA pipe                      (csrc/matern.cuh)     */
-#define MBG_CONTRACT_DMMA 2 /* GEMM recast on the FP64 tensor pipe, mma.sync.m8n8k4.f64  (csrc/matern_mma.cuh) */
+#define MBG_CONTRACT_DMMA 2 /* GEMM recast on the FP64 tensor pipe (mma.sync.m8n8k4.f64), persistent per-warp workers that read the
+                               fragment count on the device: no host round trip inside a call    (csrc/matern_pw.cuh)  */
+#define MBG_CONTRACT_DMMA_WAVE 3 /* the same arithmetic, wave-launched one CTA per query batch   (csrc/matern_mma.cuh) */
 
 #define MBG_MAX_ORDER 8       /* entities per fragment */
 #define MBG_MAX_FRAG_ATOMS 24 /* atoms per fragment */

@@ -20,7 +20,7 @@ MBG_OK, MBG_ERR_ARG, MBG_ERR_CUDA, MBG_ERR_UNSUPPORTED, MBG_ERR_NOMEM = 0, -1, -
 CRIT_NONE, CRIT_COM_DISTANCE_SUM, CRIT_MAX_ATOM_PAIR_DIST = 0, 1, 2
 BOUND_UPPER, BOUND_LOWER, BOUND_RANGE = 0, 1, 2
 FLAG_R_ON_DEVICE, FLAG_OUT_ON_DEVICE, FLAG_VIRIAL, FLAG_ACCUMULATE = 1, 2, 4, 8
-CONTRACT_AUTO, CONTRACT_FMA, CONTRACT_DMMA = 0, 1, 2
+CONTRACT_AUTO, CONTRACT_FMA, CONTRACT_DMMA, CONTRACT_DMMA_WAVE = 0, 1, 2, 3
 
 # every symbol include/mbgdml_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -193,8 +193,8 @@ class Context:
         return prev
 
     def set_contraction(self, kind):
-        """'auto' | 'fma' | 'dmma': which kernel evaluates the Matern contraction."""
-        code = {"auto": CONTRACT_AUTO, "fma": CONTRACT_FMA, "dmma": CONTRACT_DMMA}[kind] if isinstance(kind, str) else kind
+        """'auto' | 'fma' | 'dmma' | 'dmma_wave': which kernel evaluates the Matern contraction."""
+        code = {"auto": CONTRACT_AUTO, "fma": CONTRACT_FMA, "dmma": CONTRACT_DMMA, "dmma_wave": CONTRACT_DMMA_WAVE}[kind] if isinstance(kind, str) else kind
         check(self.lib.mbg_context_set_contraction(self.handle, int(code)))
 
     def synchronize(self):

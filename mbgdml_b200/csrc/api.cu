@@ -15,6 +15,7 @@
 #include "hostmath.h"
 #include "matern.cuh"
 #include "matern_mma.cuh"
+#include "matern_pw.cuh"
 #include "mbe_accum.cuh"
 #include "kernel_mat.cuh"
 
@@ -72,6 +73,8 @@ struct DevBuf {  // growable device allocation
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int kMaxPwLaunches = 1024;  // persistent-kernel launches per call whose counters / counts have their own slot
+constexpr int kMaxJobsPerCall = 256;
 constexpr int kMaxDeferred = 64;            // small jobs per call whose counts are read back once, at the end
 constexpr long long kSmallJobCand = 65536;  // candidates (all frames) up to which a job is "small"
 
@@ -90,6 +93,13 @@ struct mbg_context_s {
   DevBuf km_in, km_ints, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
+  // persistent-kernel path: per-launch device counters and counts (no host round trip inside a call)
+  DevBuf pw_counters;   // [kMaxPwLaunches][kPwMaxSlices] dynamic work counters, zeroed at the start of a call
+  DevBuf chunk_totals;  // [kMaxPwLaunches][2] (accepted, enumerated) of every cull chunk = n_frag_dev of its contraction
+  DevBuf job_totals;    // [kMaxJobsPerCall][2] running sums per job (stats)
+  int n_pw_launch = 0;
+  std::vector<int> rec_chunk_slot;  // launch record -> chunk slot (fragment count resolved lazily), -1: count is exact
+  long long* h_chunk = nullptr;     // pinned [kMaxPwLaunches][2]
   long long* h_totals = nullptr;  // pinned [2 + 2 * kMaxDeferred]
   DevBuf deferred_totals;         // [kMaxDeferred][2]: (accepted, enumerated) of jobs whose counts stay on the device
   int n_deferred = 0;
@@ -114,9 +124,12 @@ struct mbg_model_s {
   double* tiles_mma = nullptr;  // DMMA kernel: packed tiles (matern_mma.cuh)
   double* mu = nullptr;         // DMMA kernel: centre of the training descriptors [D]
   double* alphaE = nullptr;
-  int* iperm = nullptr;
+  int* iperm = nullptr;  // [P][D] pi_p^-1
+  int* perm = nullptr;   // [P][D] pi_p
   CritDev crit;
 };
+
+static inline int mbg_model_rows_padded(int n_row_blocks) { return (n_row_blocks * 8 + kTileRows - 1) / kTileRows * kTileRows; }
 
 static cudaEvent_t next_event(mbg_context_t ctx) {
   if (ctx->ev_used == ctx->ev_pool.size()) {
@@ -298,6 +311,63 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
   }
 }
 
+
+// Persistent per-warp form of the tensor-pipe contraction (matern_pw.cuh): always one CTA per SM; the kernel reads
+// the fragment count on the device, so the launch shape never depends on it.
+template <int NA, int MT, int NW, bool USE_E, bool YS>
+static int launch_matern_pw_t(mbg_context_t ctx, const MaternPwArgs& a_in, int chunk_slot) {
+  MaternPwArgs a = a_in;
+  int dev_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  int nw = NW;  // fewer warps when the per-warp regions (many fragments per item: few permutations) do not fit
+  while (nw > 1 && pw_smem_bytes<NA, MT, NW, YS>(a.P, nw) > (size_t)dev_smem) nw -= (nw > 4 ? 4 : 1);
+  const size_t smem = pw_smem_bytes<NA, MT, NW, YS>(a.P, nw);
+  if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
+  auto kern = k_matern_pw<NA, MT, NW, USE_E, YS>;
+  static thread_local size_t attr_smem = 0;  // per instantiation
+  if (smem > attr_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int n_tiles_data = (a.n_row_blocks + mma_tile_rows(NA) / 8 - 1) / (mma_tile_rows(NA) / 8);
+  a.max_slices = 1;
+  while (a.max_slices * 2 <= kPwMaxSlices && a.max_slices * 4 <= n_tiles_data) a.max_slices *= 2;  // >= 2 tiles per slice
+  if (ctx->mma_cfg == 2) a.max_slices = 1;  // developer: never slice
+  a.work_counters = ctx->pw_counters.as<unsigned int>() + (size_t)(ctx->n_pw_launch % kMaxPwLaunches) * kPwMaxSlices;
+  if (ctx->n_pw_launch >= kMaxPwLaunches)  // slots wrap around: re-zero this one (stream-ordered after its last user)
+    CUDA_TRY(cudaMemsetAsync(a.work_counters, 0, kPwMaxSlices * sizeof(unsigned int), ctx->stream));
+  ctx->n_pw_launch++;
+  cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+  kern<<<ctx->sm_count, nw * 32, smem, ctx->stream>>>(a);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches++;
+  ctx->n_contract++;
+  ctx->launch_recs.push_back({NA, a.n_frag, (mbg_model_rows_padded(a.n_row_blocks)), a.P, 0.f, MBG_CONTRACT_DMMA});
+  ctx->rec_chunk_slot.resize(ctx->launch_recs.size(), -1);
+  ctx->rec_chunk_slot.back() = chunk_slot;
+  CUDA_TRY(cudaGetLastError());
+  return MBG_OK;
+}
+
+static int launch_matern_pw(mbg_context_t ctx, int na, bool use_E, const MaternPwArgs& a, int chunk_slot) {
+  // Shapes as for the wave-launched kernel (profiles/r1_dmma_tuning.md): 9-atom fragments run 12 warps with the
+  // GEMM-1 query operands in shared memory, everything else 8 warps with the operands in registers.
+  if (na == 9 && !use_E && ctx->mma_cfg != 1) return launch_matern_pw_t<9, 3, 12, false, true>(ctx, a, chunk_slot);
+  switch (na) {
+#define X(N)                                                                                        \
+  case N: {                                                                                         \
+    constexpr int MT = (N >= 13) ? 1 : (N >= 10) ? 2 : (N >= 8) ? 3 : 4;                            \
+    return use_E ? launch_matern_pw_t<N, MT, 8, true, false>(ctx, a, chunk_slot)                    \
+                 : launch_matern_pw_t<N, MT, 8, false, false>(ctx, a, chunk_slot);                  \
+  }
+    MBG_FOR_EACH_NA(X)
+#undef X
+    default:
+      return fail(MBG_ERR_UNSUPPORTED, "no contraction kernel for fragments of %d atoms", na);
+  }
+}
+
 static int launch_matern(mbg_context_t ctx, int na, bool use_E, const MaternArgs& a) {
   switch (na) {
 #define X(N) \
@@ -319,8 +389,10 @@ __global__ void k_fill(double* p, long long n, double v) {
 }
 
 // zero the decomposed output rows of accepted fragments (the rest stay NaN)
-__global__ void k_zero_rows(const long long* rec_slot, long long n_rec, int row_len, double* E, double* F) {
+__global__ void k_zero_rows(const long long* rec_slot, long long n_rec, int row_len, double* E, double* F,
+                            const long long* n_rec_dev = nullptr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_rec_dev) n_rec = min(n_rec, *n_rec_dev);
   if (i >= n_rec * (row_len + 1)) return;
   const long long r = i / (row_len + 1);
   const int k = (int)(i - r * (row_len + 1));
@@ -599,7 +671,97 @@ struct Outputs {
   double* V;
 };
 
-// Enumerate + cull + compact + contract one job over n_frames frames.
+
+// Candidates of granules [g0, g0 + blocks) of one shard (every granule is full except the last one of the space).
+static long long shard_candidates(long long g0, long long blocks, int shard_rank, int shard_count, long long n_cand_total) {
+  if (blocks <= 0) return 0;
+  const long long last_lo = ((g0 + blocks - 1) * shard_count + shard_rank) * (long long)kCullThreads;
+  const long long last = std::max(0ll, std::min<long long>(kCullThreads, n_cand_total - last_lo));
+  return (blocks - 1) * (long long)kCullThreads + last;
+}
+
+// Enumerate + cull + compact + contract one job with the persistent contraction kernel: no host synchronisation.
+// Records and flags are sized for the candidates of a chunk (an upper bound of what it accepts); every kernel
+// downstream of the scan reads the accepted count from the device.  The counts for `stats` stay on the device
+// (job_totals[job_slot]) until the caller asks for them.
+static int run_job_pw(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
+                      int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
+                      int job_slot, long long* n_cand_shard_out) {
+  const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
+  const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads;
+  const long long my_granules = n_granules > shard_rank ? (n_granules - shard_rank + shard_count - 1) / shard_count : 0;
+  const int NA = j.n_frag_atoms;
+  *n_cand_shard_out = shard_candidates(0, my_granules, shard_rank, shard_count, n_cand_total);
+  if (my_granules == 0) return MBG_OK;
+  const size_t rec_bytes = 4 + 4 * (size_t)NA + 8 + 8;
+  long long chunk = (long long)((1ull << 30) / (kCullThreads * rec_bytes));  // <= 1 GiB of records per chunk
+  chunk = std::min(std::max(chunk, 1ll << 10), std::min(1ll << 18, my_granules));
+  const size_t n_rec_max = (size_t)chunk * kCullThreads;
+  TRY(ctx->flags.ensure(n_rec_max));
+  TRY(ctx->blk_acc.ensure((size_t)chunk * sizeof(int)));
+  TRY(ctx->blk_enum.ensure((size_t)chunk * sizeof(int)));
+  TRY(ctx->blk_off.ensure((size_t)chunk * sizeof(long long)));
+  TRY(ctx->rec_frame.ensure(n_rec_max * sizeof(int)));
+  TRY(ctx->rec_atoms.ensure(n_rec_max * NA * sizeof(int)));
+  TRY(ctx->rec_lambda.ensure(n_rec_max * sizeof(double)));
+  TRY(ctx->rec_slot.ensure(n_rec_max * sizeof(long long)));
+  long long* job_tot = ctx->job_totals.as<long long>() + 2 * (size_t)job_slot;
+  for (long long g0 = 0; g0 < my_granules; g0 += chunk) {
+    const int blocks = (int)std::min(chunk, my_granules - g0);
+    const int slot = ctx->n_pw_launch % kMaxPwLaunches;  // the contraction launched below takes the same slot
+    long long* totals = ctx->chunk_totals.as<long long>() + 2 * (size_t)slot;
+    CullArgs ca;
+    ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
+    ca.n_cand_total = n_cand_total, ca.granule0 = g0;
+    ca.shard_rank = shard_rank, ca.shard_count = shard_count;
+    ca.flags = ctx->flags.as<unsigned char>();
+    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    TRY(launch_cull(ctx, NA, blocks, ca));
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk_acc.as<int>(), ctx->blk_enum.as<int>(), blocks,
+                                               ctx->blk_off.as<long long>(), totals, job_tot);
+    CompactArgs pa;
+    pa.sys = s, pa.job = j;
+    pa.n_cand_total = n_cand_total, pa.granule0 = g0;
+    pa.shard_rank = shard_rank, pa.shard_count = shard_count;
+    pa.flags = ctx->flags.as<unsigned char>();
+    pa.block_offsets = ctx->blk_off.as<long long>();
+    pa.rec_base = 0;
+    pa.rec_frame = ctx->rec_frame.as<int>(), pa.rec_atoms = ctx->rec_atoms.as<int>();
+    pa.rec_lambda = ctx->rec_lambda.as<double>(), pa.rec_slot = ctx->rec_slot.as<long long>();
+    k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    const long long n_up = shard_candidates(g0, blocks, shard_rank, shard_count, n_cand_total);
+    if (decomp) {
+      const long long n = n_up * (NA * 3 + 1);
+      k_zero_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rec_slot.as<long long>(), n_up, NA * 3,
+                                                                         out.E, out.F, totals);
+      ctx->launches++;
+    }
+    MaternPwArgs a;
+    a.sys = s;
+    a.R = dR;
+    a.tiles = m->tiles_mma, a.mu = m->mu, a.iperm = m->iperm, a.perm = m->perm;
+    a.exp2_table = ctx->exp2_table_mma.as<double>();
+    a.P = m->P;
+    a.n_row_blocks = (m->T + 7) / 8;
+    a.max_slices = 1;
+    a.sig = m->sig, a.c = m->c, a.std = m->std;
+    a.n_frag = n_up, a.n_frag_dev = totals;
+    a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
+    a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
+    a.n_slots_per_frame = (int)j.cand_per_frame;
+    a.decomp = decomp ? 1 : 0;
+    a.want_virial = want_virial ? 1 : 0;
+    a.E = out.E, a.F = out.F, a.virial = out.V;
+    a.work_counters = nullptr;
+    TRY(launch_matern_pw(ctx, NA, m->use_E, a, slot));
+  }
+  return MBG_OK;
+}
+
+// Enumerate + cull + compact + contract one job over n_frames frames (wave-launched and FMA-pipe kernels: the
+// accepted count of large jobs makes a host round trip to size the grid).
 static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
                    int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
                    mbg_job_stats* stats, int* deferred_slot = nullptr) {
@@ -771,10 +933,20 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
   return MBG_OK;
 }
 
+static bool uses_pw(mbg_context_t ctx) {
+  return ctx->contraction == MBG_CONTRACT_AUTO || ctx->contraction == MBG_CONTRACT_DMMA;
+}
+
 static void begin_call(mbg_context_t ctx) {
   ctx->ev_used = 0;
   ctx->n_contract = 0;
   ctx->launch_recs.clear();
+  ctx->rec_chunk_slot.clear();
+  if (ctx->n_pw_launch > 0) {  // re-zero the work counters the previous call used
+    const size_t used = (size_t)std::min(ctx->n_pw_launch, kMaxPwLaunches) * kPwMaxSlices * sizeof(unsigned int);
+    cudaMemsetAsync(ctx->pw_counters.p, 0, used, ctx->stream);
+  }
+  ctx->n_pw_launch = 0;
   cudaEventRecord(ctx->ev_call0, ctx->stream);
 }
 
@@ -799,6 +971,12 @@ static void resolve_timing(mbg_context_t ctx) {
   ctx->ms_contract = contract;
   ctx->ms_other = total - contract;
   ctx->timing_pending = false;
+  // fragment counts of the persistent-kernel launches (they never came to the host during the call)
+  if (!ctx->rec_chunk_slot.empty() && ctx->n_pw_launch > 0 && ctx->n_pw_launch <= kMaxPwLaunches &&
+      cudaMemcpy(ctx->h_chunk, ctx->chunk_totals.p, (size_t)ctx->n_pw_launch * 2 * sizeof(long long),
+                 cudaMemcpyDeviceToHost) == cudaSuccess)
+    for (size_t i = 0; i < ctx->launch_recs.size() && i < ctx->rec_chunk_slot.size(); ++i)
+      if (ctx->rec_chunk_slot[i] >= 0) ctx->launch_recs[i].n_frag = ctx->h_chunk[2 * ctx->rec_chunk_slot[i]];
 }
 
 // ------------------------------------------------------------------------------------
@@ -832,6 +1010,11 @@ int mbg_context_create(int device, mbg_context_t* out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   CUDA_TRY(cudaMallocHost(&ctx->h_totals, (2 + 2 * kMaxDeferred) * sizeof(long long)));
+  CUDA_TRY(cudaMallocHost(&ctx->h_chunk, (size_t)(kMaxPwLaunches + kMaxJobsPerCall) * 2 * sizeof(long long)));
+  TRY(ctx->pw_counters.ensure((size_t)kMaxPwLaunches * kPwMaxSlices * sizeof(unsigned int)));
+  TRY(ctx->chunk_totals.ensure((size_t)kMaxPwLaunches * 2 * sizeof(long long)));
+  TRY(ctx->job_totals.ensure((size_t)kMaxJobsPerCall * 2 * sizeof(long long)));
+  CUDA_TRY(cudaMemset(ctx->pw_counters.p, 0, (size_t)kMaxPwLaunches * kPwMaxSlices * sizeof(unsigned int)));
   {
     double tab[1 << kExpTableBits];
     for (int j = 0; j < (1 << kExpTableBits); ++j) tab[j] = (double)exp2l((long double)j / (1 << kExpTableBits));
@@ -847,6 +1030,7 @@ int mbg_context_create(int device, mbg_context_t* out) {
   if (const char* v = getenv("MBG_CONTRACT")) {  // developer override; mbg_context_set_contraction wins
     if (!strcmp(v, "fma")) ctx->contraction = MBG_CONTRACT_FMA;
     if (!strcmp(v, "dmma")) ctx->contraction = MBG_CONTRACT_DMMA;
+    if (!strcmp(v, "dmma_wave")) ctx->contraction = MBG_CONTRACT_DMMA_WAVE;
   }
   if (const char* v = getenv("MBG_MMA_CFG")) ctx->mma_cfg = atoi(v);
   *out = ctx;
@@ -859,13 +1043,14 @@ int mbg_context_destroy(mbg_context_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints, &ctx->job_binom,
                     &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
-                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in, &ctx->deferred_totals,
+                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in, &ctx->deferred_totals, &ctx->pw_counters, &ctx->chunk_totals, &ctx->job_totals,
                     &ctx->km_ints, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_call0);
   cudaEventDestroy(ctx->ev_call1);
   cudaFreeHost(ctx->h_totals);
+  cudaFreeHost(ctx->h_chunk);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return MBG_OK;
@@ -886,7 +1071,7 @@ int mbg_context_synchronize(mbg_context_t ctx) {
 
 int mbg_context_set_contraction(mbg_context_t ctx, int kind) {
   if (!ctx) return fail(MBG_ERR_ARG, "ctx is NULL");
-  if (kind != MBG_CONTRACT_AUTO && kind != MBG_CONTRACT_FMA && kind != MBG_CONTRACT_DMMA)
+  if (kind != MBG_CONTRACT_AUTO && kind != MBG_CONTRACT_FMA && kind != MBG_CONTRACT_DMMA && kind != MBG_CONTRACT_DMMA_WAVE)
     return fail(MBG_ERR_ARG, "unknown contraction kind %d", kind);
   ctx->contraction = kind;
   return MBG_OK;
@@ -938,7 +1123,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   CUDA_TRY(cudaSetDevice(ctx->device));
   const int D = d->n_atoms * (d->n_atoms - 1) / 2, T = d->n_train, P = d->n_perms;
   // pi_p(dd) = tril_perms_lin[dd*P + p] mod D (gdml_model.py:109-118); must be a permutation of 0..D-1
-  std::vector<int> iperm((size_t)P * D);
+  std::vector<int> iperm((size_t)P * D), fperm((size_t)P * D);
   for (int p = 0; p < P; ++p) {
     std::vector<char> seen(D, 0);
     for (int dd = 0; dd < D; ++dd) {
@@ -948,6 +1133,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
       if (seen[e]) return fail(MBG_ERR_UNSUPPORTED, "tril_perms_lin row %d is not a permutation", p);
       seen[e] = 1;
       iperm[(size_t)p * D + e] = dd;  // pi_p^-1(e) = dd
+      fperm[(size_t)p * D + dd] = e;  // pi_p(dd) = e
     }
   }
   const int T_pad = (T + kTileRows - 1) / kTileRows * kTileRows;
@@ -963,12 +1149,14 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   m->use_E = d->alphas_E != nullptr;
   auto cleanup = [&]() { mbg_model_destroy(m); };
   if (cudaMalloc(&m->XA, xa.size() * sizeof(double2)) != cudaSuccess ||
-      cudaMalloc(&m->iperm, iperm.size() * sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&m->iperm, iperm.size() * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&m->perm, fperm.size() * sizeof(int)) != cudaSuccess) {
     cleanup();
     return fail(MBG_ERR_NOMEM, "cudaMalloc for model failed");
   }
   CUDA_TRY(cudaMemcpy(m->XA, xa.data(), xa.size() * sizeof(double2), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(m->iperm, iperm.data(), iperm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(m->perm, fperm.data(), fperm.size() * sizeof(int), cudaMemcpyHostToDevice));
   {
     // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row -|X'|^2/2 and -X'.A_s,
     // packed per tile of 64 rows; side arrays in column order (column j of a block <-> row tau(j)).
@@ -1052,6 +1240,7 @@ int mbg_model_destroy(mbg_model_t m) {
   if (m->mu) cudaFree(m->mu);
   if (m->alphaE) cudaFree(m->alphaE);
   if (m->iperm) cudaFree(m->iperm);
+  if (m->perm) cudaFree(m->perm);
   delete m;
   return MBG_OK;
 }
@@ -1095,6 +1284,11 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
   size_t ints_off = 0;
   ctx->n_deferred = 0;
   std::vector<std::pair<int, int>> deferred;  // (job, slot of its device-side counts)
+  const bool pw = uses_pw(ctx);
+  if (pw) {
+    if (n_jobs > kMaxJobsPerCall) return fail(MBG_ERR_UNSUPPORTED, "at most %d jobs per call", kMaxJobsPerCall);
+    if (n_jobs > 0) CUDA_TRY(cudaMemsetAsync(ctx->job_totals.p, 0, (size_t)n_jobs * 2 * sizeof(long long), ctx->stream));
+  }
   for (int k = 0; k < n_jobs && n_frames > 0; ++k) {
     JobDev j;
     size_t used = 0;
@@ -1115,11 +1309,23 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
     ints_off += (used + 15) / 16 * 16 + 16;  // keep slices 64-byte aligned
     mbg_job_stats st = {0, 0, 0};
     int slot = -1;
-    if (j.cand_per_frame > 0)
-      TRY(run_job(ctx, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, &st, &slot));
+    if (j.cand_per_frame > 0) {
+      if (pw) {
+        long long n_cand_shard = 0;
+        TRY(run_job_pw(ctx, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, k,
+                       &n_cand_shard));
+        st.n_candidates = n_cand_shard;
+      } else {
+        TRY(run_job(ctx, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, &st, &slot));
+      }
+    }
     if (stats) stats[k] = st;
     if (slot >= 0) deferred.push_back({k, slot});
   }
+  long long* h_job = ctx->h_chunk + 2 * (size_t)kMaxPwLaunches;
+  const bool want_job_totals = pw && stats && n_jobs > 0 && n_frames > 0;
+  if (want_job_totals)
+    CUDA_TRY(cudaMemcpyAsync(h_job, ctx->job_totals.p, (size_t)n_jobs * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   if (!deferred.empty())  // counts of the small jobs: one copy, resolved by the synchronisation below
     CUDA_TRY(cudaMemcpyAsync(ctx->h_totals + 2, ctx->deferred_totals.p, (size_t)ctx->n_deferred * 2 * sizeof(long long),
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -1129,9 +1335,11 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
     if (want_virial)
       CUDA_TRY(cudaMemcpyAsync(virial, out.V, (size_t)n_frames * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  } else if (!deferred.empty() && stats) {
+  } else if ((!deferred.empty() && stats) || want_job_totals) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // device outputs stay enqueued otherwise; the caller asked for counts
   }
+  if (want_job_totals)
+    for (int k = 0; k < n_jobs; ++k) stats[k].n_accepted = h_job[2 * k], stats[k].n_enumerated = h_job[2 * k + 1];
   if (stats)
     for (const auto& d : deferred) {
       stats[d.first].n_accepted = ctx->h_totals[2 + 2 * d.second];
@@ -1177,11 +1385,23 @@ int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc* sys, const doub
     k_fill<<<(unsigned)((n * row + 255) / 256), 256, 0, ctx->stream>>>(ctx->outF.as<double>(), n * row, nan);
     ctx->launches += 2;
     Outputs out = {ctx->outE.as<double>(), ctx->outF.as<double>(), nullptr};
-    TRY(run_job(ctx, s, j, m, dR, 1, 0, 1, false, true, out, &st));
+    if (uses_pw(ctx)) {
+      long long n_cand_shard = 0;
+      CUDA_TRY(cudaMemsetAsync(ctx->job_totals.p, 0, 2 * sizeof(long long), ctx->stream));
+      TRY(run_job_pw(ctx, s, j, m, dR, 1, 0, 1, false, true, out, 0, &n_cand_shard));
+      st.n_candidates = n_cand_shard;
+      CUDA_TRY(cudaMemcpyAsync(ctx->h_chunk + 2 * (size_t)kMaxPwLaunches, ctx->job_totals.p, 2 * sizeof(long long),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      TRY(run_job(ctx, s, j, m, dR, 1, 0, 1, false, true, out, &st));
+    }
     CUDA_TRY(cudaMemcpyAsync(E, out.E, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(F, out.F, (size_t)(n * row) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (n > 0 && uses_pw(ctx)) {
+    st.n_accepted = ctx->h_chunk[2 * (size_t)kMaxPwLaunches], st.n_enumerated = ctx->h_chunk[2 * (size_t)kMaxPwLaunches + 1];
+  }
   end_call_timing(ctx);
   if (stats) *stats = st;
   return MBG_OK;

@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(kCullThreads) k_cull(const __grid_constant__ C
 
 // Exclusive scan of per-block counts by one CTA (block counts are few: candidates/256).
 // out_offsets[i] = sum_{k<i} counts[k]; totals[0] = sum counts, totals[1] = sum counts2.
+// job_totals (optional): running (accepted, enumerated) sums of a job whose launches are chunked.
 __global__ void __launch_bounds__(1024) k_scan_blocks(const int* __restrict__ counts, const int* __restrict__ counts2,
                                                       int n, long long* __restrict__ offsets,
-                                                      long long* __restrict__ totals) {
+                                                      long long* __restrict__ totals, long long* job_totals = nullptr) {
   __shared__ long long warp_sums[32];
   __shared__ long long carry, carry2;
   if (threadIdx.x == 0) carry = 0, carry2 = 0;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const int* __restrict__ co
     for (int w = 0; w < 32; ++w) t2 += warp_sums[w];
     totals[0] = carry;
     totals[1] = t2;
+    if (job_totals) job_totals[0] += carry, job_totals[1] += t2;
   }
 }
 

@@ -48,8 +48,11 @@ __device__ __noinline__ void mic_general(const SysDev& s, const double v[3], dou
   vec_mat_rn(f, s.rcell, pos);
   double best = norm3_rn(pos[0], pos[1], pos[2]);
   out[0] = pos[0], out[1] = pos[1], out[2] = pos[2];
+#pragma unroll 1
   for (int h = -1; h <= 1; ++h)
+#pragma unroll 1
     for (int k = -1; k <= 1; ++k)
+#pragma unroll 1
       for (int l = -1; l <= 1; ++l) {
         const double hkl[3] = {(double)h, (double)k, (double)l};
         double sh[3], x[3];

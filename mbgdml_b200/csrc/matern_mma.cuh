@@ -71,7 +71,7 @@ __host__ __device__ constexpr int mma_row_pad(int na) {
 #ifdef MBG_MMA_TILE_ROWS
 __host__ __device__ constexpr int mma_tile_rows(int) { return MBG_MMA_TILE_ROWS; }
 #else
-__host__ __device__ constexpr int mma_tile_rows(int na) { return mma_row_pad(na) <= 108 ? 32 : 16; }
+__host__ __device__ constexpr int mma_tile_rows(int na) { return mma_row_pad(na) <= 100 ? 32 : 16; }
 #endif
 // doubles per packed tile: two planes, (xx5, xa) per row, alphas_E per row
 __host__ __device__ constexpr int mma_tile_doubles(int na) { return mma_tile_rows(na) * (2 * mma_row_pad(na) + 3); }

@@ -27,6 +27,12 @@
 namespace mbg {
 
 constexpr int kPwMaxSlices = 32;  // row slices a launch can be cut into (device counters per launch)
+#ifndef PW_STAGES
+#define PW_STAGES 3
+#endif
+constexpr int kPwStages = PW_STAGES;  // tile buffers of the cyclic stream: a warp may lead the slowest one by kPwStages - 1 tiles
+// Measured and rejected (profiles/r2_pw_tuning.md): 2^(k/4096) = T1[k >> 6 & 63] T2[k & 63] from two 64-entry tables
+// (frees 31 KB for another tile buffer) costs one more DMUL + LDS on the chain's critical path: +2.2 % kernel time.
 
 struct MaternPwArgs {
   SysDev sys;
@@ -34,7 +40,8 @@ struct MaternPwArgs {
   const double* tiles;       // packed model tiles (mbg_model_create, layout of matern_mma.cuh)
   const double* mu;          // [D]
   const double* exp2_table;  // [kMmaExpTable]
-  const int* iperm;          // [P][D]
+  const int* iperm;          // [P][D]: pi_p^-1
+  const int* perm;           // [P][D]: pi_p
   int P;
   int n_row_blocks;  // ceil(T / 8)
   int max_slices;    // upper bound of the device-side row-slice choice (power of two, <= kPwMaxSlices)
@@ -52,14 +59,20 @@ struct MaternPwArgs {
   double* F;
   double* virial;
   unsigned int* work_counters;  // [kPwMaxSlices], zero before the launch: dynamic work counter per row slice
+#ifdef PW_PROFILE
+  long long* prof;  // harness only: [gridDim.x][NW][8] clock64 totals per warp
+#endif
 };
 
-// rows of an m-tile staged per pass of the epilogue's un-permute (8, or fewer for wide descriptors)
-__host__ __device__ constexpr int pw_stage_rows(int na) { return na * (na - 1) / 2 + 1 <= 80 ? 8 : (na * (na - 1) / 2 + 1 <= 128 ? 4 : 2); }
+// rows of an m-tile staged per pass of the epilogue (8, or fewer for wide descriptors), and their stride:
+// the raw accumulator columns 0 .. 8 NT - 1 (column D = s1) plus the energy term
+__host__ __device__ constexpr int pw_stage_stride(int na) { return 8 * ((na * (na - 1) / 2 + 8) / 8) + 1; }
+__host__ __device__ constexpr int pw_stage_rows(int na) { return pw_stage_stride(na) <= 81 ? 8 : (pw_stage_stride(na) <= 113 ? 4 : 2); }
 
+// fragments an item (8 MT consecutive queries starting at a multiple of 8 MT) can touch
 template <int NA, int MT>
 __host__ __device__ constexpr int pw_max_frag(int P) {
-  return (8 * MT + P - 1) / P + 1;
+  return P % (8 * MT) == 0 ? 1 : ((8 * MT) % P == 0 ? (8 * MT) / P : (8 * MT + P - 1) / P + 1);
 }
 
 // doubles of one warp's private shared-memory region
@@ -67,16 +80,23 @@ template <int NA, int MT, bool YS>
 __host__ __device__ constexpr int pw_warp_doubles(int P) {
   constexpr int D = NA * (NA - 1) / 2, KS = (D + 3) / 4;
   const int maxf = pw_max_frag<NA, MT>(P);
-  const int stage = pw_stage_rows(NA) * (D + 1);
+  const int stage = pw_stage_rows(NA) * pw_stage_stride(NA);
   const int ys = YS ? MT * KS * 32 : 0;
   return maxf * D + maxf * NA * 3 + maxf * (D + 1) + ((maxf + 1) / 2) + (ys > stage ? ys : stage);
 }
 
+// NW = the launch bound (warps the kernel is compiled for), nw = warps actually launched (fewer when the per-warp
+// regions of a model with few permutations -- many fragments per item -- would not fit shared memory)
+constexpr int kPwPermSmemMax = 8 * 1024;  // both permutation tables (one byte per entry) are kept in shared memory up to this size
+__host__ __device__ constexpr int pw_perm_doubles(int na, int P) {  // doubles taken by the cached pi / pi^-1 tables
+  return (na * (na - 1) / 2 <= 255 && 2 * P * (na * (na - 1) / 2) <= kPwPermSmemMax) ? (2 * P * (na * (na - 1) / 2) + 7) / 8 : 0;
+}
 template <int NA, int MT, int NW, bool YS>
-__host__ __device__ constexpr size_t pw_smem_bytes(int P) {
+__host__ __device__ constexpr size_t pw_smem_bytes(int P, int nw) {
   constexpr int D = NA * (NA - 1) / 2;
-  return (size_t)kMmaStages * mma_tile_doubles(NA) * 8 + (size_t)kMmaExpTable * 8 + (kMmaStages + 1) * 8 +
-         (size_t)(NW + 4) * 4 + 8 + (size_t)(D + 1) * 8 + (size_t)NW * pw_warp_doubles<NA, MT, YS>(P) * 8 + 64;
+  return (size_t)kPwStages * mma_tile_doubles(NA) * 8 + (size_t)kMmaExpTable * 8 + (kPwStages + 1) * 8 +
+         (size_t)(NW + 4) * 4 + 8 + (size_t)(D + 1) * 8 + (size_t)pw_perm_doubles(NA, P) * 8 +
+         (size_t)nw * pw_warp_doubles<NA, MT, YS>(P) * 8 + 64;
 }
 
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -86,13 +106,13 @@ template <int NA, int MT, int NW, bool USE_E, bool YS>
 __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant__ MaternPwArgs a) {
   using S = MmaShape<NA>;
   constexpr int D = S::D, KS = S::KS, NT = S::NT, Dp = S::Dp;
-  constexpr int TR = mma_tile_rows(NA), ST = kMmaStages, BPT = TR / 8;
+  constexpr int TR = mma_tile_rows(NA), ST = kPwStages, BPT = TR / 8;
   constexpr int TILE = mma_tile_doubles(NA);
   constexpr int QW = 8 * MT;  // queries per work item
   constexpr int RP = pw_stage_rows(NA);
   constexpr uint32_t kTileBytes = TILE * 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nw = blockDim.x >> 5;
   const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, l = lane & 3;
   const int P = a.P;
   const int maxf = pw_max_frag<NA, MT>(P);
@@ -104,7 +124,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   const int n_tiles_data = (a.n_row_blocks + BPT - 1) / BPT;  // tiles that hold training rows
   int n_sl = 1;
   {
-    const long long slots = (long long)gridDim.x * NW;
+    const long long slots = (long long)gridDim.x * nw;
     while (n_sl * 2 <= a.max_slices && n_groups * n_sl < slots) n_sl *= 2;
   }
   const int tps = (n_tiles_data + n_sl - 1) / n_sl;  // tiles per row slice
@@ -116,19 +136,29 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   const int nts = min(tps, n_tiles_data - tile0);                 // tiles of this slice (one lap of the stream)
   const int NBs = min(a.n_row_blocks - tile0 * BPT, nts * BPT);   // row blocks of this slice that hold data
   const double* __restrict__ gtiles = a.tiles + (size_t)tile0 * TILE;
-  // staggered start only pays when every warp runs several batches
-  const bool stagger = n_groups >= 4ll * n_cta_sl * NW;
+  // staggered start only pays when every warp runs many batches (it idles the late warps for up to a lap once:
+  // measured +0.7 % at 192 items per warp, neutral at 48)
+#ifndef PW_STAGGER
+#define PW_STAGGER 1
+#endif
+  const bool stagger = PW_STAGGER && n_groups >= 64ll * n_cta_sl * nw;
 
   // ---- shared memory ------------------------------------------------------------------------------------------
   double* tiles = reinterpret_cast<double*>(smem_raw);                  // [ST][TILE]
-  double* etab = tiles + (size_t)ST * TILE;                             // [4096]
+  double* etab = tiles + (size_t)ST * TILE;                             // [4096] 2^(j/4096)
   uint64_t* bars = reinterpret_cast<uint64_t*>(etab + kMmaExpTable);    // full[ST], table
   int* ctl = reinterpret_cast<int*>(bars + ST + 1);                     // next_issue, n_retired, pad, pad, progress[NW]
   int* next_issue = ctl;
   int* n_retired = ctl + 1;
   int* progress = ctl + 4;
   double* mus = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(progress + NW + 1) + 7 & ~(uintptr_t)7);  // [D + 1]
-  double* wbase = mus + D + 1 + ((D + 1) & 1);
+  unsigned char* perm_s = reinterpret_cast<unsigned char*>(mus + D + 1 + ((D + 1) & 1));  // pi [P][D], pi^-1 [P][D] (bytes)
+  const int perm_dbl = pw_perm_doubles(NA, P);
+  double* wbase = reinterpret_cast<double*>(perm_s) + perm_dbl;
+  // permutation tables: shared-memory copies when they fit (the prologue / epilogue of every item walk them with
+  // dependent loads; from global memory that latency is what a warp's fixed cost per item mostly consists of)
+  auto fperm_at = [&](const int idx) -> int { return perm_dbl ? (int)perm_s[idx] : a.perm[idx]; };
+  auto iperm_at = [&](const int idx) -> int { return perm_dbl ? (int)perm_s[P * D + idx] : a.iperm[idx]; };
   double* xs = wbase + (size_t)warp * pw_warp_doubles<NA, MT, YS>(P);   // [maxf][D]
   double* rs = xs + (size_t)maxf * D;                                   // [maxf][NA][3]
   double* Fd = rs + (size_t)maxf * NA * 3;                              // [maxf][D + 1]: F_d and E_raw per fragment
@@ -140,10 +170,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
     for (int s = 0; s < ST; ++s) mbar_init(&bars[s], 1);
     mbar_init(&bars[ST], 1);
     *next_issue = 0, *n_retired = 0;
-    for (int w = 0; w < NW; ++w) progress[w] = 0;
+    for (int w = 0; w < NW; ++w) progress[w] = 0x7fffffff * (w >= nw);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int k = tid; k < D; k += NW * 32) mus[k] = a.mu[k];
+  for (int k = tid; k < D; k += nw * 32) mus[k] = a.mu[k];
+  if (perm_dbl)
+    for (int k = tid; k < P * D; k += nw * 32) perm_s[k] = (unsigned char)a.perm[k], perm_s[P * D + k] = (unsigned char)a.iperm[k];
   __syncthreads();  // the only CTA-wide barrier of the kernel
   if (tid == 0) {
     mbar_expect_tx(&bars[ST], kMmaExpTable * 8);
@@ -157,8 +189,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
     for (;;) {
       const int ni = ld_volatile_s32(next_issue);
       const bool must = ni <= k_need;
+#ifdef PW_EXP_NO_OPP  // harness only: no opportunistic issue, a tile is fetched by the first warp that needs it
+      if (!must) break;
+#endif
       if (ni >= ST) {
-        int pr = lane < NW ? ld_volatile_s32(progress + lane) : 0x7fffffff;
+        int pr = lane < nw ? ld_volatile_s32(progress + lane) : 0x7fffffff;
         pr = __reduce_min_sync(0xffffffffu, pr);
         if (pr < ni - ST + 1) {  // someone still reads the tile in that stage
           if (!must) break;
@@ -179,9 +214,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       (void)__shfl_sync(0xffffffffu, won, 0);
     }
   };
+#ifdef PW_PROFILE
+  long long pf_epi1 = 0, pf_acq = 0, pf_pro = 0, pf_epi = 0, pf_loop = 0, pf_items = 0, pf_t0 = clock64(), pf_mark = 0;
+#define PF_BEGIN() pf_mark = clock64()
+#define PF_END(x) x += clock64() - pf_mark
+#else
+#define PF_BEGIN()
+#define PF_END(x)
+#endif
   auto acquire = [&](const int k) {  // tile k is in shared memory when this returns
+#ifdef PW_PROFILE
+    const long long t_a = clock64();
+#endif
     produce(k);
     mbar_wait(&bars[k % ST], (k / ST) & 1);
+#ifdef PW_PROFILE
+    pf_acq += clock64() - t_a;
+#endif
   };
   auto release = [&](const int k) {  // this warp will not read tile k again
     __syncwarp();
@@ -193,7 +242,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
 
   int kt = 0;  // sequence number of the next tile this warp consumes (tile index = tile0 + kt mod nts)
   if (stagger) {
-    const int skip = (int)((long long)warp * nts / NW);
+    const int skip = (int)((long long)warp * nts / nw);
     for (; kt < skip; ++kt) {
       acquire(kt);
       release(kt);
@@ -213,21 +262,26 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   bool table_ready = false;
 
   long long grp = (long long)warp * n_cta_sl + rank;  // static first item
-  const unsigned dyn0 = (unsigned)n_cta_sl * NW;
+  const unsigned dyn0 = (unsigned)n_cta_sl * nw;
 
   while (grp < n_groups) {
     // prefetch the id of the next item (dynamic part of the schedule)
     unsigned nxt_dyn = 0;
     if (lane == 0) nxt_dyn = atomicAdd(a.work_counters + slice, 1u);
 
+    PF_BEGIN();
     // ---- prologue: geometry + descriptors of this item's fragments, query operands ----------------------------
+    // (written for small code, not speed: while one warp is here the other warps of its scheduler run the main
+    // loop, and what they need most from this warp is that it leaves their instruction cache alone)
     const long long q0 = grp * QW;
-    const long long q_end = (q0 + QW < nq) ? q0 + QW : nq;
-    const long long f_lo = q0 / P;
-    const int nf = (int)((q_end - 1) / P - f_lo) + 1;
+    const int n_act = (int)min((long long)QW, nq - q0);  // queries of this item
+    const long long f_lo = q0 / P;                        // its first fragment ...
+    const int p0 = (int)(q0 - f_lo * P);                  // ... and the permutation its first query applies
+    const int nf = (p0 + n_act - 1) / P + 1;
     for (int fl = lane; fl < nf; fl += 32) bad[fl] = 0;
     for (int idx = lane; idx < nf * (D + 1); idx += 32) Fd[idx] = 0.0;
     __syncwarp();
+#pragma unroll 1
     for (int idx = lane; idx < nf * NA; idx += 32) {
       const int fl = idx / NA, k = idx - fl * NA;
       const long long frag = f_lo + fl;
@@ -235,32 +289,34 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
       double v[3] = {p[0], p[1], p[2]};
       if (a.sys.periodic) {
-        const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
-        const double d[3] = {__dsub_rn(v[0], p0[0]), __dsub_rn(v[1], p0[1]), __dsub_rn(v[2], p0[2])};
+        const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
+        const double d[3] = {__dsub_rn(v[0], pf[0]), __dsub_rn(v[1], pf[1]), __dsub_rn(v[2], pf[2])};
         if (!(mic_naive(a.sys, d, v) < a.sys.half_min_len)) bad[fl] = 1;
       }
       rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
     }
     __syncwarp();
     if (a.sys.periodic) {  // find_mic falls back to the general algorithm for the whole fragment
+#pragma unroll 1
       for (int idx = lane; idx < nf * NA; idx += 32) {
         const int fl = idx / NA, k = idx - fl * NA;
         if (!bad[fl]) continue;
         const long long frag = f_lo + fl;
         const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
         const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
-        const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
-        const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
+        const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
+        const double d[3] = {__dsub_rn(p[0], pf[0]), __dsub_rn(p[1], pf[1]), __dsub_rn(p[2], pf[2])};
         double v[3];
         mic_general(a.sys, d, v);
         rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
       }
       __syncwarp();
     }
+#pragma unroll 1
     for (int idx = lane; idx < nf * D; idx += 32) {  // x_k = 1 / |r_i - r_j|, np.tril_indices(n, -1) order
       const int fl = idx / D, k = idx - fl * D;
       int i = 1;
-#pragma unroll
+#pragma unroll 1
       for (int ii = 1; ii < NA; ++ii)
         if (k >= ii * (ii + 1) / 2) i = ii + 1;
       const int j = k - i * (i - 1) / 2;
@@ -271,26 +327,29 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
     __syncwarp();
 
     double Y[YS ? 1 : MT][YS ? 1 : KS], yy5[MT];
-    auto query_info = [&](const long long q0_, const int i, bool& act, int& flq, const int*& ipp) {
-      const long long q = q0_ + 8 * i + g;
-      act = q < nq;
-      flq = act ? (int)(q / P - q0_ / P) : 0;
-      ipp = a.iperm + (act ? (int)(q % P) : 0) * D;
-    };
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      bool act;
-      int flq;
-      const int* ipp;
-      query_info(q0, i, act, flq, ipp);
+      const int u = 8 * i + g;  // this thread's query row of m-tile i
+      const bool act = u < n_act;
+      const int flq = act ? (p0 + u) / P : 0;
+      const int ipp = (act ? p0 + u - flq * P : 0) * D;  // row of pi^-1 of this query
       double part = 0.0;
+      if (YS) {
+#pragma unroll 3
+        for (int k = 0; k < KS; ++k) {
+          const int e = 4 * k + l;
+          const double v = (e < D && act) ? xs[flq * D + iperm_at(ipp + e)] - mus[e] : 0.0;
+          ysw[(i * KS + k) * 32 + lane] = v;
+          part = fma(v, v, part);
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const int e = 4 * k + l;
-        const double v = (e < D && act) ? xs[flq * D + ipp[e]] - mus[e] : 0.0;
-        if (YS) ysw[(i * KS + k) * 32 + lane] = v;
-        else Y[YS ? 0 : i][YS ? 0 : k] = v;
-        part = fma(v, v, part);
+        for (int k = 0; k < KS; ++k) {
+          const int e = 4 * k + l;
+          const double v = (e < D && act) ? xs[flq * D + iperm_at(ipp + e)] - mus[e] : 0.0;
+          Y[YS ? 0 : i][YS ? 0 : k] = v;
+          part = fma(v, v, part);
+        }
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -309,6 +368,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       mbar_wait(&bars[ST], 0);
       table_ready = true;
     }
+    PF_END(pf_pro);
+    PF_BEGIN();
 
     // ---- main loop: one lap over the row blocks of this slice, starting at the current tile ------------------
     double yb[2][MT];
@@ -485,23 +546,34 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       tb = tbn, b = bn;
     }
 
+    PF_END(pf_loop);
+    PF_BEGIN();
+#ifdef PW_EXP_SLEEP_NS  // harness only: a pure absence of this warp between two items (does it overlap?)
+    {
+      const long long t_s = clock64();
+      while (clock64() - t_s < (long long)PW_EXP_SLEEP_NS * 2) __nanosleep(1000);
+    }
+#endif
     // ---- epilogue: G = base (s1 y' - Gacc), un-permute, reduce over this item's queries, project, scatter ----
+#ifdef PW_EXP_SKIP_EPILOGUE  // harness only: wrong results, measures the cost of the epilogue
+    if (G[0][0][0] != 123.456) {
+      grp = (long long)dyn0 + __shfl_sync(0xffffffffu, nxt_dyn, 0);
+      continue;
+    }
+#endif
     const double base = 5.0 / (3.0 * sig * sig * sig);
     long long grp_e;  // == grp, hidden from the optimiser so that the item bookkeeping is re-derived here
     asm volatile("mov.b64 %0, %1;" : "=l"(grp_e) : "l"(grp));
     const long long q0e = grp_e * QW;
-    const long long q_ende = (q0e + QW < nq) ? q0e + QW : nq;
+    const int n_acte = (int)min((long long)QW, nq - q0e);
     const long long f_loe = q0e / P;
-    const int nfe = (int)((q_ende - 1) / P - f_loe) + 1;
-    double* stg = ysw;  // [RP][D + 1]
+    const int p0e = (int)(q0e - f_loe * P);
+    const int nfe = (p0e + n_acte - 1) / P + 1;
+    constexpr int RS = pw_stage_stride(NA);  // raw accumulator columns (s1 in column D) + the energy term
+    double* stg = ysw;                       // [RP][RS]
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      bool act;
-      int flq;
-      const int* ipp;
-      query_info(q0e, i, act, flq, ipp);
       double eq = Eacc[i], e2q = E2[i];
-      const double s1q = __shfl_sync(0xffffffffu, G[i][D / 8][(D % 8) & 1], (lane & ~3) | ((D % 8) >> 1));
       eq += __shfl_xor_sync(0xffffffffu, eq, 1);
       eq += __shfl_xor_sync(0xffffffffu, eq, 2);
       if (USE_E) {
@@ -512,52 +584,61 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       for (int pass = 0; pass < 8 / RP; ++pass) {
         __syncwarp();  // the staging rows (and, first time, the query operands) are no longer read
         if (g / RP == pass) {
-          double* row = stg + (g % RP) * (D + 1);
+          double* row = stg + (g % RP) * RS + 2 * l;
 #pragma unroll
-          for (int n = 0; n < NT; ++n)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int e = 8 * n + 2 * l + cc;
-              if (e < D) {
-                const int d = ipp[e];
-                const double yv = xs[flq * D + d] - mus[e];
-                row[d] = act ? base * fma(s1q, yv, -G[i][n][cc]) : 0.0;
-              }
-            }
-          if (l == 0) row[D] = act ? fma(base, eq, e2q) : 0.0;
+          for (int n = 0; n < NT; ++n) row[8 * n] = G[i][n][0], row[8 * n + 1] = G[i][n][1];
+          if (l == 0) row[8 * NT] = fma(base, eq, e2q);
         }
         __syncwarp();
-        // rows of this pass: queries q0e + 8 i + pass RP + [0, RP); those of fragment fl are contiguous
-        const long long qa = q0e + 8 * i + pass * RP;
+        // Rows of this pass are the queries u0 .. u0 + RP - 1 of the item; those of fragment fl are contiguous.
+        // F_d[d] += base sum_rows (s1 y'[e] - Gacc[e]), e = pi_p(d)  (un-permute), E_raw += sum_rows E_row
+        const int u0 = 8 * i + pass * RP;
+#pragma unroll 1
         for (int idx = lane; idx < nfe * (D + 1); idx += 32) {
           const int fl = idx / (D + 1), d = idx - fl * (D + 1);
-          const long long fq0 = (f_loe + fl) * P, fq1 = fq0 + P;
-          const int r_lo = (int)(max(fq0, qa) - qa);
-          const int r_hi = (int)(min(min(fq1, q_ende), qa + RP) - qa);
+          const int r_lo = max(fl * P - p0e, u0) - u0;
+          const int r_hi = min(min((fl + 1) * P - p0e, n_acte), u0 + RP) - u0;
+          if (r_hi <= r_lo) continue;
           double sum = 0.0;
-          for (int r = r_lo; r < r_hi; ++r) sum += stg[r * (D + 1) + d];
-          if (r_hi > r_lo) Fd[idx] += sum;
+          if (d < D) {
+            const double xd = xs[fl * D + d];
+            int pr = (p0e + u0 + r_lo - fl * P) * D + d;
+#pragma unroll 4
+            for (int r = r_lo; r < r_hi; ++r, pr += D) {
+              const int e = fperm_at(pr);
+              sum += fma(stg[r * RS + D], xd - mus[e], -stg[r * RS + e]);
+            }
+            sum *= base;
+          } else {
+#pragma unroll 1
+            for (int r = r_lo; r < r_hi; ++r) sum += stg[r * RS + 8 * NT];
+          }
+          Fd[idx] += sum;
         }
       }
     }
     __syncwarp();
+#ifdef PW_PROFILE
+    pf_epi1 += clock64() - pf_mark;
+#endif
+#pragma unroll 1
     for (int idx = lane; idx < nfe * (NA * 3 + 1); idx += 32) {
       const int fl = idx / (NA * 3 + 1), rem = idx - fl * (NA * 3 + 1);
       const long long frag = f_loe + fl;
-      const long long fq0 = frag * P;
       const double lam = a.rec_lambda[frag];
       const double* Fdf = Fd + fl * (D + 1);
       const double* rf = rs + fl * NA * 3;
       const double* xf = xs + fl * D;
       if (rem == NA * 3) {
-        const double e = (Fdf[D] * a.std + ((fq0 >= q0e && slice == 0) ? a.c : 0.0)) * lam;
+        // the integration constant is added once per fragment: by the item that holds its first query, slice 0
+        const double e = (Fdf[D] * a.std + ((fl * P >= p0e && slice == 0) ? a.c : 0.0)) * lam;
         double* dst = a.decomp ? a.E + ((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag])
                                : a.E + a.rec_frame[frag];
         atomicAdd(dst, e);
       } else {
         const int m = rem / 3, c = rem - m * 3;
         double f = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int bb = 0; bb < NA; ++bb) {
           if (bb == m) continue;
           const int i = bb > m ? bb : m, j = bb > m ? m : bb;
@@ -580,8 +661,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
         const double* rf = rs + fl * NA * 3;
         const double* xf = xs + fl * D;
         double wv = 0.0;
+#pragma unroll 1
         for (int m = 0; m < NA; ++m) {
           double f = 0.0;
+#pragma unroll 1
           for (int bb = 0; bb < NA; ++bb) {
             if (bb == m) continue;
             const int i = bb > m ? bb : m, j = bb > m ? m : bb;
@@ -595,7 +678,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
     }
     __syncwarp();
     grp = (long long)dyn0 + __shfl_sync(0xffffffffu, nxt_dyn, 0);
+    PF_END(pf_epi);
+#ifdef PW_PROFILE
+    pf_items++;
+#endif
   }
+#ifdef PW_PROFILE
+  if (lane == 0) {
+    long long* o = a.prof + ((long long)blockIdx.x * NW + warp) * 8;
+    o[0] = clock64() - pf_t0, o[1] = pf_pro, o[2] = pf_loop, o[3] = pf_epi, o[4] = pf_acq, o[5] = pf_items, o[6] = pf_epi1;
+  }
+#endif
 
   // ---- retire: stop holding stages; the last warp out waits for the copies still in flight ---------------------
   __syncwarp();
@@ -603,7 +696,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   if (lane == 0) {
     st_volatile_s32(progress + warp, 0x7fffffff);
     __threadfence_block();
-    last_out = atomicAdd(n_retired, 1) == NW - 1;
+    last_out = atomicAdd(n_retired, 1) == nw - 1;
   }
   last_out = __shfl_sync(0xffffffffu, last_out, 0);
   if (last_out) {

@@ -83,16 +83,17 @@ class mbeCalculator(Calculator):  # pylint: disable=invalid-name
             self.results["stress"] = stress[0][0] * self.e_conv
 
     def todict(self, skip_default=True):
-        defaults = self.get_default_parameters()
-        dct = {}
+        """Serialisable copy of ``parameters`` for ASE's trajectory writers (interfaces/ase.py:110-128): entries that
+        repeat a class default are dropped, nested objects are flattened through their own ``todict`` and string
+        arrays become lists (ASE cannot reload NumPy string arrays)."""
+        defaults = self.get_default_parameters() if hasattr(self, "get_default_parameters") else {}
+        out = {}
         for key, value in self.parameters.items():
+            if skip_default and key in defaults:
+                continue
             if hasattr(value, "todict"):
                 value = value.todict()
-            if skip_default:
-                default = defaults.get(key, "_no_default_")
-                if default != "_no_default_":
-                    continue
-            if isinstance(value, np.ndarray) and value.dtype.kind in {"U", "S"}:
-                value = value.tolist()  # ASE cannot reload string arrays
-            dct[key] = value
-        return dct
+            elif isinstance(value, np.ndarray) and value.dtype.kind in "US":
+                value = value.tolist()
+            out[key] = value
+        return out

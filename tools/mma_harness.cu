@@ -12,6 +12,7 @@
 #include "../mbgdml_b200/csrc/common.cuh"
 #include "../mbgdml_b200/csrc/geom.cuh"
 #include "../mbgdml_b200/csrc/matern_mma.cuh"
+#include "../mbgdml_b200/csrc/matern_pw.cuh"
 
 using namespace mbg;
 
@@ -55,6 +56,88 @@ static int run(const char* name, MaternMmaArgs a, int reps) {
   const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * 36 + 10);
   printf("%-28s grid %6u  smem %6zu  %8.3f ms  %6.2f TFLOP/s (algorithmic, T=1000 formula scaled by rows %d)\n", name, grid,
          smem, best, flop * (a.n_row_blocks * 8 / 1000.0) / best / 1e9, a.n_row_blocks * 8);
+  return 0;
+}
+
+// persistent per-warp kernel (matern_pw.cuh): one CTA per SM, work counters zeroed before every launch
+template <int MT, int NW, bool YS>
+static int run_pw(const char* name, const MaternMmaArgs& m, int reps, int sm_count, int nw_launch = NW) {
+  constexpr int NA = 9;
+  MaternPwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.sys = m.sys, a.R = m.R, a.tiles = m.tiles, a.mu = m.mu, a.exp2_table = m.exp2_table, a.iperm = m.iperm;
+  {  // forward permutations from the inverse table
+    std::vector<int> ip((size_t)m.P * 36), fp((size_t)m.P * 36);
+    CK(cudaMemcpy(ip.data(), m.iperm, ip.size() * 4, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < m.P; ++p)
+      for (int e = 0; e < 36; ++e) fp[p * 36 + ip[p * 36 + e]] = e;
+    int* dfp;
+    CK(cudaMalloc(&dfp, fp.size() * 4));
+    CK(cudaMemcpy(dfp, fp.data(), fp.size() * 4, cudaMemcpyHostToDevice));
+    a.perm = dfp;
+  }
+  a.P = m.P, a.n_row_blocks = m.n_row_blocks, a.max_slices = 1;
+#ifdef EXP_SLICES
+  a.max_slices = EXP_SLICES;
+#endif
+  a.sig = m.sig, a.c = m.c, a.std = m.std, a.n_frag = m.n_frag, a.n_frag_dev = nullptr;
+  a.rec_frame = m.rec_frame, a.rec_atoms = m.rec_atoms, a.rec_lambda = m.rec_lambda, a.rec_slot = m.rec_slot;
+  a.n_slots_per_frame = m.n_slots_per_frame, a.decomp = 0, a.want_virial = 0;
+  a.E = m.E, a.F = m.F, a.virial = nullptr;
+  unsigned int* ctr;
+  CK(cudaMalloc(&ctr, kPwMaxSlices * 4));
+  a.work_counters = ctr;
+#ifdef PW_PROFILE
+  long long* dprof;
+  CK(cudaMalloc(&dprof, (size_t)sm_count * NW * 8 * 8));
+  CK(cudaMemset(dprof, 0, (size_t)sm_count * NW * 8 * 8));
+  a.prof = dprof;
+#endif
+  auto kern = k_matern_pw<NA, MT, NW, false, YS>;
+  const size_t smem = pw_smem_bytes<NA, MT, NW, YS>(a.P, nw_launch);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  CK(cudaMemset(m.E, 0, 8));
+  CK(cudaMemset(ctr, 0, kPwMaxSlices * 4));
+  kern<<<sm_count, nw_launch * 32, smem>>>(a);
+  CK(cudaDeviceSynchronize());
+  double E;
+  CK(cudaMemcpy(&E, m.E, 8, cudaMemcpyDeviceToHost));
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaMemset(ctr, 0, kPwMaxSlices * 4));
+    cudaEventRecord(e0);
+    kern<<<sm_count, nw_launch * 32, smem>>>(a);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * 36 + 10);
+  printf("%-28s grid %6d  smem %6zu  %8.3f ms  %6.2f TFLOP/s   E(one launch) = %.9e\n", name, sm_count, smem, best,
+         flop * (a.n_row_blocks * 8 / 1000.0) / best / 1e9, E);
+#ifdef PW_PROFILE
+  {
+    std::vector<long long> hp((size_t)sm_count * NW * 8);
+    CK(cudaMemcpy(hp.data(), dprof, hp.size() * 8, cudaMemcpyDeviceToHost));
+    double tot = 0, pro = 0, loop = 0, epi = 0, acq = 0, items = 0, epi1 = 0;
+    int n = 0;
+    for (int c = 0; c < sm_count; ++c)
+      for (int w = 0; w < nw_launch; ++w) {
+        const long long* o = hp.data() + ((size_t)c * NW + w) * 8;
+        tot += o[0], pro += o[1], loop += o[2], epi += o[3], acq += o[4], items += o[5], epi1 += o[6], ++n;
+      }
+    printf("   per warp (cycles, mean over %d warps): total %.0f  prologue %.0f  loop %.0f  epilogue %.0f  [acquire waits inside: %.0f]  items %.1f\n",
+           n, tot / n, pro / n, loop / n, epi / n, acq / n, items / n);
+    printf("   per item: prologue %.0f  loop %.0f  epilogue %.0f (stage+reduce %.0f)  acquire wait %.0f cycles\n", pro / items, loop / items, epi / items, epi1 / items, acq / items);
+    const long long* o = hp.data();
+    for (int w = 0; w < nw_launch; ++w)
+      printf("   CTA 0 warp %2d: total %lld pro %lld loop %lld epi %lld acq %lld items %lld\n", w, o[w * 8], o[w * 8 + 1], o[w * 8 + 2], o[w * 8 + 3], o[w * 8 + 4], o[w * 8 + 5]);
+  }
+#endif
+  cudaFree(ctr);
   return 0;
 }
 
@@ -137,8 +220,23 @@ int main(int argc, char** argv) {
   if (run<3, 192, true, 2>("MT=3 192 thr x 2 CTA/SM, y' smem", a, 5)) return 1;
 #else
   if (run<3, 256, false>("MT=3 256 thr", a, 5)) return 1;
+  CK(cudaMemset(dE, 0, 8));
+  if (run<3, 384, true>("MT=3 384 thr, y' in smem", a, 0)) return 1;
+  {
+    double E1;
+    CK(cudaMemcpy(&E1, dE, 8, cudaMemcpyDeviceToHost));
+    printf("wave kernel                  E(one launch) = %.9e\n", E1);
+  }
   if (run<3, 384, true>("MT=3 384 thr, y' in smem", a, 5)) return 1;
 #endif
+  int sm_count = 0;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
+  if (run_pw<3, 12, true>("persistent 12 warps, y' smem", a, 5, sm_count)) return 1;
+#ifdef EXP_16W
+  if (run_pw<2, 16, true>("persistent 16 warps MT=2 ys", a, 5, sm_count)) return 1;
+  if (run<2, 512, true>("wave MT=2 512 thr, y' smem", a, 5)) return 1;
+#endif
+  if (run_pw<3, 8, false>("persistent 8 warps", a, 5, sm_count)) return 1;
   double E;
   CK(cudaMemcpy(&E, dE, 8, cudaMemcpyDeviceToHost));
   printf("E (sum over all launches) = %.6e\n", E);
