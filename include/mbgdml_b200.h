@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MBG_ABI_VERSION 1
+#define MBG_ABI_VERSION 2
 
 #define MBG_OK 0
 #define MBG_ERR_ARG (-1)         /* invalid argument (the Python mirror raises ValueError/AssertionError) */
@@ -91,6 +91,10 @@ typedef struct mbg_system_desc {
   const double *masses;          /* [n_atoms] qcelemental.periodictable.to_mass(Z[i]) (descriptors.py:125) */
   const double *cell;            /* [9] row-major cell vectors (Cell.cell_v) or NULL for no periodicity    */
   double cell_cutoff;            /* Cell.cutoff (periodic.py:82); ignored when cell == NULL                */
+  /* One cell per frame (overrides cell / cell_cutoff when non-NULL): NPT trajectories, and the 18 strained boxes
+   * of the finite-difference virial (stress.py:75-152) evaluated as ONE 18-frame call.                     */
+  const double *frame_cells;     /* [n_frames][9] or NULL                                                  */
+  const double *frame_cutoffs;   /* [n_frames] Cell.cutoff of each frame's cell (required with frame_cells) */
 } mbg_system_desc;
 
 /* One model applied to the system: the fragments it predicts and its alchemical scalers. */
@@ -165,6 +169,22 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc *sys, const double *R, 
  * combs: E[n_combs], F[n_combs][model n_atoms][3]; rows of rejected fragments are NaN. */
 int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc *sys, const double *R,
                        const mbg_job *job, uint32_t flags, double *E, double *F, mbg_job_stats *stats);
+
+/* ---- prepared steps: the MD caller (mbeCalculator.calculate, interfaces/ase.py:65-108, one mbePredict.predict per
+ * integrator step) evaluates the SAME system, models and frame count over and over.  mbg_step_create uploads the
+ * tables once and records the whole evaluation -- H2D of the coordinates (and cells), enumeration, culling,
+ * contraction, scatter, D2H of the results -- into a CUDA graph; mbg_step_run replays it: one graph launch and one
+ * synchronisation per step.  Flags: MBG_FLAG_VIRIAL.  Needs MBG_CONTRACT_DMMA / AUTO (the persistent kernel reads the
+ * accepted-fragment counts on the device, so the launch sequence does not depend on them).
+ *   cells / cutoffs: NULL = the cell(s) the step was created with, else [n_cells][9] / [n_cells] with n_cells = 1
+ *   (sys->cell) or n_frames (sys->frame_cells) -- NPT steps and the strained boxes of virial_finite_diff
+ *   (stress.py:75-152) reuse one step. */
+typedef struct mbg_step_s *mbg_step_t;
+int mbg_step_create(mbg_context_t ctx, const mbg_system_desc *sys, int32_t n_frames, const mbg_job *jobs,
+                    int32_t n_jobs, uint32_t flags, mbg_step_t *step);
+int mbg_step_run(mbg_step_t step, const double *R, const double *cells, const double *cutoffs, double *E, double *F,
+                 double *virial, mbg_job_stats *stats);
+int mbg_step_destroy(mbg_step_t step);
 
 /* The accept decision predict_gdml takes for every candidate fragment before it evaluates the model
  * (gdml_predict.py:214-235: slice -> Cell.r_mic, periodic.py:61-107 -> Criteria.accept, descriptors.py:65-103),

@@ -33,7 +33,7 @@ class _ModelDesc(C.Structure):  # struct mbg_model_desc (include/mbgdml_b200.h),
 
 class _SystemDesc(C.Structure):  # struct mbg_system_desc
     _fields_ = [("n_atoms", C.c_int32), ("n_entities", C.c_int32), ("entity_offsets", _ip), ("entity_atoms", _ip),
-                ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double)]
+                ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double), ("frame_cells", _dp), ("frame_cutoffs", _dp)]
 
 
 class _Job(C.Structure):  # struct mbg_job
@@ -136,7 +136,8 @@ def _system(Z, entity_ids, periodic_cell, keep):
         cutoff = float(periodic_cell.cutoff)
     keep += [order, offs, masses, cell]
     return _SystemDesc(len(Z), len(offs) - 1, offs.ctypes.data_as(_ip), order.ctypes.data_as(_ip),
-                       masses.ctypes.data_as(_dp), cell.ctypes.data_as(_dp) if cell is not None else _dp(), cutoff)
+                       masses.ctypes.data_as(_dp), cell.ctypes.data_as(_dp) if cell is not None else _dp(), cutoff,
+                       _dp(), _dp())
 
 
 def _job(model, entity_combs, scalers, keep):

@@ -14,7 +14,7 @@ from .utils import CombGenerator
 class System:
     """mbg_system_desc plus the arrays that back its pointers."""
 
-    def __init__(self, Z, entity_ids, periodic_cell=None, need_masses=True):
+    def __init__(self, Z, entity_ids, periodic_cell=None, need_masses=True, frame_cells=None):
         Z = np.asarray(Z)
         entity_ids = np.asarray(entity_ids)
         if entity_ids.shape != Z.shape:
@@ -37,12 +37,19 @@ class System:
         cutoff = 0.0
         if periodic_cell is not None:
             self.cell, cutoff = periodic_cell.native_cell()
+        self.frame_cells = self.frame_cutoffs = None
+        if frame_cells is not None:  # one cell per frame: (cells (n, 3, 3), cutoffs (n,))
+            self.frame_cells = _native.as_f64(frame_cells[0]).reshape(-1, 9)
+            self.frame_cutoffs = _native.as_f64(frame_cells[1]).reshape(-1)
+            if len(self.frame_cells) != len(self.frame_cutoffs):
+                raise ValueError("one cutoff per frame cell")
         self.desc = _native.SystemDesc(
             n_atoms=self.n_atoms, n_entities=self.n_entities,
             entity_offsets=_native.ptr(self.entity_offsets, _native._ip),
             entity_atoms=_native.ptr(self.entity_atoms, _native._ip),
             masses=_native.ptr(self.masses, _native._dp),
             cell=_native.ptr(self.cell, _native._dp), cell_cutoff=cutoff,
+            frame_cells=_native.ptr(self.frame_cells, _native._dp), frame_cutoffs=_native.ptr(self.frame_cutoffs, _native._dp),
         )
 
 
@@ -117,8 +124,60 @@ def make_job(ctx, model, entity_combs, alchemy_scalers, keep):
     return job
 
 
+def step_key(Z, entity_ids, comp_ids, models, scalers_per_model, n_frames, periodic_cell, frame_cells, compute_virial):
+    """What a prepared step fixes: system, models (+ criteria), scalers, frame count, periodicity -- not the cell values."""
+    cell_kind = "frames" if frame_cells is not None else ("cell" if periodic_cell is not None else None)
+    return (np.asarray(Z).tobytes(), np.asarray(entity_ids).tobytes(), tuple(np.asarray(comp_ids).tolist()),
+            tuple((m._uid, m._criteria_key()) for m in models),
+            tuple(tuple((s.entity_id, s.order, s.native_factor()) for s in (sc or [])) for sc in scalers_per_model),
+            int(n_frames), cell_kind, bool(compute_virial))
+
+
+class StepCache:
+    """Prepared steps of one predictor.  A step is built the second time a key is seen (a one-off evaluation does not pay
+    for the capture) and at most ``capacity`` of them are kept."""
+
+    def __init__(self, capacity=4):
+        self.capacity, self.seen, self.steps = capacity, {}, {}
+
+    def get(self, key, build):
+        step = self.steps.get(key)
+        if step is not None:
+            return step
+        self.seen[key] = self.seen.get(key, 0) + 1
+        if self.seen[key] < 2:
+            if len(self.seen) > 64:
+                self.seen.clear()
+            return None
+        step = build()
+        if len(self.steps) >= self.capacity:
+            self.steps.pop(next(iter(self.steps))).close()
+        self.steps[key] = step
+        return step
+
+    def clear(self):
+        for st in self.steps.values():
+            st.close()
+        self.steps.clear()
+        self.seen.clear()
+
+
+def make_step(ctx, Z, entity_ids, models, comb_sources, scalers_per_model, periodic_cell, n_frames, compute_virial=False,
+              frame_cells=None):
+    """mbg_step_create for (system, models, scalers, frame count): see include/mbgdml_b200.h."""
+    if frame_cells is not None:
+        system = System(Z, entity_ids, None, need_masses=_needs_masses(models), frame_cells=frame_cells)
+    else:
+        system = System(Z, entity_ids, periodic_cell, need_masses=_needs_masses(models))
+    keep = []
+    jobs = (_native.Job * len(models))()
+    for k, (m, src, sc) in enumerate(zip(models, comb_sources, scalers_per_model)):
+        jobs[k] = make_job(ctx, m, src, sc, keep)
+    return _native.Step(ctx, system.desc, int(n_frames), system.n_atoms, jobs, len(models), bool(compute_virial))
+
+
 def predict_total(ctx, Z, R, entity_ids, models, comb_sources, scalers_per_model, periodic_cell,
-                  compute_virial=False, shard=(0, 1), device_out=None):
+                  compute_virial=False, shard=(0, 1), device_out=None, frame_cells=None):
     """All frames x all jobs in one native call.  Returns (E, F, virial-or-None, stats).
 
     ``R`` is a host array, or a contiguous float64 torch CUDA tensor (n_frames, n_atoms, 3) that
@@ -134,7 +193,12 @@ def predict_total(ctx, Z, R, entity_ids, models, comb_sources, scalers_per_model
             R = R[None]
         n_frames, n_atoms = R.shape[0], R.shape[1]
         r_ptr = R.ctypes.data
-    system = cached_system(Z, entity_ids, periodic_cell, _needs_masses(models))
+    if frame_cells is not None:
+        system = System(Z, entity_ids, None, need_masses=_needs_masses(models), frame_cells=frame_cells)
+        if len(system.frame_cells) != n_frames:
+            raise ValueError("one cell per frame")
+    else:
+        system = cached_system(Z, entity_ids, periodic_cell, _needs_masses(models))
     if system.n_atoms != n_atoms:
         raise ValueError("R and Z disagree on the number of atoms")
     keep = []

@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = [
     "mbg_last_error", "mbg_abi_version", "mbg_device_count", "mbg_context_create", "mbg_context_destroy",
     "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
-    "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_accept_mask", "mbg_enumerate",
+    "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_step_create", "mbg_step_run",
+    "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
     "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
     "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
 ]
@@ -54,7 +55,7 @@ class ModelDesc(C.Structure):
 class SystemDesc(C.Structure):
     _fields_ = [
         ("n_atoms", C.c_int32), ("n_entities", C.c_int32), ("entity_offsets", _ip), ("entity_atoms", _ip),
-        ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double),
+        ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double), ("frame_cells", _dp), ("frame_cutoffs", _dp),
     ]
 
 
@@ -103,6 +104,11 @@ def load_library():
                                     C.POINTER(JobStats)]
         lib.mbg_predict_decomp.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.POINTER(Job), C.c_uint32,
                                            C.c_void_p, C.c_void_p, C.POINTER(JobStats)]
+        lib.mbg_step_create.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_int32, C.POINTER(Job), C.c_int32, C.c_uint32,
+                                        C.POINTER(C.c_void_p)]
+        lib.mbg_step_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(JobStats)]
+        lib.mbg_step_destroy.argtypes = [C.c_void_p]
         lib.mbg_accept_mask.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.c_int32, C.POINTER(Job), C.c_uint32,
                                         C.c_void_p, _lp]
         lib.mbg_enumerate.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, _lp]
@@ -337,6 +343,43 @@ class Context:
         check(self.lib.mbg_r_mic(self.handle, ptr(cell, _dp), float(cutoff), ptr(r, _dp), r.shape[0], ptr(out, _dp),
                                  C.byref(acc)))
         return out, bool(acc.value)
+
+
+class Step:
+    """A prepared evaluation (mbg_step_create): tables on the device, the whole pipeline in one CUDA graph."""
+
+    def __init__(self, ctx, system_desc, n_frames, n_atoms, jobs, n_jobs, want_virial):
+        self.ctx, self.n_frames, self.n_atoms, self.n_jobs, self.want_virial = ctx, n_frames, n_atoms, n_jobs, want_virial
+        h = C.c_void_p()
+        check(ctx.lib.mbg_step_create(ctx.handle, C.byref(system_desc), n_frames, jobs, n_jobs,
+                                      FLAG_VIRIAL if want_virial else 0, C.byref(h)))
+        self.handle = h
+
+    def run(self, R, cells=None, cutoffs=None):
+        R = as_f64(R)
+        assert R.shape == (self.n_frames, self.n_atoms, 3)
+        E = np.empty(self.n_frames)
+        F = np.empty((self.n_frames, self.n_atoms, 3))
+        V = np.empty((self.n_frames, 3, 3)) if self.want_virial else None
+        stats = (JobStats * self.n_jobs)()
+        cells = as_f64(cells) if cells is not None else None
+        cutoffs = as_f64(cutoffs) if cutoffs is not None else None
+        check(self.ctx.lib.mbg_step_run(
+            self.handle, R.ctypes.data, cells.ctypes.data if cells is not None else None,
+            cutoffs.ctypes.data if cutoffs is not None else None, E.ctypes.data, F.ctypes.data,
+            V.ctypes.data if V is not None else None, stats))
+        return E, F, V, [(s_.n_candidates, s_.n_enumerated, s_.n_accepted) for s_ in stats]
+
+    def close(self):
+        if getattr(self, "handle", None) and self.ctx.handle:
+            self.ctx.lib.mbg_step_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _contexts = {}

@@ -78,6 +78,36 @@ constexpr int kMaxJobsPerCall = 256;
 constexpr int kMaxDeferred = 64;            // small jobs per call whose counts are read back once, at the end
 constexpr long long kSmallJobCand = 65536;  // candidates (all frames) up to which a job is "small"
 
+// Device tables of one (system, jobs) description: entity CSR, masses, cells, per-job entity sets / tuples / binomials.
+struct Tables {
+  DevBuf sys_ints, sys_masses, cells, job_ints;
+  std::vector<DevBuf> job_binom;  // one per job (a captured step keeps all of them alive)
+  std::vector<CellDev> h_cells;
+  void release() {
+    for (DevBuf* b : {&sys_ints, &sys_masses, &cells, &job_ints}) b->release();
+    for (DevBuf& b : job_binom) b.release();
+    job_binom.clear();
+  }
+};
+
+// Scratch of the enumerate -> cull -> compact -> contract pipeline.  The context owns one set; a captured step
+// (mbg_step_create) owns its own, because the graph's kernel nodes keep the addresses.
+struct Scratch {
+  DevBuf flags, blk_acc, blk_enum, blk_off;
+  DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
+  // persistent-kernel path: per-launch device counters and counts (no host round trip inside a call)
+  DevBuf pw_counters;   // [kMaxPwLaunches][kPwMaxSlices] dynamic work counters, zeroed at the start of a call
+  DevBuf chunk_totals;  // [kMaxPwLaunches][2] (accepted, enumerated) of every cull chunk = n_frag_dev of its contraction
+  DevBuf job_totals;    // [kMaxJobsPerCall][2] running sums per job (stats)
+  int n_pw_launch = 0;
+  int init();
+  void release() {
+    for (DevBuf* b : {&flags, &blk_acc, &blk_enum, &blk_off, &rec_frame, &rec_atoms, &rec_lambda, &rec_slot, &pw_counters,
+                      &chunk_totals, &job_totals})
+      b->release();
+  }
+};
+
 struct mbg_context_s {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -87,17 +117,13 @@ struct mbg_context_s {
   int contraction = MBG_CONTRACT_AUTO;  // which contraction kernel mbg_predict uses
   int mma_cfg = 0;                      // developer builds: MT*1000 + threads of the trimer DMMA kernel
   // scratch
-  DevBuf sys_ints, sys_masses, R, outE, outF, outV;
-  DevBuf job_ints, job_binom, flags, blk_acc, blk_enum, blk_off, totals;
-  DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
+  Tables tab;
+  Scratch scr;
+  bool capturing = false;  // a step is being captured: no events, no launch records
+  DevBuf R, outE, outF, outV, totals;
   DevBuf km_in, km_ints, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
-  // persistent-kernel path: per-launch device counters and counts (no host round trip inside a call)
-  DevBuf pw_counters;   // [kMaxPwLaunches][kPwMaxSlices] dynamic work counters, zeroed at the start of a call
-  DevBuf chunk_totals;  // [kMaxPwLaunches][2] (accepted, enumerated) of every cull chunk = n_frag_dev of its contraction
-  DevBuf job_totals;    // [kMaxJobsPerCall][2] running sums per job (stats)
-  int n_pw_launch = 0;
   std::vector<int> rec_chunk_slot;  // launch record -> chunk slot (fragment count resolved lazily), -1: count is exact
   long long* h_chunk = nullptr;     // pinned [kMaxPwLaunches][2]
   long long* h_totals = nullptr;  // pinned [2 + 2 * kMaxDeferred]
@@ -128,6 +154,14 @@ struct mbg_model_s {
   int* perm = nullptr;   // [P][D] pi_p
   CritDev crit;
 };
+
+int Scratch::init() {
+  TRY(pw_counters.ensure((size_t)kMaxPwLaunches * kPwMaxSlices * sizeof(unsigned int)));
+  TRY(chunk_totals.ensure((size_t)kMaxPwLaunches * 2 * sizeof(long long)));
+  TRY(job_totals.ensure((size_t)kMaxJobsPerCall * 2 * sizeof(long long)));
+  CUDA_TRY(cudaMemset(pw_counters.p, 0, (size_t)kMaxPwLaunches * kPwMaxSlices * sizeof(unsigned int)));
+  return MBG_OK;
+}
 
 static inline int mbg_model_rows_padded(int n_row_blocks) { return (n_row_blocks * 8 + kTileRows - 1) / kTileRows * kTileRows; }
 
@@ -315,7 +349,7 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
 // Persistent per-warp form of the tensor-pipe contraction (matern_pw.cuh): always one CTA per SM; the kernel reads
 // the fragment count on the device, so the launch shape never depends on it.
 template <int NA, int MT, int NW, bool USE_E, bool YS>
-static int launch_matern_pw_t(mbg_context_t ctx, const MaternPwArgs& a_in, int chunk_slot) {
+static int launch_matern_pw_t(mbg_context_t ctx, Scratch& sc, const MaternPwArgs& a_in, int chunk_slot) {
   MaternPwArgs a = a_in;
   int dev_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
@@ -333,10 +367,16 @@ static int launch_matern_pw_t(mbg_context_t ctx, const MaternPwArgs& a_in, int c
   a.max_slices = 1;
   while (a.max_slices * 2 <= kPwMaxSlices && a.max_slices * 4 <= n_tiles_data) a.max_slices *= 2;  // >= 2 tiles per slice
   if (ctx->mma_cfg == 2) a.max_slices = 1;  // developer: never slice
-  a.work_counters = ctx->pw_counters.as<unsigned int>() + (size_t)(ctx->n_pw_launch % kMaxPwLaunches) * kPwMaxSlices;
-  if (ctx->n_pw_launch >= kMaxPwLaunches)  // slots wrap around: re-zero this one (stream-ordered after its last user)
+  a.work_counters = sc.pw_counters.as<unsigned int>() + (size_t)(sc.n_pw_launch % kMaxPwLaunches) * kPwMaxSlices;
+  if (sc.n_pw_launch >= kMaxPwLaunches)  // slots wrap around: re-zero this one (stream-ordered after its last user)
     CUDA_TRY(cudaMemsetAsync(a.work_counters, 0, kPwMaxSlices * sizeof(unsigned int), ctx->stream));
-  ctx->n_pw_launch++;
+  sc.n_pw_launch++;
+  if (ctx->capturing) {  // inside a captured step: no timing events, no records
+    kern<<<ctx->sm_count, nw * 32, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MBG_OK;
+  }
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
   kern<<<ctx->sm_count, nw * 32, smem, ctx->stream>>>(a);
@@ -350,16 +390,16 @@ static int launch_matern_pw_t(mbg_context_t ctx, const MaternPwArgs& a_in, int c
   return MBG_OK;
 }
 
-static int launch_matern_pw(mbg_context_t ctx, int na, bool use_E, const MaternPwArgs& a, int chunk_slot) {
+static int launch_matern_pw(mbg_context_t ctx, Scratch& sc, int na, bool use_E, const MaternPwArgs& a, int chunk_slot) {
   // Shapes as for the wave-launched kernel (profiles/r1_dmma_tuning.md): 9-atom fragments run 12 warps with the
   // GEMM-1 query operands in shared memory, everything else 8 warps with the operands in registers.
-  if (na == 9 && !use_E && ctx->mma_cfg != 1) return launch_matern_pw_t<9, 3, 12, false, true>(ctx, a, chunk_slot);
+  if (na == 9 && !use_E && ctx->mma_cfg != 1) return launch_matern_pw_t<9, 3, 12, false, true>(ctx, sc, a, chunk_slot);
   switch (na) {
 #define X(N)                                                                                        \
   case N: {                                                                                         \
     constexpr int MT = (N >= 13) ? 1 : (N >= 10) ? 2 : (N >= 8) ? 3 : 4;                            \
-    return use_E ? launch_matern_pw_t<N, MT, 8, true, false>(ctx, a, chunk_slot)                    \
-                 : launch_matern_pw_t<N, MT, 8, false, false>(ctx, a, chunk_slot);                  \
+    return use_E ? launch_matern_pw_t<N, MT, 8, true, false>(ctx, sc, a, chunk_slot)                    \
+                 : launch_matern_pw_t<N, MT, 8, false, false>(ctx, sc, a, chunk_slot);                  \
   }
     MBG_FOR_EACH_NA(X)
 #undef X
@@ -471,7 +511,7 @@ __global__ void k_criteria_eval(int kind, int n, const double* masses, const int
   out[s] = dsum;
 }
 
-__global__ void k_r_mic(SysDev s, const double* r, int n, double* out, int* accepted) {
+__global__ void k_r_mic(CellDev s, const double* r, int n, double* out, int* accepted) {
   if (threadIdx.x || blockIdx.x) return;
   bool naive_ok = true;
   for (int a = 0; a < n; ++a) {
@@ -499,12 +539,9 @@ __global__ void k_r_mic(SysDev s, const double* r, int n, double* out, int* acce
 // ------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------
-static int fill_cell(SysDev& s, const double* cell, double cutoff) {
-  s.periodic = cell != nullptr;
-  s.fast_reject = 0;
+static int fill_cell(CellDev& s, const double* cell, double cutoff) {
+  memset(&s, 0, sizeof(s));
   s.cutoff = cutoff;
-  s.half_min_len = 0;
-  if (!cell) return MBG_OK;
   memcpy(s.cell, cell, 9 * sizeof(double));
   if (!hostmath::inverse3(s.cell, s.cell_inv)) return fail(MBG_ERR_ARG, "cell is singular");
   double mn = std::numeric_limits<double>::infinity();
@@ -520,7 +557,23 @@ static int fill_cell(SysDev& s, const double* cell, double cutoff) {
   return MBG_OK;
 }
 
-static int upload_system(mbg_context_t ctx, const mbg_system_desc* sys, SysDev& s) {
+// Cell table of a call: one CellDev for all frames (sys->cell) or one per frame (sys->frame_cells).
+static int build_cells(const mbg_system_desc* sys, int n_frames, std::vector<CellDev>& cells, int* stride) {
+  cells.clear();
+  *stride = 0;
+  if (sys->frame_cells) {
+    if (!sys->frame_cutoffs) return fail(MBG_ERR_ARG, "frame_cells without frame_cutoffs");
+    cells.resize(std::max(n_frames, 0));
+    for (int f = 0; f < n_frames; ++f) TRY(fill_cell(cells[f], sys->frame_cells + 9 * (size_t)f, sys->frame_cutoffs[f]));
+    *stride = 1;
+  } else if (sys->cell) {
+    cells.resize(1);
+    TRY(fill_cell(cells[0], sys->cell, sys->cell_cutoff));
+  }
+  return MBG_OK;
+}
+
+static int upload_system(mbg_context_t ctx, Tables& tb, const mbg_system_desc* sys, int n_frames, SysDev& s) {
   if (!sys || sys->n_atoms <= 0 || sys->n_entities <= 0 || !sys->entity_offsets || !sys->entity_atoms)
     return fail(MBG_ERR_ARG, "invalid system description");
   if (sys->entity_offsets[0] != 0 || sys->entity_offsets[sys->n_entities] > sys->n_atoms)
@@ -532,11 +585,11 @@ static int upload_system(mbg_context_t ctx, const mbg_system_desc* sys, SysDev& 
     if (sys->entity_atoms[k] < 0 || sys->entity_atoms[k] >= sys->n_atoms)
       return fail(MBG_ERR_ARG, "entity_atoms[%d] out of range", k);
   const size_t n_int = (size_t)sys->n_entities + 1 + n_vals;
-  TRY(ctx->sys_ints.ensure(n_int * sizeof(int)));
-  TRY(ctx->sys_masses.ensure((size_t)sys->n_atoms * sizeof(double)));
-  CUDA_TRY(cudaMemcpyAsync(ctx->sys_ints.p, sys->entity_offsets, ((size_t)sys->n_entities + 1) * sizeof(int),
+  TRY(tb.sys_ints.ensure(n_int * sizeof(int)));
+  TRY(tb.sys_masses.ensure((size_t)sys->n_atoms * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(tb.sys_ints.p, sys->entity_offsets, ((size_t)sys->n_entities + 1) * sizeof(int),
                            cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(ctx->sys_ints.as<int>() + sys->n_entities + 1, sys->entity_atoms, (size_t)n_vals * sizeof(int),
+  CUDA_TRY(cudaMemcpyAsync(tb.sys_ints.as<int>() + sys->n_entities + 1, sys->entity_atoms, (size_t)n_vals * sizeof(int),
                            cudaMemcpyHostToDevice, ctx->stream));
   std::vector<double> ones;
   const double* masses = sys->masses;
@@ -544,20 +597,29 @@ static int upload_system(mbg_context_t ctx, const mbg_system_desc* sys, SysDev& 
     ones.assign(sys->n_atoms, 1.0);
     masses = ones.data();
   }
-  CUDA_TRY(cudaMemcpyAsync(ctx->sys_masses.p, masses, (size_t)sys->n_atoms * sizeof(double), cudaMemcpyHostToDevice,
+  CUDA_TRY(cudaMemcpyAsync(tb.sys_masses.p, masses, (size_t)sys->n_atoms * sizeof(double), cudaMemcpyHostToDevice,
                            ctx->stream));
   if (!sys->masses) CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `ones` goes out of scope
   s.n_atoms = sys->n_atoms;
   s.n_entities = sys->n_entities;
-  s.ent_off = ctx->sys_ints.as<int>();
-  s.ent_atoms = ctx->sys_ints.as<int>() + sys->n_entities + 1;
-  s.masses = ctx->sys_masses.as<double>();
-  return fill_cell(s, sys->cell, sys->cell_cutoff);
+  s.ent_off = tb.sys_ints.as<int>();
+  s.ent_atoms = tb.sys_ints.as<int>() + sys->n_entities + 1;
+  s.masses = tb.sys_masses.as<double>();
+  std::vector<CellDev>& cells = tb.h_cells;  // stays alive until the next call
+  TRY(build_cells(sys, n_frames, cells, &s.cell_stride));
+  s.periodic = cells.empty() ? 0 : 1;
+  s.cells = nullptr;
+  if (!cells.empty()) {
+    TRY(tb.cells.ensure(cells.size() * sizeof(CellDev)));
+    CUDA_TRY(cudaMemcpyAsync(tb.cells.p, cells.data(), cells.size() * sizeof(CellDev), cudaMemcpyHostToDevice, ctx->stream));
+    s.cells = tb.cells.as<CellDev>();
+  }
+  return MBG_OK;
 }
 
 // Validate a job against the system and build its device description.
-static int build_job(mbg_context_t ctx, const mbg_system_desc* sys, const mbg_job* job, size_t ints_offset,
-                     JobDev& j, size_t* ints_used) {
+static int build_job(mbg_context_t ctx, Tables& tb, const mbg_system_desc* sys, const mbg_job* job, size_t ints_offset,
+                     JobDev& j, size_t* ints_used, int job_index = 0) {
   if (!job || !job->model) return fail(MBG_ERR_ARG, "job without model");
   const mbg_model_t m = job->model;
   if (m->ctx != ctx) return fail(MBG_ERR_ARG, "model belongs to another context");
@@ -565,7 +627,7 @@ static int build_job(mbg_context_t ctx, const mbg_system_desc* sys, const mbg_jo
   j.order = m->order;
   j.n_frag_atoms = m->n_atoms;
   auto ent_size = [&](int e) { return sys->entity_offsets[e + 1] - sys->entity_offsets[e]; };
-  int* d_ints = ctx->job_ints.as<int>() + ints_offset;
+  int* d_ints = tb.job_ints.as<int>() + ints_offset;
   if (job->combs) {
     if (job->n_combs < 0) return fail(MBG_ERR_ARG, "n_combs < 0");
     j.explicit_combs = 1;
@@ -581,8 +643,8 @@ static int build_job(mbg_context_t ctx, const mbg_system_desc* sys, const mbg_jo
         return fail(MBG_ERR_ARG, "comb %lld has %d atoms but the model expects %d", c, na, m->n_atoms);
     }
     const size_t n = (size_t)job->n_combs * m->order;
-    TRY(ctx->job_ints.ensure((ints_offset + n + 16) * sizeof(int)));
-    d_ints = ctx->job_ints.as<int>() + ints_offset;
+    TRY(tb.job_ints.ensure((ints_offset + n + 16) * sizeof(int)));
+    d_ints = tb.job_ints.as<int>() + ints_offset;
     if (n) CUDA_TRY(cudaMemcpyAsync(d_ints, job->combs, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     j.combs = d_ints;
     *ints_used = n;
@@ -613,8 +675,8 @@ static int build_job(mbg_context_t ctx, const mbg_system_desc* sys, const mbg_jo
       return fail(MBG_ERR_ARG, "fragments have %d atoms but the model expects %d", na, m->n_atoms);
     j.cand_per_frame = prod;
     const size_t n = (size_t)job->set_offsets[m->order];
-    TRY(ctx->job_ints.ensure((ints_offset + n + 16) * sizeof(int)));
-    d_ints = ctx->job_ints.as<int>() + ints_offset;
+    TRY(tb.job_ints.ensure((ints_offset + n + 16) * sizeof(int)));
+    d_ints = tb.job_ints.as<int>() + ints_offset;
     if (n) CUDA_TRY(cudaMemcpyAsync(d_ints, job->set_entities, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     j.set_ent = d_ints;
     *ints_used = n;
@@ -643,11 +705,13 @@ static int build_job(mbg_context_t ctx, const mbg_system_desc* sys, const mbg_jo
         }
         const long long n_comb = binom[(size_t)n0 * w + m->order];
         if (n_comb < kSat) {
-          TRY(ctx->job_binom.ensure(tbl * sizeof(long long)));
-          CUDA_TRY(cudaMemcpyAsync(ctx->job_binom.p, binom.data(), tbl * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+          if ((int)tb.job_binom.size() <= job_index) tb.job_binom.resize(job_index + 1);
+          DevBuf& bb = tb.job_binom[job_index];
+          TRY(bb.ensure(tbl * sizeof(long long)));
+          CUDA_TRY(cudaMemcpyAsync(bb.p, binom.data(), tbl * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
           j.homogeneous = 1;
           j.n_set = n0;
-          j.binom = ctx->job_binom.as<long long>();
+          j.binom = bb.as<long long>();
           j.cand_per_frame = n_comb;
         }
       }
@@ -684,7 +748,7 @@ static long long shard_candidates(long long g0, long long blocks, int shard_rank
 // Records and flags are sized for the candidates of a chunk (an upper bound of what it accepts); every kernel
 // downstream of the scan reads the accepted count from the device.  The counts for `stats` stay on the device
 // (job_totals[job_slot]) until the caller asks for them.
-static int run_job_pw(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
+static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
                       int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
                       int job_slot, long long* n_cand_shard_out) {
   const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
@@ -697,44 +761,44 @@ static int run_job_pw(mbg_context_t ctx, const SysDev& s, const JobDev& j, const
   long long chunk = (long long)((1ull << 30) / (kCullThreads * rec_bytes));  // <= 1 GiB of records per chunk
   chunk = std::min(std::max(chunk, 1ll << 10), std::min(1ll << 18, my_granules));
   const size_t n_rec_max = (size_t)chunk * kCullThreads;
-  TRY(ctx->flags.ensure(n_rec_max));
-  TRY(ctx->blk_acc.ensure((size_t)chunk * sizeof(int)));
-  TRY(ctx->blk_enum.ensure((size_t)chunk * sizeof(int)));
-  TRY(ctx->blk_off.ensure((size_t)chunk * sizeof(long long)));
-  TRY(ctx->rec_frame.ensure(n_rec_max * sizeof(int)));
-  TRY(ctx->rec_atoms.ensure(n_rec_max * NA * sizeof(int)));
-  TRY(ctx->rec_lambda.ensure(n_rec_max * sizeof(double)));
-  TRY(ctx->rec_slot.ensure(n_rec_max * sizeof(long long)));
-  long long* job_tot = ctx->job_totals.as<long long>() + 2 * (size_t)job_slot;
+  TRY(sc.flags.ensure(n_rec_max));
+  TRY(sc.blk_acc.ensure((size_t)chunk * sizeof(int)));
+  TRY(sc.blk_enum.ensure((size_t)chunk * sizeof(int)));
+  TRY(sc.blk_off.ensure((size_t)chunk * sizeof(long long)));
+  TRY(sc.rec_frame.ensure(n_rec_max * sizeof(int)));
+  TRY(sc.rec_atoms.ensure(n_rec_max * NA * sizeof(int)));
+  TRY(sc.rec_lambda.ensure(n_rec_max * sizeof(double)));
+  TRY(sc.rec_slot.ensure(n_rec_max * sizeof(long long)));
+  long long* job_tot = sc.job_totals.as<long long>() + 2 * (size_t)job_slot;
   for (long long g0 = 0; g0 < my_granules; g0 += chunk) {
     const int blocks = (int)std::min(chunk, my_granules - g0);
-    const int slot = ctx->n_pw_launch % kMaxPwLaunches;  // the contraction launched below takes the same slot
-    long long* totals = ctx->chunk_totals.as<long long>() + 2 * (size_t)slot;
+    const int slot = sc.n_pw_launch % kMaxPwLaunches;  // the contraction launched below takes the same slot
+    long long* totals = sc.chunk_totals.as<long long>() + 2 * (size_t)slot;
     CullArgs ca;
     ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
     ca.n_cand_total = n_cand_total, ca.granule0 = g0;
     ca.shard_rank = shard_rank, ca.shard_count = shard_count;
-    ca.flags = ctx->flags.as<unsigned char>();
-    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    ca.flags = sc.flags.as<unsigned char>();
+    ca.block_accept = sc.blk_acc.as<int>(), ca.block_enum = sc.blk_enum.as<int>();
     TRY(launch_cull(ctx, NA, blocks, ca));
-    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk_acc.as<int>(), ctx->blk_enum.as<int>(), blocks,
-                                               ctx->blk_off.as<long long>(), totals, job_tot);
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(sc.blk_acc.as<int>(), sc.blk_enum.as<int>(), blocks,
+                                               sc.blk_off.as<long long>(), totals, job_tot);
     CompactArgs pa;
     pa.sys = s, pa.job = j;
     pa.n_cand_total = n_cand_total, pa.granule0 = g0;
     pa.shard_rank = shard_rank, pa.shard_count = shard_count;
-    pa.flags = ctx->flags.as<unsigned char>();
-    pa.block_offsets = ctx->blk_off.as<long long>();
+    pa.flags = sc.flags.as<unsigned char>();
+    pa.block_offsets = sc.blk_off.as<long long>();
     pa.rec_base = 0;
-    pa.rec_frame = ctx->rec_frame.as<int>(), pa.rec_atoms = ctx->rec_atoms.as<int>();
-    pa.rec_lambda = ctx->rec_lambda.as<double>(), pa.rec_slot = ctx->rec_slot.as<long long>();
+    pa.rec_frame = sc.rec_frame.as<int>(), pa.rec_atoms = sc.rec_atoms.as<int>();
+    pa.rec_lambda = sc.rec_lambda.as<double>(), pa.rec_slot = sc.rec_slot.as<long long>();
     k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     const long long n_up = shard_candidates(g0, blocks, shard_rank, shard_count, n_cand_total);
     if (decomp) {
       const long long n = n_up * (NA * 3 + 1);
-      k_zero_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rec_slot.as<long long>(), n_up, NA * 3,
+      k_zero_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sc.rec_slot.as<long long>(), n_up, NA * 3,
                                                                          out.E, out.F, totals);
       ctx->launches++;
     }
@@ -748,14 +812,14 @@ static int run_job_pw(mbg_context_t ctx, const SysDev& s, const JobDev& j, const
     a.max_slices = 1;
     a.sig = m->sig, a.c = m->c, a.std = m->std;
     a.n_frag = n_up, a.n_frag_dev = totals;
-    a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
-    a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
+    a.rec_frame = sc.rec_frame.as<int>(), a.rec_atoms = sc.rec_atoms.as<int>();
+    a.rec_lambda = sc.rec_lambda.as<double>(), a.rec_slot = sc.rec_slot.as<long long>();
     a.n_slots_per_frame = (int)j.cand_per_frame;
     a.decomp = decomp ? 1 : 0;
     a.want_virial = want_virial ? 1 : 0;
     a.E = out.E, a.F = out.F, a.virial = out.V;
     a.work_counters = nullptr;
-    TRY(launch_matern_pw(ctx, NA, m->use_E, a, slot));
+    TRY(launch_matern_pw(ctx, sc, NA, m->use_E, a, slot));
   }
   return MBG_OK;
 }
@@ -779,7 +843,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     if (rec_pending == 0) return MBG_OK;
     if (decomp) {
       const long long n = rec_pending * (NA * 3 + 1);
-      k_zero_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rec_slot.as<long long>(), rec_pending,
+      k_zero_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scr.rec_slot.as<long long>(), rec_pending,
                                                                          NA * 3, out.E, out.F);
       ctx->launches++;
     }
@@ -793,8 +857,8 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
       a.n_row_blocks = (m->T + 7) / 8;
       a.sig = m->sig, a.c = m->c, a.std = m->std;
       a.n_frag = rec_pending, a.n_frag_dev = n_frag_dev;
-      a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
-      a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
+      a.rec_frame = ctx->scr.rec_frame.as<int>(), a.rec_atoms = ctx->scr.rec_atoms.as<int>();
+      a.rec_lambda = ctx->scr.rec_lambda.as<double>(), a.rec_slot = ctx->scr.rec_slot.as<long long>();
       a.n_slots_per_frame = (int)j.cand_per_frame;
       a.decomp = decomp ? 1 : 0;
       a.want_virial = want_virial ? 1 : 0;
@@ -811,8 +875,8 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     a.T_pad = m->T_pad, a.P = m->P;
     a.sig = m->sig, a.c = m->c, a.std = m->std;
     a.n_frag = rec_pending, a.n_frag_dev = n_frag_dev;
-    a.rec_frame = ctx->rec_frame.as<int>(), a.rec_atoms = ctx->rec_atoms.as<int>();
-    a.rec_lambda = ctx->rec_lambda.as<double>(), a.rec_slot = ctx->rec_slot.as<long long>();
+    a.rec_frame = ctx->scr.rec_frame.as<int>(), a.rec_atoms = ctx->scr.rec_atoms.as<int>();
+    a.rec_lambda = ctx->scr.rec_lambda.as<double>(), a.rec_slot = ctx->scr.rec_slot.as<long long>();
     a.n_slots_per_frame = (int)j.cand_per_frame;
     a.decomp = decomp ? 1 : 0;
     a.want_virial = want_virial ? 1 : 0;
@@ -829,39 +893,39 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
   if (deferred_slot && !decomp && my_granules > 0 && my_granules <= kChunk && n_cand_total <= kSmallJobCand &&
       ctx->n_deferred < kMaxDeferred && ctx->mma_cfg != 3) {
     const int blocks = (int)my_granules, slot = ctx->n_deferred++;
-    TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
-    TRY(ctx->blk_acc.ensure((size_t)blocks * sizeof(int)));
-    TRY(ctx->blk_enum.ensure((size_t)blocks * sizeof(int)));
-    TRY(ctx->blk_off.ensure((size_t)blocks * sizeof(long long)));
+    TRY(ctx->scr.flags.ensure((size_t)blocks * kCullThreads));
+    TRY(ctx->scr.blk_acc.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.blk_enum.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.blk_off.ensure((size_t)blocks * sizeof(long long)));
     TRY(ctx->deferred_totals.ensure((size_t)kMaxDeferred * 2 * sizeof(long long)));
     long long* totals = ctx->deferred_totals.as<long long>() + 2 * slot;
     CullArgs ca;
     ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
     ca.n_cand_total = n_cand_total, ca.granule0 = 0;
     ca.shard_rank = shard_rank, ca.shard_count = shard_count;
-    ca.flags = ctx->flags.as<unsigned char>();
-    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    ca.flags = ctx->scr.flags.as<unsigned char>();
+    ca.block_accept = ctx->scr.blk_acc.as<int>(), ca.block_enum = ctx->scr.blk_enum.as<int>();
     TRY(launch_cull(ctx, NA, blocks, ca));
-    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk_acc.as<int>(), ctx->blk_enum.as<int>(), blocks,
-                                               ctx->blk_off.as<long long>(), totals);
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->scr.blk_acc.as<int>(), ctx->scr.blk_enum.as<int>(), blocks,
+                                               ctx->scr.blk_off.as<long long>(), totals);
     ctx->launches++;
     for (long long b = 0; b < blocks; ++b) {
       const long long lo = (b * shard_count + shard_rank) * kCullThreads;
       n_cand_shard += std::max(0ll, std::min<long long>(kCullThreads, n_cand_total - lo));
     }
-    TRY(ctx->rec_frame.ensure((size_t)n_cand_shard * sizeof(int)));
-    TRY(ctx->rec_atoms.ensure((size_t)n_cand_shard * NA * sizeof(int)));
-    TRY(ctx->rec_lambda.ensure((size_t)n_cand_shard * sizeof(double)));
-    TRY(ctx->rec_slot.ensure((size_t)n_cand_shard * sizeof(long long)));
+    TRY(ctx->scr.rec_frame.ensure((size_t)n_cand_shard * sizeof(int)));
+    TRY(ctx->scr.rec_atoms.ensure((size_t)n_cand_shard * NA * sizeof(int)));
+    TRY(ctx->scr.rec_lambda.ensure((size_t)n_cand_shard * sizeof(double)));
+    TRY(ctx->scr.rec_slot.ensure((size_t)n_cand_shard * sizeof(long long)));
     CompactArgs pa;
     pa.sys = s, pa.job = j;
     pa.n_cand_total = n_cand_total, pa.granule0 = 0;
     pa.shard_rank = shard_rank, pa.shard_count = shard_count;
-    pa.flags = ctx->flags.as<unsigned char>();
-    pa.block_offsets = ctx->blk_off.as<long long>();
+    pa.flags = ctx->scr.flags.as<unsigned char>();
+    pa.block_offsets = ctx->scr.blk_off.as<long long>();
     pa.rec_base = 0;
-    pa.rec_frame = ctx->rec_frame.as<int>(), pa.rec_atoms = ctx->rec_atoms.as<int>();
-    pa.rec_lambda = ctx->rec_lambda.as<double>(), pa.rec_slot = ctx->rec_slot.as<long long>();
+    pa.rec_frame = ctx->scr.rec_frame.as<int>(), pa.rec_atoms = ctx->scr.rec_atoms.as<int>();
+    pa.rec_lambda = ctx->scr.rec_lambda.as<double>(), pa.rec_slot = ctx->scr.rec_slot.as<long long>();
     k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -874,20 +938,20 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
   }
   for (long long g0 = 0; g0 < my_granules; g0 += kChunk) {
     const int blocks = (int)std::min(kChunk, my_granules - g0);
-    TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
-    TRY(ctx->blk_acc.ensure((size_t)blocks * sizeof(int)));
-    TRY(ctx->blk_enum.ensure((size_t)blocks * sizeof(int)));
-    TRY(ctx->blk_off.ensure((size_t)blocks * sizeof(long long)));
+    TRY(ctx->scr.flags.ensure((size_t)blocks * kCullThreads));
+    TRY(ctx->scr.blk_acc.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.blk_enum.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.blk_off.ensure((size_t)blocks * sizeof(long long)));
     TRY(ctx->totals.ensure(2 * sizeof(long long)));
     CullArgs ca;
     ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
     ca.n_cand_total = n_cand_total, ca.granule0 = g0;
     ca.shard_rank = shard_rank, ca.shard_count = shard_count;
-    ca.flags = ctx->flags.as<unsigned char>();
-    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    ca.flags = ctx->scr.flags.as<unsigned char>();
+    ca.block_accept = ctx->scr.blk_acc.as<int>(), ca.block_enum = ctx->scr.blk_enum.as<int>();
     TRY(launch_cull(ctx, NA, blocks, ca));
-    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk_acc.as<int>(), ctx->blk_enum.as<int>(), blocks,
-                                               ctx->blk_off.as<long long>(), ctx->totals.as<long long>());
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->scr.blk_acc.as<int>(), ctx->scr.blk_enum.as<int>(), blocks,
+                                               ctx->scr.blk_off.as<long long>(), ctx->totals.as<long long>());
     ctx->launches++;
     CUDA_TRY(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -901,24 +965,24 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     }
     if (acc == 0) continue;
     const long long need = rec_pending + acc;
-    const bool fits = (size_t)need * sizeof(int) <= ctx->rec_frame.cap && (size_t)need * NA * sizeof(int) <= ctx->rec_atoms.cap &&
-                      (size_t)need * sizeof(double) <= ctx->rec_lambda.cap && (size_t)need * sizeof(long long) <= ctx->rec_slot.cap;
+    const bool fits = (size_t)need * sizeof(int) <= ctx->scr.rec_frame.cap && (size_t)need * NA * sizeof(int) <= ctx->scr.rec_atoms.cap &&
+                      (size_t)need * sizeof(double) <= ctx->scr.rec_lambda.cap && (size_t)need * sizeof(long long) <= ctx->scr.rec_slot.cap;
     // growing a record buffer would drop pending records: contract them first
     if (rec_pending > 0 && (need > kMaxRec || !fits)) TRY(flush());
     const long long need2 = rec_pending + acc;
-    TRY(ctx->rec_frame.ensure((size_t)need2 * sizeof(int)));
-    TRY(ctx->rec_atoms.ensure((size_t)need2 * NA * sizeof(int)));
-    TRY(ctx->rec_lambda.ensure((size_t)need2 * sizeof(double)));
-    TRY(ctx->rec_slot.ensure((size_t)need2 * sizeof(long long)));
+    TRY(ctx->scr.rec_frame.ensure((size_t)need2 * sizeof(int)));
+    TRY(ctx->scr.rec_atoms.ensure((size_t)need2 * NA * sizeof(int)));
+    TRY(ctx->scr.rec_lambda.ensure((size_t)need2 * sizeof(double)));
+    TRY(ctx->scr.rec_slot.ensure((size_t)need2 * sizeof(long long)));
     CompactArgs pa;
     pa.sys = s, pa.job = j;
     pa.n_cand_total = n_cand_total, pa.granule0 = g0;
     pa.shard_rank = shard_rank, pa.shard_count = shard_count;
-    pa.flags = ctx->flags.as<unsigned char>();
-    pa.block_offsets = ctx->blk_off.as<long long>();
+    pa.flags = ctx->scr.flags.as<unsigned char>();
+    pa.block_offsets = ctx->scr.blk_off.as<long long>();
     pa.rec_base = rec_pending;
-    pa.rec_frame = ctx->rec_frame.as<int>(), pa.rec_atoms = ctx->rec_atoms.as<int>();
-    pa.rec_lambda = ctx->rec_lambda.as<double>(), pa.rec_slot = ctx->rec_slot.as<long long>();
+    pa.rec_frame = ctx->scr.rec_frame.as<int>(), pa.rec_atoms = ctx->scr.rec_atoms.as<int>();
+    pa.rec_lambda = ctx->scr.rec_lambda.as<double>(), pa.rec_slot = ctx->scr.rec_slot.as<long long>();
     k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -942,11 +1006,11 @@ static void begin_call(mbg_context_t ctx) {
   ctx->n_contract = 0;
   ctx->launch_recs.clear();
   ctx->rec_chunk_slot.clear();
-  if (ctx->n_pw_launch > 0) {  // re-zero the work counters the previous call used
-    const size_t used = (size_t)std::min(ctx->n_pw_launch, kMaxPwLaunches) * kPwMaxSlices * sizeof(unsigned int);
-    cudaMemsetAsync(ctx->pw_counters.p, 0, used, ctx->stream);
+  if (ctx->scr.n_pw_launch > 0) {  // re-zero the work counters the previous call used
+    const size_t used = (size_t)std::min(ctx->scr.n_pw_launch, kMaxPwLaunches) * kPwMaxSlices * sizeof(unsigned int);
+    cudaMemsetAsync(ctx->scr.pw_counters.p, 0, used, ctx->stream);
   }
-  ctx->n_pw_launch = 0;
+  ctx->scr.n_pw_launch = 0;
   cudaEventRecord(ctx->ev_call0, ctx->stream);
 }
 
@@ -972,11 +1036,178 @@ static void resolve_timing(mbg_context_t ctx) {
   ctx->ms_other = total - contract;
   ctx->timing_pending = false;
   // fragment counts of the persistent-kernel launches (they never came to the host during the call)
-  if (!ctx->rec_chunk_slot.empty() && ctx->n_pw_launch > 0 && ctx->n_pw_launch <= kMaxPwLaunches &&
-      cudaMemcpy(ctx->h_chunk, ctx->chunk_totals.p, (size_t)ctx->n_pw_launch * 2 * sizeof(long long),
+  if (!ctx->rec_chunk_slot.empty() && ctx->scr.n_pw_launch > 0 && ctx->scr.n_pw_launch <= kMaxPwLaunches &&
+      cudaMemcpy(ctx->h_chunk, ctx->scr.chunk_totals.p, (size_t)ctx->scr.n_pw_launch * 2 * sizeof(long long),
                  cudaMemcpyDeviceToHost) == cudaSuccess)
     for (size_t i = 0; i < ctx->launch_recs.size() && i < ctx->rec_chunk_slot.size(); ++i)
       if (ctx->rec_chunk_slot[i] >= 0) ctx->launch_recs[i].n_frag = ctx->h_chunk[2 * ctx->rec_chunk_slot[i]];
+}
+
+
+// ------------------------------------------------------------------------------------
+// Prepared steps: fixed (system, jobs, frame count), device-resident tables, the whole evaluation in one CUDA graph
+// ------------------------------------------------------------------------------------
+struct mbg_step_s {
+  mbg_context_t ctx = nullptr;
+  int n_atoms = 0, n_frames = 0, n_jobs = 0, n_cells = 0;
+  bool want_virial = false;
+  Tables tab;
+  Scratch scr;
+  SysDev sys;
+  std::vector<JobDev> jobs;
+  std::vector<mbg_model_t> models;
+  std::vector<long long> n_candidates;
+  DevBuf dR, dOut;             // [n_frames][n_atoms][3]; [E | F | virial]
+  double* h_R = nullptr;       // pinned mirrors: the graph's copy nodes keep these addresses
+  double* h_out = nullptr;
+  CellDev* h_cells = nullptr;
+  long long* h_tot = nullptr;  // [n_jobs][2]
+  size_t n_out = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+// Everything one evaluation enqueues on the context's stream -- no host synchronisation, no allocation after the
+// first pass (sizes depend only on what mbg_step_create fixed).
+static int step_enqueue(mbg_step_t st) {
+  mbg_context_t ctx = st->ctx;
+  const size_t nR = (size_t)st->n_frames * st->n_atoms * 3;
+  CUDA_TRY(cudaMemcpyAsync(st->dR.p, st->h_R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (st->n_cells)
+    CUDA_TRY(cudaMemcpyAsync(st->tab.cells.p, st->h_cells, (size_t)st->n_cells * sizeof(CellDev), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(st->dOut.p, 0, st->n_out * sizeof(double), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(st->scr.job_totals.p, 0, (size_t)std::max(st->n_jobs, 1) * 2 * sizeof(long long), ctx->stream));
+  if (st->scr.n_pw_launch > 0)
+    CUDA_TRY(cudaMemsetAsync(st->scr.pw_counters.p, 0,
+                             (size_t)std::min(st->scr.n_pw_launch, kMaxPwLaunches) * kPwMaxSlices * sizeof(unsigned int), ctx->stream));
+  st->scr.n_pw_launch = 0;
+  Outputs out;
+  out.E = st->dOut.as<double>(), out.F = out.E + st->n_frames, out.V = out.F + nR;
+  for (int k = 0; k < st->n_jobs; ++k) {
+    if (st->jobs[k].cand_per_frame <= 0) continue;
+    long long ncs = 0;
+    TRY(run_job_pw(ctx, st->scr, st->sys, st->jobs[k], st->models[k], st->dR.as<double>(), st->n_frames, 0, 1, st->want_virial,
+                   false, out, k, &ncs));
+    st->n_candidates[k] = ncs;
+  }
+  CUDA_TRY(cudaMemcpyAsync(st->h_out, st->dOut.p, st->n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(st->h_tot, st->scr.job_totals.p, (size_t)std::max(st->n_jobs, 1) * 2 * sizeof(long long),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  return MBG_OK;
+}
+
+extern "C" int mbg_step_destroy(mbg_step_t st) {
+  if (!st) return MBG_OK;
+  cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->ctx->stream);
+  if (st->exec) cudaGraphExecDestroy(st->exec);
+  if (st->graph) cudaGraphDestroy(st->graph);
+  st->tab.release();
+  st->scr.release();
+  st->dR.release();
+  st->dOut.release();
+  if (st->h_R) cudaFreeHost(st->h_R);
+  if (st->h_out) cudaFreeHost(st->h_out);
+  if (st->h_cells) cudaFreeHost(st->h_cells);
+  if (st->h_tot) cudaFreeHost(st->h_tot);
+  delete st;
+  return MBG_OK;
+}
+
+extern "C" int mbg_step_create(mbg_context_t ctx, const mbg_system_desc* sys, int32_t n_frames, const mbg_job* jobs,
+                               int32_t n_jobs, uint32_t flags, mbg_step_t* out_step) {
+  if (!ctx || !sys || !jobs || !out_step) return fail(MBG_ERR_ARG, "NULL argument");
+  if (n_frames < 1 || n_jobs < 1 || n_jobs > kMaxJobsPerCall) return fail(MBG_ERR_ARG, "bad frame / job count");
+  if (flags & ~(uint32_t)MBG_FLAG_VIRIAL) return fail(MBG_ERR_UNSUPPORTED, "flag not supported by mbg_step_create");
+  if (!uses_pw(ctx)) return fail(MBG_ERR_UNSUPPORTED, "prepared steps need the persistent contraction kernel (MBG_CONTRACT_DMMA / AUTO)");
+  const bool want_virial = (flags & MBG_FLAG_VIRIAL) != 0;
+  if (want_virial && !sys->cell && !sys->frame_cells) return fail(MBG_ERR_ARG, "virial requires a periodic cell (gdml_predict.py:204-205)");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  mbg_step_t st = new mbg_step_s();
+  st->ctx = ctx;
+  st->n_atoms = sys->n_atoms, st->n_frames = n_frames, st->n_jobs = n_jobs, st->want_virial = want_virial;
+  auto bail = [&](int rc) {
+    ctx->capturing = false;
+    mbg_step_destroy(st);
+    return rc;
+  };
+  int rc = st->scr.init();
+  if (rc != MBG_OK) return bail(rc);
+  memset(&st->sys, 0, sizeof(st->sys));
+  if ((rc = upload_system(ctx, st->tab, sys, n_frames, st->sys)) != MBG_OK) return bail(rc);
+  st->n_cells = (int)st->tab.h_cells.size();
+  size_t total = 0;
+  for (int q = 0; q < n_jobs; ++q) {
+    const mbg_job& jq = jobs[q];
+    if (!jq.model) return bail(fail(MBG_ERR_ARG, "job %d without model", q));
+    total += jq.combs ? (size_t)std::max<int64_t>(jq.n_combs, 0) * jq.model->order
+                      : (jq.set_offsets ? (size_t)jq.set_offsets[jq.model->order] : 0);
+    total += 64;
+  }
+  if ((rc = st->tab.job_ints.ensure(total * sizeof(int))) != MBG_OK) return bail(rc);
+  st->jobs.resize(n_jobs), st->models.resize(n_jobs), st->n_candidates.assign(n_jobs, 0);
+  size_t ints_off = 0;
+  for (int k = 0; k < n_jobs; ++k) {
+    size_t used = 0;
+    if ((rc = build_job(ctx, st->tab, sys, &jobs[k], ints_off, st->jobs[k], &used, k)) != MBG_OK) return bail(rc);
+    ints_off += (used + 15) / 16 * 16 + 16;
+    st->models[k] = jobs[k].model;
+  }
+  const size_t nR = (size_t)n_frames * sys->n_atoms * 3;
+  st->n_out = (size_t)n_frames + nR + (size_t)n_frames * 9;
+  if ((rc = st->dR.ensure(nR * sizeof(double) + 8)) != MBG_OK || (rc = st->dOut.ensure(st->n_out * sizeof(double) + 8)) != MBG_OK)
+    return bail(rc);
+  if (cudaMallocHost(&st->h_R, nR * sizeof(double) + 8) != cudaSuccess ||
+      cudaMallocHost(&st->h_out, st->n_out * sizeof(double) + 8) != cudaSuccess ||
+      cudaMallocHost(&st->h_cells, (size_t)std::max(st->n_cells, 1) * sizeof(CellDev)) != cudaSuccess ||
+      cudaMallocHost(&st->h_tot, (size_t)n_jobs * 2 * sizeof(long long)) != cudaSuccess)
+    return bail(fail(MBG_ERR_NOMEM, "cudaMallocHost for the step failed"));
+  memset(st->h_R, 0, nR * sizeof(double));
+  for (int c = 0; c < st->n_cells; ++c) st->h_cells[c] = st->tab.h_cells[c];
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(fail(MBG_ERR_CUDA, "table upload failed"));
+  // pass 1 (not captured): sizes every scratch buffer; pass 2: the same sequence recorded into a graph
+  ctx->capturing = true;
+  if ((rc = step_enqueue(st)) != MBG_OK) return bail(rc);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(fail(MBG_ERR_CUDA, "step warm-up failed: %s", cudaGetErrorString(cudaGetLastError())));
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+    return bail(fail(MBG_ERR_CUDA, "cudaStreamBeginCapture failed (is the context's stream the legacy default stream?)"));
+  rc = step_enqueue(st);
+  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &st->graph);
+  ctx->capturing = false;
+  if (rc != MBG_OK) return bail(rc);
+  if (ce != cudaSuccess || !st->graph) return bail(fail(MBG_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce)));
+  if (cudaGraphInstantiate(&st->exec, st->graph, 0) != cudaSuccess) return bail(fail(MBG_ERR_CUDA, "cudaGraphInstantiate failed"));
+  *out_step = st;
+  return MBG_OK;
+}
+
+extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells, const double* cutoffs, double* E, double* F,
+                            double* virial, mbg_job_stats* stats) {
+  if (!st || !R || !E || !F) return fail(MBG_ERR_ARG, "NULL argument");
+  if (st->want_virial && !virial) return fail(MBG_ERR_ARG, "the step computes the virial: pass a virial buffer");
+  mbg_context_t ctx = st->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t nR = (size_t)st->n_frames * st->n_atoms * 3;
+  memcpy(st->h_R, R, nR * sizeof(double));
+  if (cells) {
+    if (!st->n_cells) return fail(MBG_ERR_ARG, "the step was created without a periodic cell");
+    if (!cutoffs) return fail(MBG_ERR_ARG, "cells without cutoffs");
+    for (int c = 0; c < st->n_cells; ++c)
+      if (memcmp(st->h_cells[c].cell, cells + 9 * (size_t)c, 9 * sizeof(double)) != 0 || st->h_cells[c].cutoff != cutoffs[c])
+        TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c]));
+  }
+  CUDA_TRY(cudaGraphLaunch(st->exec, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->launches += 0;  // (graph launches replay the kernels counted at capture time)
+  memcpy(E, st->h_out, (size_t)st->n_frames * sizeof(double));
+  memcpy(F, st->h_out + st->n_frames, nR * sizeof(double));
+  if (st->want_virial) memcpy(virial, st->h_out + st->n_frames + nR, (size_t)st->n_frames * 9 * sizeof(double));
+  if (stats)
+    for (int k = 0; k < st->n_jobs; ++k) {
+      stats[k].n_candidates = st->n_candidates[k];
+      stats[k].n_accepted = st->h_tot[2 * k], stats[k].n_enumerated = st->h_tot[2 * k + 1];
+    }
+  return MBG_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1011,10 +1242,7 @@ int mbg_context_create(int device, mbg_context_t* out) {
   ctx->stream = ctx->own_stream;
   CUDA_TRY(cudaMallocHost(&ctx->h_totals, (2 + 2 * kMaxDeferred) * sizeof(long long)));
   CUDA_TRY(cudaMallocHost(&ctx->h_chunk, (size_t)(kMaxPwLaunches + kMaxJobsPerCall) * 2 * sizeof(long long)));
-  TRY(ctx->pw_counters.ensure((size_t)kMaxPwLaunches * kPwMaxSlices * sizeof(unsigned int)));
-  TRY(ctx->chunk_totals.ensure((size_t)kMaxPwLaunches * 2 * sizeof(long long)));
-  TRY(ctx->job_totals.ensure((size_t)kMaxJobsPerCall * 2 * sizeof(long long)));
-  CUDA_TRY(cudaMemset(ctx->pw_counters.p, 0, (size_t)kMaxPwLaunches * kPwMaxSlices * sizeof(unsigned int)));
+  TRY(ctx->scr.init());
   {
     double tab[1 << kExpTableBits];
     for (int j = 0; j < (1 << kExpTableBits); ++j) tab[j] = (double)exp2l((long double)j / (1 << kExpTableBits));
@@ -1041,10 +1269,10 @@ int mbg_context_destroy(mbg_context_t ctx) {
   if (!ctx) return MBG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->sys_ints, &ctx->sys_masses, &ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->job_ints, &ctx->job_binom,
-                    &ctx->flags, &ctx->blk_acc, &ctx->blk_enum, &ctx->blk_off, &ctx->totals, &ctx->rec_frame,
-                    &ctx->rec_atoms, &ctx->rec_lambda, &ctx->rec_slot, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in, &ctx->deferred_totals, &ctx->pw_counters, &ctx->chunk_totals, &ctx->job_totals,
-                    &ctx->km_ints, &ctx->km_out})
+  ctx->tab.release();
+  ctx->scr.release();
+  for (DevBuf* b : {&ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->totals, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
+                    &ctx->deferred_totals, &ctx->km_ints, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_call0);
@@ -1253,12 +1481,13 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
   if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(MBG_ERR_ARG, "bad shard spec");
   const bool want_virial = (flags & MBG_FLAG_VIRIAL) != 0;
   if (want_virial && !virial) return fail(MBG_ERR_ARG, "MBG_FLAG_VIRIAL without a virial buffer");
-  if (want_virial && !sys->cell) return fail(MBG_ERR_ARG, "virial requires a periodic cell (gdml_predict.py:204-205)");
+  if (want_virial && !sys->cell && !sys->frame_cells)
+    return fail(MBG_ERR_ARG, "virial requires a periodic cell (gdml_predict.py:204-205)");
   CUDA_TRY(cudaSetDevice(ctx->device));
   begin_call(ctx);
   SysDev s;
   memset(&s, 0, sizeof(s));
-  TRY(upload_system(ctx, sys, s));
+  TRY(upload_system(ctx, ctx->tab, sys, n_frames, s));
   const size_t nR = (size_t)n_frames * sys->n_atoms * 3;
   const double* dR = R;
   if (!(flags & MBG_FLAG_R_ON_DEVICE)) {
@@ -1287,7 +1516,7 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
   const bool pw = uses_pw(ctx);
   if (pw) {
     if (n_jobs > kMaxJobsPerCall) return fail(MBG_ERR_UNSUPPORTED, "at most %d jobs per call", kMaxJobsPerCall);
-    if (n_jobs > 0) CUDA_TRY(cudaMemsetAsync(ctx->job_totals.p, 0, (size_t)n_jobs * 2 * sizeof(long long), ctx->stream));
+    if (n_jobs > 0) CUDA_TRY(cudaMemsetAsync(ctx->scr.job_totals.p, 0, (size_t)n_jobs * 2 * sizeof(long long), ctx->stream));
   }
   for (int k = 0; k < n_jobs && n_frames > 0; ++k) {
     JobDev j;
@@ -1303,16 +1532,16 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
                           : (jq.set_offsets ? (size_t)jq.set_offsets[jq.model->order] : 0);
         total += 64;
       }
-      TRY(ctx->job_ints.ensure(total * sizeof(int)));
+      TRY(ctx->tab.job_ints.ensure(total * sizeof(int)));
     }
-    TRY(build_job(ctx, sys, &jobs[k], ints_off, j, &used));
+    TRY(build_job(ctx, ctx->tab, sys, &jobs[k], ints_off, j, &used, k));
     ints_off += (used + 15) / 16 * 16 + 16;  // keep slices 64-byte aligned
     mbg_job_stats st = {0, 0, 0};
     int slot = -1;
     if (j.cand_per_frame > 0) {
       if (pw) {
         long long n_cand_shard = 0;
-        TRY(run_job_pw(ctx, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, k,
+        TRY(run_job_pw(ctx, ctx->scr, s, j, jobs[k].model, dR, n_frames, shard_rank, shard_count, want_virial, false, out, k,
                        &n_cand_shard));
         st.n_candidates = n_cand_shard;
       } else {
@@ -1325,7 +1554,7 @@ int mbg_predict(mbg_context_t ctx, const mbg_system_desc* sys, const double* R, 
   long long* h_job = ctx->h_chunk + 2 * (size_t)kMaxPwLaunches;
   const bool want_job_totals = pw && stats && n_jobs > 0 && n_frames > 0;
   if (want_job_totals)
-    CUDA_TRY(cudaMemcpyAsync(h_job, ctx->job_totals.p, (size_t)n_jobs * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_job, ctx->scr.job_totals.p, (size_t)n_jobs * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   if (!deferred.empty())  // counts of the small jobs: one copy, resolved by the synchronisation below
     CUDA_TRY(cudaMemcpyAsync(ctx->h_totals + 2, ctx->deferred_totals.p, (size_t)ctx->n_deferred * 2 * sizeof(long long),
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -1361,7 +1590,7 @@ int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc* sys, const doub
   begin_call(ctx);
   SysDev s;
   memset(&s, 0, sizeof(s));
-  TRY(upload_system(ctx, sys, s));
+  TRY(upload_system(ctx, ctx->tab, sys, 1, s));
   const size_t nR = (size_t)sys->n_atoms * 3;
   const double* dR = R;
   if (!(flags & MBG_FLAG_R_ON_DEVICE)) {
@@ -1374,10 +1603,10 @@ int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc* sys, const doub
   const long long n = job->n_combs, row = (long long)m->n_atoms * 3;
   mbg_job_stats st = {0, 0, 0};
   if (n > 0) {
-    TRY(ctx->job_ints.ensure(((size_t)n * m->order + 32) * sizeof(int)));
+    TRY(ctx->tab.job_ints.ensure(((size_t)n * m->order + 32) * sizeof(int)));
     JobDev j;
     size_t used = 0;
-    TRY(build_job(ctx, sys, job, 0, j, &used));
+    TRY(build_job(ctx, ctx->tab, sys, job, 0, j, &used));
     TRY(ctx->outE.ensure((size_t)n * sizeof(double) + 8));
     TRY(ctx->outF.ensure((size_t)(n * row) * sizeof(double) + 8));
     const double nan = std::numeric_limits<double>::quiet_NaN();
@@ -1387,10 +1616,10 @@ int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc* sys, const doub
     Outputs out = {ctx->outE.as<double>(), ctx->outF.as<double>(), nullptr};
     if (uses_pw(ctx)) {
       long long n_cand_shard = 0;
-      CUDA_TRY(cudaMemsetAsync(ctx->job_totals.p, 0, 2 * sizeof(long long), ctx->stream));
-      TRY(run_job_pw(ctx, s, j, m, dR, 1, 0, 1, false, true, out, 0, &n_cand_shard));
+      CUDA_TRY(cudaMemsetAsync(ctx->scr.job_totals.p, 0, 2 * sizeof(long long), ctx->stream));
+      TRY(run_job_pw(ctx, ctx->scr, s, j, m, dR, 1, 0, 1, false, true, out, 0, &n_cand_shard));
       st.n_candidates = n_cand_shard;
-      CUDA_TRY(cudaMemcpyAsync(ctx->h_chunk + 2 * (size_t)kMaxPwLaunches, ctx->job_totals.p, 2 * sizeof(long long),
+      CUDA_TRY(cudaMemcpyAsync(ctx->h_chunk + 2 * (size_t)kMaxPwLaunches, ctx->scr.job_totals.p, 2 * sizeof(long long),
                                cudaMemcpyDeviceToHost, ctx->stream));
     } else {
       TRY(run_job(ctx, s, j, m, dR, 1, 0, 1, false, true, out, &st));
@@ -1416,14 +1645,14 @@ int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc* sys, const double*
   CUDA_TRY(cudaSetDevice(ctx->device));
   SysDev s;
   memset(&s, 0, sizeof(s));
-  TRY(upload_system(ctx, sys, s));
+  TRY(upload_system(ctx, ctx->tab, sys, n_frames, s));
   const mbg_model_t m = job->model;
   const size_t n_ints = job->combs ? (size_t)std::max<int64_t>(job->n_combs, 0) * m->order
                                    : (job->set_offsets ? (size_t)job->set_offsets[m->order] : 0);
-  TRY(ctx->job_ints.ensure((n_ints + 64) * sizeof(int)));
+  TRY(ctx->tab.job_ints.ensure((n_ints + 64) * sizeof(int)));
   JobDev j;
   size_t used = 0;
-  TRY(build_job(ctx, sys, job, 0, j, &used));
+  TRY(build_job(ctx, ctx->tab, sys, job, 0, j, &used));
   *n_per_frame = j.cand_per_frame;
   if (!mask || n_frames == 0 || j.cand_per_frame == 0) return MBG_OK;
   const size_t nR = (size_t)n_frames * sys->n_atoms * 3;
@@ -1437,18 +1666,18 @@ int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc* sys, const double*
   const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads, kChunk = 1ll << 18;
   for (long long g0 = 0; g0 < n_granules; g0 += kChunk) {
     const int blocks = (int)std::min(kChunk, n_granules - g0);
-    TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
-    TRY(ctx->blk_acc.ensure((size_t)blocks * sizeof(int)));
-    TRY(ctx->blk_enum.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.flags.ensure((size_t)blocks * kCullThreads));
+    TRY(ctx->scr.blk_acc.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.blk_enum.ensure((size_t)blocks * sizeof(int)));
     CullArgs ca;
     ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
     ca.n_cand_total = n_cand_total, ca.granule0 = g0;
     ca.shard_rank = 0, ca.shard_count = 1;
-    ca.flags = ctx->flags.as<unsigned char>();
-    ca.block_accept = ctx->blk_acc.as<int>(), ca.block_enum = ctx->blk_enum.as<int>();
+    ca.flags = ctx->scr.flags.as<unsigned char>();
+    ca.block_accept = ctx->scr.blk_acc.as<int>(), ca.block_enum = ctx->scr.blk_enum.as<int>();
     TRY(launch_cull(ctx, m->n_atoms, blocks, ca));
     const long long lo = g0 * kCullThreads, n = std::min<long long>((long long)blocks * kCullThreads, n_cand_total - lo);
-    CUDA_TRY(cudaMemcpyAsync(mask + lo, ctx->flags.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(mask + lo, ctx->scr.flags.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
   return MBG_OK;
@@ -1472,9 +1701,9 @@ int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t* set_offsets, 
     else prod *= n_s;
   }
   const size_t n_int = (size_t)set_offsets[order];
-  TRY(ctx->job_ints.ensure((n_int + 16) * sizeof(int)));
-  if (n_int) CUDA_TRY(cudaMemcpyAsync(ctx->job_ints.p, set_entities, n_int * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  j.set_ent = ctx->job_ints.as<int>();
+  TRY(ctx->tab.job_ints.ensure((n_int + 16) * sizeof(int)));
+  if (n_int) CUDA_TRY(cudaMemcpyAsync(ctx->tab.job_ints.p, set_entities, n_int * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  j.set_ent = ctx->tab.job_ints.as<int>();
   j.cand_per_frame = prod;
   const long long capacity = combs ? *n_combs : 0;
   long long total = 0;
@@ -1482,14 +1711,14 @@ int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t* set_offsets, 
   const long long n_blocks = (prod + kCullThreads - 1) / kCullThreads;
   for (long long b0 = 0; b0 < n_blocks; b0 += kChunk) {
     const int blocks = (int)std::min(kChunk, n_blocks - b0);
-    TRY(ctx->flags.ensure((size_t)blocks * kCullThreads));
-    TRY(ctx->blk_acc.ensure((size_t)blocks * sizeof(int)));
-    TRY(ctx->blk_off.ensure((size_t)blocks * sizeof(long long)));
+    TRY(ctx->scr.flags.ensure((size_t)blocks * kCullThreads));
+    TRY(ctx->scr.blk_acc.ensure((size_t)blocks * sizeof(int)));
+    TRY(ctx->scr.blk_off.ensure((size_t)blocks * sizeof(long long)));
     TRY(ctx->totals.ensure(2 * sizeof(long long)));
     const long long cand0 = b0 * kCullThreads;
-    k_flag_ascending<<<blocks, kCullThreads, 0, ctx->stream>>>(j, cand0, prod, ctx->flags.as<unsigned char>(),
-                                                               ctx->blk_acc.as<int>());
-    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk_acc.as<int>(), nullptr, blocks, ctx->blk_off.as<long long>(),
+    k_flag_ascending<<<blocks, kCullThreads, 0, ctx->stream>>>(j, cand0, prod, ctx->scr.flags.as<unsigned char>(),
+                                                               ctx->scr.blk_acc.as<int>());
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->scr.blk_acc.as<int>(), nullptr, blocks, ctx->scr.blk_off.as<long long>(),
                                                ctx->totals.as<long long>());
     ctx->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1497,11 +1726,11 @@ int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t* set_offsets, 
     const long long cnt = ctx->h_totals[0];
     if (combs && cnt > 0) {
       if (total + cnt > capacity) return fail(MBG_ERR_ARG, "combs buffer too small");
-      TRY(ctx->rec_atoms.ensure((size_t)cnt * order * sizeof(int)));
-      k_write_combs<<<blocks, kCullThreads, 0, ctx->stream>>>(j, cand0, ctx->flags.as<unsigned char>(),
-                                                              ctx->blk_off.as<long long>(), 0, ctx->rec_atoms.as<int>());
+      TRY(ctx->scr.rec_atoms.ensure((size_t)cnt * order * sizeof(int)));
+      k_write_combs<<<blocks, kCullThreads, 0, ctx->stream>>>(j, cand0, ctx->scr.flags.as<unsigned char>(),
+                                                              ctx->scr.blk_off.as<long long>(), 0, ctx->scr.rec_atoms.as<int>());
       ctx->launches++;
-      CUDA_TRY(cudaMemcpyAsync(combs + total * order, ctx->rec_atoms.p, (size_t)cnt * order * sizeof(int),
+      CUDA_TRY(cudaMemcpyAsync(combs + total * order, ctx->scr.rec_atoms.p, (size_t)cnt * order * sizeof(int),
                                cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
@@ -1537,13 +1766,13 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
   const size_t nR = (size_t)n_R * n_atoms * 3;
   TRY(ctx->R.ensure(nR * sizeof(double)));
   TRY(ctx->outE.ensure((size_t)n_R * sizeof(double)));
-  TRY(ctx->sys_masses.ensure((size_t)n_atoms * sizeof(double)));
-  TRY(ctx->sys_ints.ensure((size_t)n_atoms * sizeof(int)));
+  TRY(ctx->tab.sys_masses.ensure((size_t)n_atoms * sizeof(double)));
+  TRY(ctx->tab.sys_ints.ensure((size_t)n_atoms * sizeof(int)));
   CUDA_TRY(cudaMemcpyAsync(ctx->R.p, R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(ctx->sys_masses.p, m.data(), (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(ctx->sys_ints.p, group.data(), (size_t)n_atoms * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  k_criteria_eval<<<(unsigned)((n_R + 127) / 128), 128, 0, ctx->stream>>>(kind, n_atoms, ctx->sys_masses.as<double>(),
-                                                                          ctx->sys_ints.as<int>(), n_groups,
+  CUDA_TRY(cudaMemcpyAsync(ctx->tab.sys_masses.p, m.data(), (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->tab.sys_ints.p, group.data(), (size_t)n_atoms * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  k_criteria_eval<<<(unsigned)((n_R + 127) / 128), 128, 0, ctx->stream>>>(kind, n_atoms, ctx->tab.sys_masses.as<double>(),
+                                                                          ctx->tab.sys_ints.as<int>(), n_groups,
                                                                           ctx->R.as<double>(), n_R, ctx->outE.as<double>());
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1557,8 +1786,7 @@ int mbg_r_mic(mbg_context_t ctx, const double* cell, double cutoff, const double
   if (!ctx || !cell || !r || !out || !accepted) return fail(MBG_ERR_ARG, "NULL argument");
   if (n < 1) return fail(MBG_ERR_ARG, "n < 1");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  SysDev s;
-  memset(&s, 0, sizeof(s));
+  CellDev s;
   TRY(fill_cell(s, cell, cutoff));
   s.fast_reject = 0;  // the caller wants the coordinates even when the fragment is rejected
   TRY(ctx->R.ensure((size_t)n * 3 * sizeof(double)));
@@ -1650,8 +1878,8 @@ int mbg_mbe_accumulate(mbg_context_t ctx, int64_t n_ref, const int64_t* ref_rows
   const size_t nd_low = (size_t)n_lower * (1 + 3 * (size_t)n_atoms_lower);
   const size_t nd_out = (size_t)n_total * (1 + 3 * (size_t)n_atoms_ref);
   const size_t bytes = n64 * 8 + ((n32 * 4 + 7) / 8) * 8 + (nd_low + nd_out) * 8;
-  TRY(ctx->flags.ensure(bytes + 64));
-  char* base = ctx->flags.as<char>();
+  TRY(ctx->scr.flags.ensure(bytes + 64));
+  char* base = ctx->scr.flags.as<char>();
   long long* d64 = reinterpret_cast<long long*>(base);
   int* d32 = reinterpret_cast<int*>(base + n64 * 8);
   double* dd = reinterpret_cast<double*>(base + n64 * 8 + ((n32 * 4 + 7) / 8) * 8);

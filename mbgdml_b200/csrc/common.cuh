@@ -13,6 +13,18 @@ constexpr int kMaxFragAtoms = MBG_MAX_FRAG_ATOMS;
 constexpr int kMaxAlchemy = MBG_MAX_ALCHEMY;
 constexpr int kCullThreads = 256;  // candidates per cull/compact block == sharding granule
 
+// One periodic cell on device (mbgdml/periodic.py:32-140): lives in device memory so that every frame of a batch can
+// have its own (NPT trajectories, the strained boxes of the finite-difference virial, stress.py:75-152) and so that
+// a captured CUDA graph of a step sees a new cell without being re-captured.
+struct CellDev {
+  double cell[9], cell_inv[9];    // row vectors; f = v @ cell_inv
+  double rcell[9], rcell_inv[9];  // Minkowski-reduced cell for the general branch
+  double half_min_len;            // 0.5 * min |cell vector|
+  double cutoff;                  // Cell.cutoff
+  int fast_reject;                // orthorhombic cell and cutoff <= half_min_len: a naive image beyond L_min/2 implies rejection
+  int pad;
+};
+
 // The supersystem on device.
 struct SysDev {
   int n_atoms;
@@ -20,13 +32,12 @@ struct SysDev {
   const int* ent_off;    // [n_entities+1]
   const int* ent_atoms;  // CSR values
   const double* masses;  // [n_atoms]
-  int periodic;          // 0: cluster, 1: minimum-image under `cell`
-  int fast_reject;       // orthorhombic cell and cutoff <= half_min_len: a failed naive MIC implies rejection
-  double cell[9], cell_inv[9];    // row vectors; f = v @ cell_inv
-  double rcell[9], rcell_inv[9];  // Minkowski-reduced cell for the general branch
-  double half_min_len;            // 0.5 * min |cell vector|
-  double cutoff;                  // Cell.cutoff
+  int periodic;          // 0: cluster, 1: minimum-image under cells[frame * cell_stride]
+  int cell_stride;       // 0: one cell for all frames, 1: one per frame
+  const CellDev* cells;
 };
+
+__device__ __forceinline__ const CellDev& cell_of(const SysDev& s, long long frame) { return s.cells[frame * s.cell_stride]; }
 
 // Acceptance criteria of one model.
 struct CritDev {

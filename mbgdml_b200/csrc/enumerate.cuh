@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(kCullThreads) k_cull(const __grid_constant__ C
     if (decode_tuple(a.job, cand, ent)) {
       const double* Rf = a.R + frame * 3ll * a.sys.n_atoms;
       flag = 2;
-      if (first_atoms_may_pass(a.sys, a.job, Rf, ent)) {
+      if (first_atoms_may_pass(a.sys, frame, a.job, Rf, ent)) {
         int atoms[kMaxFragAtoms];
         gather_atoms(a.sys, a.job, ent, atoms);
         double r[NA][3];
-        flag = fragment_accept<NA>(a.sys, a.crit, Rf, atoms, r) ? 1 : 2;
+        flag = fragment_accept<NA>(a.sys, frame, a.crit, Rf, atoms, r) ? 1 : 2;
       }
     }
   }

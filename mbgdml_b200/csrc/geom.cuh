@@ -29,7 +29,7 @@ __device__ __forceinline__ void vec_mat_rn(const double v[3], const double* M, d
 }
 
 // ase.geometry.naive_find_mic: f = v cell^-1 ; f -= floor(f + 0.5) ; v' = f cell.  Returns |v'|.
-__device__ __forceinline__ double mic_naive(const SysDev& s, const double v[3], double out[3]) {
+__device__ __forceinline__ double mic_naive(const CellDev& s, const double v[3], double out[3]) {
   double f[3];
   vec_mat_rn(v, s.cell_inv, f);
 #pragma unroll
@@ -40,7 +40,7 @@ __device__ __forceinline__ double mic_naive(const SysDev& s, const double v[3], 
 
 // ase.geometry.general_find_mic on the Minkowski-reduced cell: wrap into [0,1)^3, then the
 // shortest of (0,0,0) followed by itertools.product([-1,0,1], repeat=3); first minimum wins.
-__device__ __noinline__ void mic_general(const SysDev& s, const double v[3], double out[3]) {
+__device__ __noinline__ void mic_general(const CellDev& s, const double v[3], double out[3]) {
   double f[3], pos[3];
   vec_mat_rn(v, s.rcell_inv, f);
 #pragma unroll
@@ -139,14 +139,15 @@ __device__ __forceinline__ double alchemy_lambda(const JobDev& j, const int ent[
 // Load the fragment's coordinates; under periodicity re-express them relative to the first atom
 // in the minimum image and apply the pair cut-off (periodic.py:61-107).  Returns false if rejected.
 template <int NA>
-__device__ __forceinline__ bool fragment_coords(const SysDev& s, const double* __restrict__ Rf,
+__device__ __forceinline__ bool fragment_coords(const SysDev& sys, long long frame, const double* __restrict__ Rf,
                                                 const int* atoms, double (*r)[3]) {
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
     const double* p = Rf + 3 * (long long)atoms[a];
     r[a][0] = p[0], r[a][1] = p[1], r[a][2] = p[2];
   }
-  if (!s.periodic) return true;
+  if (!sys.periodic) return true;
+  const CellDev& s = cell_of(sys, frame);
   const double r0[3] = {r[0][0], r[0][1], r[0][2]};
   bool naive_ok = true, naive_far = false;
 #pragma unroll
@@ -244,16 +245,18 @@ __device__ __forceinline__ bool criteria_accept(const CritDev& c, double v) {
 // rounding differs from the naive image by a few ulp); everything closer goes to the full evaluation, so
 // returning false early never changes the accept mask.  Consecutive candidates share their leading entities,
 // so warps exit together.
-__device__ __forceinline__ bool first_atoms_may_pass(const SysDev& s, const JobDev& j, const double* __restrict__ Rf,
-                                                     const int ent[kMaxOrder]) {
-  if (!(s.periodic && s.fast_reject)) return true;
+__device__ __forceinline__ bool first_atoms_may_pass(const SysDev& sys, long long frame, const JobDev& j,
+                                                     const double* __restrict__ Rf, const int ent[kMaxOrder]) {
+  if (!sys.periodic) return true;
+  const CellDev& s = cell_of(sys, frame);
+  if (!s.fast_reject) return true;
   double v[kMaxOrder][3];
   bool safe[kMaxOrder];  // the naive image is the unique minimum image, whatever branch find_mic ends up taking
-  const double* p0 = Rf + 3ll * s.ent_atoms[s.ent_off[ent[0]]];
+  const double* p0 = Rf + 3ll * sys.ent_atoms[sys.ent_off[ent[0]]];
 #pragma unroll
   for (int k = 0; k < kMaxOrder; ++k) {
     if (k >= j.order) break;
-    const double* p = Rf + 3ll * s.ent_atoms[s.ent_off[ent[k]]];
+    const double* p = Rf + 3ll * sys.ent_atoms[sys.ent_off[ent[k]]];
     const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
     const double len = mic_naive(s, d, v[k]);
     if (len >= s.half_min_len * kGuard) return false;
@@ -270,9 +273,9 @@ __device__ __forceinline__ bool first_atoms_may_pass(const SysDev& s, const JobD
 
 // Full accept decision for one fragment; r receives the coordinates the descriptor is built from.
 template <int NA>
-__device__ __forceinline__ bool fragment_accept(const SysDev& s, const CritDev& c, const double* __restrict__ Rf,
-                                                const int* atoms, double (*r)[3]) {
-  if (!fragment_coords<NA>(s, Rf, atoms, r)) return false;
+__device__ __forceinline__ bool fragment_accept(const SysDev& s, long long frame, const CritDev& c,
+                                                const double* __restrict__ Rf, const int* atoms, double (*r)[3]) {
+  if (!fragment_coords<NA>(s, frame, Rf, atoms, r)) return false;
   if (c.kind == MBG_CRIT_NONE) return true;
   return criteria_accept(c, criteria_value<NA>(s, c, atoms, r));
 }

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kMaternThreads, Blocking<NA>::MinCtas) k_mater
     int at[NA];
 #pragma unroll
     for (int k = 0; k < NA; ++k) at[k] = atoms[k];
-    fragment_coords<NA>(a.sys, Rf, at, r);
+    fragment_coords<NA>(a.sys, a.rec_frame[frag], Rf, at, r);
     int k = 0;
 #pragma unroll
     for (int i = 0; i < NA; ++i) {

@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
     if (a.sys.periodic) {
       const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
       const double d[3] = {__dsub_rn(v[0], p0[0]), __dsub_rn(v[1], p0[1]), __dsub_rn(v[2], p0[2])};
-      if (!(mic_naive(a.sys, d, v) < a.sys.half_min_len)) bad[fl] = 1;
+      const CellDev& cl = cell_of(a.sys, a.rec_frame[frag]);
+        if (!(mic_naive(cl, d, v) < cl.half_min_len)) bad[fl] = 1;
     }
     rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
   }
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
       const double* p0 = Rf + 3ll * a.rec_atoms[frag * NA];
       const double d[3] = {__dsub_rn(p[0], p0[0]), __dsub_rn(p[1], p0[1]), __dsub_rn(p[2], p0[2])};
       double v[3];
-      mic_general(a.sys, d, v);
+      mic_general(cell_of(a.sys, a.rec_frame[frag]), d, v);
       rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
     }
     __syncthreads();

@@ -122,10 +122,24 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   const long long nq = n_frag * P;
   const long long n_groups = (nq + QW - 1) / QW;
   const int n_tiles_data = (a.n_row_blocks + BPT - 1) / BPT;  // tiles that hold training rows
+  // Row slices: the launch is cut into n_sl slices of the training rows when there are too few items to occupy the
+  // warps.  Cost model (units: one row block of one warp with all nw warps busy): an item costs its row blocks times
+  // the share of a scheduler its warp gets, floored at the single-warp latency (~0.35), plus ~4 for prologue and
+  // epilogue; the slowest warp runs ceil(items / warp slots) of them.
   int n_sl = 1;
   {
-    const long long slots = (long long)gridDim.x * nw;
-    while (n_sl * 2 <= a.max_slices && n_groups * n_sl < slots) n_sl *= 2;
+    const double slots = (double)gridDim.x * nw;
+    double best = 1e300;
+    for (int cand = 1; cand <= a.max_slices; cand *= 2) {
+      const int tps_c = (n_tiles_data + cand - 1) / cand;
+      const int sl_eff = (n_tiles_data + tps_c - 1) / tps_c;
+      const double items = (double)n_groups * sl_eff;
+      const double rounds = ceil(items / slots);
+      const double busy = fmin(1.0, items / slots / rounds * 1.0);         // fraction of the warp slots in use
+      const double share = fmax(0.35, busy);                               // per-block time relative to full occupancy
+      const double cost = rounds * (fmin((double)a.n_row_blocks, (double)tps_c * BPT) * share + 4.0);
+      if (cost < best * 0.97) best = cost, n_sl = cand;
+    }
   }
   const int tps = (n_tiles_data + n_sl - 1) / n_sl;  // tiles per row slice
   n_sl = (n_tiles_data + tps - 1) / tps;             // slices that hold data
@@ -291,7 +305,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       if (a.sys.periodic) {
         const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
         const double d[3] = {__dsub_rn(v[0], pf[0]), __dsub_rn(v[1], pf[1]), __dsub_rn(v[2], pf[2])};
-        if (!(mic_naive(a.sys, d, v) < a.sys.half_min_len)) bad[fl] = 1;
+        const CellDev& cl = cell_of(a.sys, a.rec_frame[frag]);
+        if (!(mic_naive(cl, d, v) < cl.half_min_len)) bad[fl] = 1;
       }
       rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
     }
@@ -307,7 +322,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
         const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
         const double d[3] = {__dsub_rn(p[0], pf[0]), __dsub_rn(p[1], pf[1]), __dsub_rn(p[2], pf[2])};
         double v[3];
-        mic_general(a.sys, d, v);
+        mic_general(cell_of(a.sys, a.rec_frame[frag]), d, v);
         rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
       }
       __syncwarp();

@@ -212,6 +212,11 @@ class mbePredict:  # pylint: disable=invalid-name
         self.box_scaling_type = "anisotropic"
         self.last_stats = None
         self.shard_group = None  # opt-in multi-GPU fragment sharding (see _shard_group)
+        # Latency mode (MD: interfaces/ase.py:65-108 calls predict once per integrator step with the same system):
+        # from the second evaluation of the same (system, models, frame count) on, the whole call is one replay of
+        # a captured CUDA graph (mbg_step_create / mbg_step_run).  Set to False to always take the plain call.
+        self.use_graph = True
+        self._steps = _engine.StepCache()
 
     @property
     def periodic_cell(self):
@@ -265,15 +270,37 @@ class mbePredict:  # pylint: disable=invalid-name
         return E, F, entity_combs
 
     # ------------------------------------------------------------------------------
-    def _predict_batched(self, Z, R, entity_ids, comp_ids, want_virial):
-        """Fast path: every frame and every model in one native call (+ one all-reduce)."""
+    def _predict_batched(self, Z, R, entity_ids, comp_ids, want_virial, frame_cells=None):
+        """Fast path: every frame and every model in one native call (+ one all-reduce).  ``frame_cells`` =
+        (cells (n_frames, 3, 3), cutoffs (n_frames,)) evaluates every frame under its own periodic cell."""
         ctx = _native.get_context()
         sources = [gen_combs(self.get_avail_entities(comp_ids, m.comp_ids)) for m in self.models]
         scalers = [self._scalers_for(m) for m in self.models]
+        cell = None if frame_cells is not None else self.periodic_cell
         group = _shard_group(self.shard_group)
         if group is None:
-            E, F, V, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
-                                                   self.periodic_cell, compute_virial=want_virial)
+            step = None
+            if self.use_graph and not hasattr(R, "data_ptr"):
+                try:
+                    key = _engine.step_key(Z, entity_ids, comp_ids, self.models, scalers, R.shape[0], cell, frame_cells,
+                                           want_virial)
+                    step = self._steps.get(key, lambda: _engine.make_step(
+                        ctx, Z, entity_ids, self.models, sources, scalers, cell, R.shape[0], compute_virial=want_virial,
+                        frame_cells=frame_cells))
+                except NotImplementedError:  # e.g. the FMA-pipe / wave-launched kernels are selected
+                    self.use_graph, step = False, None
+            if step is not None:
+                if frame_cells is not None:
+                    cells, cutoffs = frame_cells
+                elif cell is not None:
+                    cells, cutoffs = cell.native_cell()
+                    cutoffs = np.array([cutoffs])
+                else:
+                    cells = cutoffs = None
+                E, F, V, stats = step.run(R, cells, cutoffs)
+            else:
+                E, F, V, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers, cell,
+                                                       compute_virial=want_virial, frame_cells=frame_cells)
             self.last_stats = stats
             return E, F, V
         import torch
@@ -293,9 +320,9 @@ class mbePredict:  # pylint: disable=invalid-name
         prev = ctx.swap_stream(cur if cur != 0 else 1)
         try:
             _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
-                                                   self.periodic_cell, compute_virial=want_virial,
+                                                   cell, compute_virial=want_virial,
                                                    shard=(dist.get_rank(group), dist.get_world_size(group)),
-                                                   device_out=(E_t, F_t, V_t))
+                                                   device_out=(E_t, F_t, V_t), frame_cells=frame_cells)
         finally:
             ctx.swap_stream(prev)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
@@ -335,6 +362,7 @@ class mbePredict:  # pylint: disable=invalid-name
         if compute_stress and self.virial_form == "finite_diff":
             cell_v = self.periodic_cell.cell_v
             for i, r in enumerate(R):
+                # like the reference (mbe.py:1065-1073) the call does not forward self.finite_diff_dh: dh stays 1e-4
                 stress[i] = virial_finite_diff(Z, r, entity_ids, comp_ids, cell_v, self,
                                                only_normal_stress=self.only_normal_stress)
 
