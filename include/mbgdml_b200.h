@@ -79,6 +79,10 @@ typedef struct mbg_model_desc {
   int32_t criteria_bound;        /* MBG_BOUND_*                                                         */
   double criteria_lo, criteria_hi;
   const int32_t *criteria_entity_ids; /* [n_atoms] desc_kwargs["entity_ids"] for com_distance_sum, else NULL */
+  /* model["lattice"] (gdml_model.py:97-101), lattice vectors as COLUMNS, or NULL: when present the descriptor and
+   * its Jacobian use pair differences clamped to this lattice (_gdml/desc.py:42-76 _pbc_diff).  Runs on the
+   * MBG_CONTRACT_DMMA / AUTO kernel. */
+  const double *lattice;         /* [9] row-major or NULL                                                  */
 } mbg_model_desc;
 
 /* The supersystem: which atoms form which entity, masses, optional periodic cell
@@ -200,6 +204,13 @@ int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc *sys, const double 
  * then with a buffer of [*n_combs][order] int32. */
 int mbg_enumerate(mbg_context_t ctx, int32_t order, const int32_t *set_offsets,
                   const int32_t *set_entities, int32_t *combs, int64_t *n_combs);
+
+/* _from_r (_gdml/desc.py:203-233) on device for n_R geometries R[n_R][n_atoms][3]: descriptor x[n_R][D] (1 / pair
+ * distance, np.tril_indices(n, -1) order) and its compressed Jacobian J[n_R][D][3] ((r_i - r_j) / |r_i - r_j|^3), with the
+ * pair differences clamped to `lattice` ([9], vectors as columns; NULL: none) as _pbc_diff does.  This is what
+ * gdmlModel.desc_func evaluates for a predictor that consumes the model object itself. */
+int mbg_from_r(mbg_context_t ctx, int32_t n_atoms, const double *lattice, const double *R, int64_t n_R, double *x,
+               double *J);
 
 /* Criteria.desc on device for a batch of same-size structures (descriptors.py:131-201):
  * R[n_R][n_atoms][3] -> values[n_R].  entity_ids is used by MBG_CRIT_COM_DISTANCE_SUM only. */

@@ -28,7 +28,7 @@ class _ModelDesc(C.Structure):  # struct mbg_model_desc (include/mbgdml_b200.h),
                 ("sig", C.c_double), ("c", C.c_double), ("std", C.c_double),
                 ("R_desc", _dp), ("R_d_desc_alpha", _dp), ("tril_perms_lin", _lp), ("alphas_E", _dp),
                 ("criteria_kind", C.c_int32), ("criteria_bound", C.c_int32),
-                ("criteria_lo", C.c_double), ("criteria_hi", C.c_double), ("criteria_entity_ids", _ip)]
+                ("criteria_lo", C.c_double), ("criteria_hi", C.c_double), ("criteria_entity_ids", _ip), ("lattice", _dp)]
 
 
 class _SystemDesc(C.Structure):  # struct mbg_system_desc
@@ -103,8 +103,7 @@ def _handle(model):
         return cached
     lib = _library()
     m = model.model_dict
-    if "lattice" in m:
-        raise NotImplementedError("models carrying `lattice` are not supported by this binding")
+    lat = np.ascontiguousarray(m["lattice"], dtype=np.float64).reshape(9) if "lattice" in m else None
     n_atoms = len(model.Z)
     R_desc = np.ascontiguousarray(m["R_desc"], dtype=np.float64)
     RdA = np.ascontiguousarray(m["R_d_desc_alpha"], dtype=np.float64)
@@ -115,7 +114,8 @@ def _handle(model):
                    float(m["c"]), float(m["std"]) if "std" in m else 1.0,
                    R_desc.ctypes.data_as(_dp), RdA.ctypes.data_as(_dp), tpl.ctypes.data_as(_lp),
                    aE.ctypes.data_as(_dp) if aE is not None else _dp(), kind, bound, lo, hi,
-                   eids.ctypes.data_as(_ip) if eids is not None else _ip())
+                   eids.ctypes.data_as(_ip) if eids is not None else _ip(),
+                   lat.ctypes.data_as(_dp) if lat is not None else _dp())
     h = C.c_void_p()
     _check(lib, lib.mbg_model_create(_ctx, C.byref(d), C.byref(h)))
     model._b200_handle = h

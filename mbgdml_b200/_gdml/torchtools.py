@@ -22,9 +22,10 @@ class GDMLTorchPredict(nn.Module):
     def __init__(self, model, lat_and_inv=None, batch_size=None, n_perm_batches=1, max_memory=None,
                  max_processes=None, log_level=None):  # pylint: disable=unused-argument
         super().__init__()
-        if lat_and_inv is not None:
-            raise NotImplementedError("sGDML periodic descriptors (lat_and_inv) have no device implementation")
         model = dict(model)
+        if lat_and_inv is not None:  # the kernels clamp pair differences to this lattice (_gdml/desc.py:42-76)
+            lat = lat_and_inv[0]
+            model["lattice"] = lat.detach().cpu().numpy() if hasattr(lat, "detach") else np.asarray(lat)
         model.setdefault("r_unit", np.array("Angstrom"))
         self.dim_d, self.n_train = model["R_desc"].shape[:2]
         self.n_perms, self.n_atoms = model["perms"].shape

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_step_create", "mbg_step_run",
     "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
-    "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
+    "mbg_from_r", "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
     "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
 ]
 
@@ -48,7 +48,7 @@ class ModelDesc(C.Structure):
         ("sig", C.c_double), ("c", C.c_double), ("std", C.c_double),
         ("R_desc", _dp), ("R_d_desc_alpha", _dp), ("tril_perms_lin", _lp), ("alphas_E", _dp),
         ("criteria_kind", C.c_int32), ("criteria_bound", C.c_int32),
-        ("criteria_lo", C.c_double), ("criteria_hi", C.c_double), ("criteria_entity_ids", _ip),
+        ("criteria_lo", C.c_double), ("criteria_hi", C.c_double), ("criteria_entity_ids", _ip), ("lattice", _dp),
     ]
 
 
@@ -112,6 +112,7 @@ def load_library():
         lib.mbg_accept_mask.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.c_int32, C.POINTER(Job), C.c_uint32,
                                         C.c_void_p, _lp]
         lib.mbg_enumerate.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, _lp]
+        lib.mbg_from_r.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp]
         lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
         lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
         lib.mbg_mbe_accumulate.argtypes = [C.c_void_p, C.c_int64, _lp, _lp, _lp, _ip, C.c_int32, C.c_int32, _ip, _ip,
@@ -270,6 +271,16 @@ class Context:
             check(self.lib.mbg_enumerate(self.handle, order, ptr(offs, _ip), ptr(vals, _ip), ptr(combs, _ip),
                                          C.byref(n)))
         return combs
+
+    def from_r(self, R, lattice=None):
+        """_from_r (_gdml/desc.py:203-233) for R (n_R, n_atoms, 3): descriptors (n_R, D) and Jacobians (n_R, D, 3)."""
+        R = as_f64(R)
+        n_R, n_atoms = R.shape[0], R.shape[1]
+        D = n_atoms * (n_atoms - 1) // 2
+        x, J = np.empty((n_R, D)), np.empty((n_R, D, 3))
+        lat = as_f64(lattice).reshape(9) if lattice is not None else None
+        check(self.lib.mbg_from_r(self.handle, n_atoms, ptr(lat, _dp), ptr(R, _dp), n_R, ptr(x, _dp), ptr(J, _dp)))
+        return x, J
 
     def criteria_eval(self, kind, masses, entity_ids, R):
         R = as_f64(R)

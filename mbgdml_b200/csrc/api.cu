@@ -146,6 +146,8 @@ struct mbg_model_s {
   int n_atoms, order, D, T, T_pad, P;
   double sig, c, std;
   bool use_E;
+  bool use_lat = false;
+  double lat[9], lat_inv[9];
   double2* XA = nullptr;     // FMA-pipe kernel: [T_pad][Dp] (X, A) interleaved
   double* tiles_mma = nullptr;  // DMMA kernel: packed tiles (matern_mma.cuh)
   double* mu = nullptr;         // DMMA kernel: centre of the training descriptors [D]
@@ -511,6 +513,27 @@ __global__ void k_criteria_eval(int kind, int n, const double* masses, const int
   out[s] = dsum;
 }
 
+// _from_r (_gdml/desc.py:203-233): one thread per (structure, atom pair)
+__global__ void k_from_r(int n, int use_lat, CellDev lat /* .cell = lattice, .cell_inv = inverse */, const double* R,
+                         long long n_R, double* x, double* J) {
+  const int D = n * (n - 1) / 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_R * D) return;
+  const long long s = t / D;
+  const int k = (int)(t - s * D);
+  int i = 1;
+  while ((i + 1) * i / 2 <= k) ++i;
+  const int j = k - i * (i - 1) / 2;
+  const double* ri = R + (s * n + i) * 3;
+  const double* rj = R + (s * n + j) * 3;
+  double d[3] = {__dsub_rn(ri[0], rj[0]), __dsub_rn(ri[1], rj[1]), __dsub_rn(ri[2], rj[2])};
+  if (use_lat) pbc_diff(lat.cell, lat.cell_inv, d);
+  const double dist = norm3_rn(d[0], d[1], d[2]);
+  x[t] = __ddiv_rn(1.0, dist);
+  const double d3 = dist * dist * dist;
+  J[t * 3] = d[0] / d3, J[t * 3 + 1] = d[1] / d3, J[t * 3 + 2] = d[2] / d3;
+}
+
 __global__ void k_r_mic(CellDev s, const double* r, int n, double* out, int* accepted) {
   if (threadIdx.x || blockIdx.x) return;
   bool naive_ok = true;
@@ -819,6 +842,8 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
     a.want_virial = want_virial ? 1 : 0;
     a.E = out.E, a.F = out.F, a.virial = out.V;
     a.work_counters = nullptr;
+    a.use_lat = m->use_lat ? 1 : 0;
+    if (m->use_lat) memcpy(a.lat, m->lat, sizeof(a.lat)), memcpy(a.lat_inv, m->lat_inv, sizeof(a.lat_inv));
     TRY(launch_matern_pw(ctx, sc, NA, m->use_E, a, slot));
   }
   return MBG_OK;
@@ -829,6 +854,8 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
 static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
                    int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
                    mbg_job_stats* stats, int* deferred_slot = nullptr) {
+  if (m->use_lat)
+    return fail(MBG_ERR_UNSUPPORTED, "models carrying a lattice run on the MBG_CONTRACT_DMMA / AUTO kernel only");
   const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
   long long n_cand_shard = 0, n_enum = 0, n_acc = 0;
   const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads;
@@ -1376,6 +1403,14 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   m->sig = d->sig, m->c = d->c, m->std = d->std;
   m->use_E = d->alphas_E != nullptr;
   auto cleanup = [&]() { mbg_model_destroy(m); };
+  if (d->lattice) {
+    m->use_lat = true;
+    memcpy(m->lat, d->lattice, 9 * sizeof(double));
+    if (!hostmath::inverse3(m->lat, m->lat_inv)) {
+      cleanup();
+      return fail(MBG_ERR_ARG, "model lattice is singular");
+    }
+  }
   if (cudaMalloc(&m->XA, xa.size() * sizeof(double2)) != cudaSuccess ||
       cudaMalloc(&m->iperm, iperm.size() * sizeof(int)) != cudaSuccess ||
       cudaMalloc(&m->perm, fperm.size() * sizeof(int)) != cudaSuccess) {
@@ -1777,6 +1812,33 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(values, ctx->outE.p, (size_t)n_R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MBG_OK;
+}
+
+int mbg_from_r(mbg_context_t ctx, int32_t n_atoms, const double* lattice, const double* R, int64_t n_R, double* x, double* J) {
+  if (!ctx || !R || !x || !J) return fail(MBG_ERR_ARG, "NULL argument");
+  if (n_atoms < 2 || n_R < 0) return fail(MBG_ERR_ARG, "bad sizes");
+  if (n_R == 0) return MBG_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CellDev lat;
+  memset(&lat, 0, sizeof(lat));
+  if (lattice) {
+    memcpy(lat.cell, lattice, 9 * sizeof(double));
+    if (!hostmath::inverse3(lat.cell, lat.cell_inv)) return fail(MBG_ERR_ARG, "lattice is singular");
+  }
+  const long long D = (long long)n_atoms * (n_atoms - 1) / 2, nt = n_R * D;
+  const size_t nR = (size_t)n_R * n_atoms * 3;
+  TRY(ctx->R.ensure(nR * sizeof(double)));
+  TRY(ctx->outE.ensure((size_t)nt * sizeof(double)));
+  TRY(ctx->outF.ensure((size_t)nt * 3 * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->R.p, R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_from_r<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(n_atoms, lattice ? 1 : 0, lat, ctx->R.as<double>(), n_R,
+                                                                ctx->outE.as<double>(), ctx->outF.as<double>());
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(x, ctx->outE.p, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(J, ctx->outF.p, (size_t)nt * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MBG_OK;
 }

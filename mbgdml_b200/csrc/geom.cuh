@@ -67,6 +67,18 @@ __device__ __noinline__ void mic_general(const CellDev& s, const double v[3], do
       }
 }
 
+// _gdml/desc.py:42-76 (_pbc_diff): clamp a pair difference to the lattice a MODEL carries (sGDML periodic descriptors;
+// lattice vectors as columns): d -= lat . around(lat_inv . d).  np.around rounds half to even, as rint does.
+__device__ __forceinline__ void pbc_diff(const double* __restrict__ lat, const double* __restrict__ lat_inv, double d[3]) {
+  double c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = rint(lat_inv[3 * i] * d[0] + lat_inv[3 * i + 1] * d[1] + lat_inv[3 * i + 2] * d[2]);
+  const double s0 = lat[0] * c[0] + lat[1] * c[1] + lat[2] * c[2];
+  const double s1 = lat[3] * c[0] + lat[4] * c[1] + lat[5] * c[2];
+  const double s2 = lat[6] * c[0] + lat[7] * c[1] + lat[8] * c[2];
+  d[0] -= s0, d[1] -= s1, d[2] -= s2;
+}
+
 // Decode candidate -> entity tuple.  Returns false when the tuple is not strictly ascending
 // (utils.gen_combs drops it, utils.py:479-488).  Explicit tuples are taken as given.
 __device__ __forceinline__ bool decode_tuple(const JobDev& j, long long cand, int ent[kMaxOrder]) {

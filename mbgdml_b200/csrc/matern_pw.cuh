@@ -59,6 +59,8 @@ struct MaternPwArgs {
   double* F;
   double* virial;
   unsigned int* work_counters;  // [kPwMaxSlices], zero before the launch: dynamic work counter per row slice
+  int use_lat;                  // the model carries its own lattice: pair differences are clamped (_gdml/desc.py:42-76)
+  double lat[9], lat_inv[9];
 #ifdef PW_PROFILE
   long long* prof;  // harness only: [gridDim.x][NW][8] clock64 totals per warp
 #endif
@@ -96,7 +98,7 @@ __host__ __device__ constexpr size_t pw_smem_bytes(int P, int nw) {
   constexpr int D = NA * (NA - 1) / 2;
   return (size_t)kPwStages * mma_tile_doubles(NA) * 8 + (size_t)kMmaExpTable * 8 + (kPwStages + 1) * 8 +
          (size_t)(NW + 4) * 4 + 8 + (size_t)(D + 1) * 8 + (size_t)pw_perm_doubles(NA, P) * 8 +
-         (size_t)nw * pw_warp_doubles<NA, MT, YS>(P) * 8 + 64;
+         (size_t)nw * pw_warp_doubles<NA, MT, YS>(P) * 8 + sizeof(CellDev) + 64;
 }
 
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -168,7 +170,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   double* mus = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(progress + NW + 1) + 7 & ~(uintptr_t)7);  // [D + 1]
   unsigned char* perm_s = reinterpret_cast<unsigned char*>(mus + D + 1 + ((D + 1) & 1));  // pi [P][D], pi^-1 [P][D] (bytes)
   const int perm_dbl = pw_perm_doubles(NA, P);
-  double* wbase = reinterpret_cast<double*>(perm_s) + perm_dbl;
+  CellDev* cell_s = reinterpret_cast<CellDev*>(reinterpret_cast<double*>(perm_s) + perm_dbl);  // the cell, when all frames share one
+  double* wbase = reinterpret_cast<double*>(cell_s) + sizeof(CellDev) / 8;
   // permutation tables: shared-memory copies when they fit (the prologue / epilogue of every item walk them with
   // dependent loads; from global memory that latency is what a warp's fixed cost per item mostly consists of)
   auto fperm_at = [&](const int idx) -> int { return perm_dbl ? (int)perm_s[idx] : a.perm[idx]; };
@@ -188,6 +191,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int k = tid; k < D; k += nw * 32) mus[k] = a.mu[k];
+  if (a.sys.periodic && a.sys.cell_stride == 0)
+    for (int k = tid; k < (int)(sizeof(CellDev) / 8); k += nw * 32)
+      reinterpret_cast<double*>(cell_s)[k] = reinterpret_cast<const double*>(a.sys.cells)[k];
   if (perm_dbl)
     for (int k = tid; k < P * D; k += nw * 32) perm_s[k] = (unsigned char)a.perm[k], perm_s[P * D + k] = (unsigned char)a.iperm[k];
   __syncthreads();  // the only CTA-wide barrier of the kernel
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       if (a.sys.periodic) {
         const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
         const double d[3] = {__dsub_rn(v[0], pf[0]), __dsub_rn(v[1], pf[1]), __dsub_rn(v[2], pf[2])};
-        const CellDev& cl = cell_of(a.sys, a.rec_frame[frag]);
+        const CellDev& cl = a.sys.cell_stride ? cell_of(a.sys, a.rec_frame[frag]) : *cell_s;
         if (!(mic_naive(cl, d, v) < cl.half_min_len)) bad[fl] = 1;
       }
       rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
         const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
         const double d[3] = {__dsub_rn(p[0], pf[0]), __dsub_rn(p[1], pf[1]), __dsub_rn(p[2], pf[2])};
         double v[3];
-        mic_general(cell_of(a.sys, a.rec_frame[frag]), d, v);
+        mic_general(a.sys.cell_stride ? cell_of(a.sys, a.rec_frame[frag]) : *cell_s, d, v);
         rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
       }
       __syncwarp();
@@ -337,7 +343,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       const int j = k - i * (i - 1) / 2;
       const double* ri = rs + (fl * NA + i) * 3;
       const double* rj = rs + (fl * NA + j) * 3;
-      xs[idx] = __ddiv_rn(1.0, norm3_rn(__dsub_rn(ri[0], rj[0]), __dsub_rn(ri[1], rj[1]), __dsub_rn(ri[2], rj[2])));
+      double dv[3] = {__dsub_rn(ri[0], rj[0]), __dsub_rn(ri[1], rj[1]), __dsub_rn(ri[2], rj[2])};
+      if (a.use_lat) pbc_diff(a.lat, a.lat_inv, dv);
+      xs[idx] = __ddiv_rn(1.0, norm3_rn(dv[0], dv[1], dv[2]));
     }
     __syncwarp();
 
@@ -658,7 +666,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
           if (bb == m) continue;
           const int i = bb > m ? bb : m, j = bb > m ? m : bb;
           const double inv = xf[i * (i - 1) / 2 + j];
-          f = fma((rf[bb * 3 + c] - rf[m * 3 + c]) * (inv * inv * inv), Fdf[i * (i - 1) / 2 + j], f);
+          double dc = rf[bb * 3 + c] - rf[m * 3 + c];
+          if (a.use_lat) {
+            double dv[3] = {rf[bb * 3] - rf[m * 3], rf[bb * 3 + 1] - rf[m * 3 + 1], rf[bb * 3 + 2] - rf[m * 3 + 2]};
+            pbc_diff(a.lat, a.lat_inv, dv);
+            dc = dv[c];
+          }
+          f = fma(dc * (inv * inv * inv), Fdf[i * (i - 1) / 2 + j], f);
         }
         f *= a.std * lam;
         double* dst =
@@ -684,7 +698,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
             if (bb == m) continue;
             const int i = bb > m ? bb : m, j = bb > m ? m : bb;
             const double inv = xf[i * (i - 1) / 2 + j];
-            f = fma((rf[bb * 3 + vj] - rf[m * 3 + vj]) * (inv * inv * inv), Fdf[i * (i - 1) / 2 + j], f);
+            double dc = rf[bb * 3 + vj] - rf[m * 3 + vj];
+            if (a.use_lat) {
+              double dv[3] = {rf[bb * 3] - rf[m * 3], rf[bb * 3 + 1] - rf[m * 3 + 1], rf[bb * 3 + 2] - rf[m * 3 + 2]};
+              pbc_diff(a.lat, a.lat_inv, dv);
+              dc = dv[vj];
+            }
+            f = fma(dc * (inv * inv * inv), Fdf[i * (i - 1) / 2 + j], f);
           }
           wv = fma(rf[m * 3 + vi], f, wv);
         }

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import itertools
 
 import numpy as np
@@ -9,6 +10,16 @@ import numpy as np
 from . import _native
 
 _uid = itertools.count()
+
+
+def _from_r(r, lat_and_inv=None):
+    """Descriptor and (compressed) Jacobian of one geometry, evaluated on the GPU (``mbg_from_r``): the callable the
+    reference stores as ``gdmlModel.desc_func`` (gdml_model.py:95, _gdml/desc.py:203-233).  ``r`` is the flattened
+    (3N,) geometry; ``lat_and_inv`` the model's (lattice, inverse) pair or None."""
+    r = np.asarray(r, dtype=np.float64).reshape(1, -1, 3)
+    lattice = None if lat_and_inv is None else lat_and_inv[0]
+    x, J = _native.get_context().from_r(r, lattice)
+    return x, J[0]
 
 
 class Model:
@@ -52,16 +63,69 @@ class gdmlModel(Model):  # pylint: disable=invalid-name
         model = self.model_dict
         self.sig = model["sig"]
         self.n_atoms = self.Z.shape[0]
-        if "lattice" in model:
-            raise NotImplementedError("models carrying their own `lattice` (sGDML periodic descriptors, "
-                                      "desc.py:42-76) have no device implementation; use periodic.Cell")
-        self.lat_and_inv = None
+        self.desc_func = _from_r
+        # model["lattice"] (vectors as columns): the kernels clamp pair differences to it (_gdml/desc.py:42-76)
+        self.lat_and_inv = ((np.asarray(model["lattice"], dtype=np.float64), np.linalg.inv(model["lattice"]))
+                            if "lattice" in model else None)
         self.n_train = model["R_desc"].shape[1]
         self.stdev = model["std"] if "std" in model else 1.0
         self.integ_c = model["c"]
         self.n_perms = model["perms"].shape[0]
         self.tril_perms_lin = model["tril_perms_lin"]
         self.alphas_E = model["alphas_E"] if "alphas_E" in model.keys() else None
+        self.use_torch = False
+        self._perm_cache = {}
+
+    # The reference expands the training set under every permutation at load time (gdml_model.py:109-125: two
+    # (T P, D) arrays, 27.6 MB for a water trimer model).  The kernels never need them -- they permute the query --
+    # so here they are built only if a foreign predictor asks (pure indexing, no arithmetic), then cached.
+    def _expanded(self, key):
+        if key not in self._perm_cache:
+            src = self.model_dict["R_desc"].T if key == "R_desc" else self.model_dict["R_d_desc_alpha"]
+            self._perm_cache[key] = (
+                np.tile(src, self.n_perms)[:, self.tril_perms_lin]
+                .reshape(self.n_train, self.n_perms, -1, order="F")
+                .reshape(self.n_train * self.n_perms, -1))
+        return self._perm_cache[key]
+
+    @property
+    def R_desc_perms(self):
+        return self._expanded("R_desc")
+
+    @property
+    def R_d_desc_alpha_perms(self):
+        return self._expanded("R_d_desc_alpha")
+
+    @property
+    def alphas_E_lin(self):
+        if self.alphas_E is None:
+            return None
+        return np.tile(np.asarray(self.alphas_E)[:, None], (1, self.n_perms)).ravel()
+
+    @property
+    def code_version(self):
+        if hasattr(self, "model_dict"):
+            return self.model_dict["code_version"].item()
+        raise AttributeError("No model is loaded.")
+
+    @property
+    def md5(self):
+        """MD5 of the model (gdml_model.py:141-163 + utils.md5_data: the attributes present among md5_train, Z, R_desc,
+        R_d_desc_alpha, sig, alphas_F, digested in sorted key order)."""
+        keys = sorted(k for k in ("md5_train", "Z", "R_desc", "R_d_desc_alpha", "sig", "alphas_F") if hasattr(self, k))
+        md5_hash = hashlib.md5()
+        for key in keys:
+            d = getattr(self, key)
+            if isinstance(d, np.ndarray):
+                d = d.ravel()
+            md5_hash.update(hashlib.md5(d).digest())
+        return md5_hash.hexdigest()
+
+    def add_modifications(self, dset):
+        """gdml_model.py:165-179: transfer entity_ids / comp_ids of a data set into the model dict."""
+        for key in ("entity_ids", "comp_ids"):
+            self.model_dict[key] = dset[key]
+        self.model_dict["md5"] = np.array(self.md5)
 
     # -- device side --------------------------------------------------------------------
     def _criteria_key(self):
@@ -87,6 +151,7 @@ class gdmlModel(Model):  # pylint: disable=invalid-name
             if R_desc.shape != (dim_d, T) or RdA.shape != (T, dim_d) or tpl.shape != (P * dim_d,):
                 raise ValueError("model arrays have inconsistent shapes")
             aE = _native.as_f64(self.alphas_E) if self.alphas_E is not None else None
+            lat = _native.as_f64(self.lat_and_inv[0]).reshape(9) if self.lat_and_inv is not None else None
             if self.criteria is None:
                 kind, bound, lo, hi, eids = _native.CRIT_NONE, _native.BOUND_UPPER, 0.0, 0.0, None
             else:
@@ -97,9 +162,9 @@ class gdmlModel(Model):  # pylint: disable=invalid-name
                 R_desc=_native.ptr(R_desc, _native._dp), R_d_desc_alpha=_native.ptr(RdA, _native._dp),
                 tril_perms_lin=_native.ptr(tpl, _native._lp), alphas_E=_native.ptr(aE, _native._dp),
                 criteria_kind=kind, criteria_bound=bound, criteria_lo=lo, criteria_hi=hi,
-                criteria_entity_ids=_native.ptr(eids, _native._ip),
+                criteria_entity_ids=_native.ptr(eids, _native._ip), lattice=_native.ptr(lat, _native._dp),
             )
-            return d, (R_desc, RdA, tpl, aE, eids)
+            return d, (R_desc, RdA, tpl, aE, eids, lat)
 
         return ctx.model_handle(key, build)
 

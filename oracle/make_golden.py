@@ -40,7 +40,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 os.makedirs(GOLD, exist_ok=True)
 
 MODEL_KEYS = ["z", "sig", "R_desc", "R_d_desc_alpha", "c", "std", "perms", "tril_perms_lin", "comp_ids",
-              "entity_ids", "alphas_E"]
+              "entity_ids", "alphas_E", "lattice"]
 
 
 def relerr(a, b):
@@ -483,8 +483,45 @@ def case_train_kernel():
     np.savez_compressed(os.path.join(GOLD, "train_kernel.npz"), **out)
 
 
+def case_lattice():
+    """Models that carry their own `lattice` (sGDML periodic descriptors): _from_r with _pbc_diff (desc.py:42-76) and
+    predict_gdml through it, cubic and triclinic lattices, fragments that straddle the lattice boundary."""
+    out = {}
+    lattices = {"cub": np.eye(3) * 7.5, "tri": np.array([[7.9, 1.1, -0.6], [0.0, 7.2, 0.9], [0.0, 0.0, 8.4]])}  # columns
+    for tag, lat in lattices.items():
+        mds = []
+        for k, comps in enumerate((["h2o"], ["h2o", "h2o"], ["h2o", "h2o", "h2o"])):
+            md = syn.make_model(comps, n_train=40, sig=(10.0, 80.0, 300.0)[k], seed=31 + k, c=0.5 * k - 1.0, std=1.0 + 0.25 * k)
+            md["lattice"] = lat.copy()
+            mds.append(md)
+        rng = np.random.default_rng(9)
+        Z, R0, eids, cids = syn.make_cluster(5, seed=4, spacing=2.9)
+        # move whole molecules by lattice vectors (columns of lat) so that pair differences need the clamp
+        shifts = rng.integers(-1, 2, size=(5, 3)) @ lat.T
+        R = np.array([R0 + np.repeat(shifts, 3, axis=0), R0 + rng.normal(scale=0.04, size=R0.shape)])
+        rms = [gdmlModel(dict(md)) for md in mds]
+        oms = [orc.Model(dict(md)) for md in mds]
+        ref = mbePredict(rms, predict_gdml).predict(Z, R, eids, cids)
+        got = orc.mbe_predict(oms, Z, R, eids, cids)
+        check(f"lattice {tag} E", got[0], ref[0]); check(f"lattice {tag} F", got[1], ref[1])
+        # clamped geometry reproduces the un-shifted one's energy (the lattice makes them equivalent)
+        plain = mbePredict(rms, predict_gdml).predict(Z, R0[None], eids, cids)
+        assert relerr(ref[0][:1], plain[0]) <= 1e-10
+        frag = R[0][:9]
+        x, J = _from_r(frag.flatten(), rms[2].lat_and_inv)
+        xo, Jo = orc.from_r(frag.flatten(), oms[2].lat_and_inv)
+        check(f"lattice {tag} from_r x", xo, x.ravel(), 1e-14); check(f"lattice {tag} from_r J", Jo, J, 1e-13)
+        out.update(pack_models(f"{tag}_m", mds))
+        out.update({f"{tag}_Z": Z, f"{tag}_R": R, f"{tag}_eids": eids, f"{tag}_cids": cids, f"{tag}_E": ref[0],
+                    f"{tag}_F": ref[1], f"{tag}_frag": frag, f"{tag}_x": x.ravel(), f"{tag}_J": J, f"{tag}_lat": lat})
+    np.savez_compressed(os.path.join(GOLD, "lattice_model.npz"), **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="raise", under="ignore")
+    if "--only-lattice" in sys.argv:
+        print("lattice models"); case_lattice()
+        sys.exit(0)
     print("gen_combs"); case_gen_combs()
     print("fragment kernel"); case_desc_and_kernel()
     print("cluster"); case_cluster()
@@ -493,5 +530,6 @@ if __name__ == "__main__":
     print("reference fixtures"); case_reference_fixtures()
     print("mbe_contrib"); case_mbe_contrib()
     print("train kernel"); case_train_kernel()
+    print("lattice models"); case_lattice()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden fixtures written: %.1f KB" % (total / 1024))
