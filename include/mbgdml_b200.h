@@ -222,6 +222,12 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
 int mbg_r_mic(mbg_context_t ctx, const double *cell, double cutoff, const double *r, int32_t n,
               double *out, int32_t *accepted);
 
+/* Cell.d_mic (periodic.py:61-84) on device: minimum image of n displacement vectors d[n][3] -> out[n][3]; with
+ * check_cutoff, *accepted = 0 when any pair distance among the imaged vectors is >= cutoff (the reference returns
+ * None); without it *accepted = 1. */
+int mbg_d_mic(mbg_context_t ctx, const double *cell, double cutoff, const double *d, int32_t n, int32_t check_cutoff,
+              double *out, int32_t *accepted);
+
 /* mbe_worker + the add/remove step of mbe_contrib (mbe.py:73-197, 381-427), used by decomp_to_total
  * (mbe.py:432-508): for each selected reference structure i (row ref_rows[i] of E[n_total] /
  * Deriv[n_total][n_atoms_ref][3], updated in place) the pairs [pair_offsets[i], pair_offsets[i+1]) name the

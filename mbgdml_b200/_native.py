@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_step_create", "mbg_step_run",
     "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
-    "mbg_from_r", "mbg_criteria_eval", "mbg_r_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
+    "mbg_from_r", "mbg_criteria_eval", "mbg_r_mic", "mbg_d_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
     "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
 ]
 
@@ -115,6 +115,7 @@ def load_library():
         lib.mbg_from_r.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp]
         lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
         lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
+        lib.mbg_d_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, C.c_int32, _dp, _ip]
         lib.mbg_mbe_accumulate.argtypes = [C.c_void_p, C.c_int64, _lp, _lp, _lp, _ip, C.c_int32, C.c_int32, _ip, _ip,
                                            C.c_int32, _ip, _ip, _dp, _dp, C.c_int64, C.c_double, _dp, _dp, C.c_int64]
         lib.mbg_kernel_mat.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _lp, C.c_double, C.c_int32,
@@ -345,6 +346,15 @@ class Context:
         check(self.lib.mbg_mat52_rows(self.handle, rows.shape[1], ptr(q, _dp), q.shape[0], float(sig), ptr(rows, _dp),
                                       rows.shape[0], ptr(out, _dp)))
         return out
+
+    def d_mic(self, cell, cutoff, d, check_cutoff=True):
+        d = as_f64(d)
+        cell = as_f64(cell).reshape(9)
+        out = np.zeros_like(d)
+        acc = C.c_int32(0)
+        check(self.lib.mbg_d_mic(self.handle, ptr(cell, _dp), float(cutoff), ptr(d, _dp), d.shape[0], int(bool(check_cutoff)),
+                                 ptr(out, _dp), C.byref(acc)))
+        return out, bool(acc.value)
 
     def r_mic(self, cell, cutoff, r):
         r = as_f64(r)

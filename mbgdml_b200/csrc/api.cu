@@ -534,6 +534,34 @@ __global__ void k_from_r(int n, int use_lat, CellDev lat /* .cell = lattice, .ce
   J[t * 3] = d[0] / d3, J[t * 3 + 1] = d[1] / d3, J[t * 3 + 2] = d[2] / d3;
 }
 
+// Cell.d_mic (periodic.py:61-84): minimum image of n displacement vectors; the cut-off test runs over the pair
+// distances of the vectors themselves (pdist(d_periodic)), not against an origin atom.
+__global__ void k_d_mic(CellDev s, const double* d_in, int n, int check_cutoff, double* out, int* accepted) {
+  if (threadIdx.x || blockIdx.x) return;
+  bool naive_ok = true;
+  for (int a = 0; a < n; ++a) {
+    const double d[3] = {d_in[3 * a], d_in[3 * a + 1], d_in[3 * a + 2]};
+    double v[3];
+    naive_ok = (mic_naive(s, d, v) < s.half_min_len) && naive_ok;
+    out[3 * a] = v[0], out[3 * a + 1] = v[1], out[3 * a + 2] = v[2];
+  }
+  if (!naive_ok)
+    for (int a = 0; a < n; ++a) {
+      const double d[3] = {d_in[3 * a], d_in[3 * a + 1], d_in[3 * a + 2]};
+      double v[3];
+      mic_general(s, d, v);
+      out[3 * a] = v[0], out[3 * a + 1] = v[1], out[3 * a + 2] = v[2];
+    }
+  int ok = 1;
+  if (check_cutoff)
+    for (int i = 0; i < n; ++i)
+      for (int k = i + 1; k < n; ++k)
+        if (norm3_rn(__dsub_rn(out[3 * i], out[3 * k]), __dsub_rn(out[3 * i + 1], out[3 * k + 1]),
+                     __dsub_rn(out[3 * i + 2], out[3 * k + 2])) >= s.cutoff)
+          ok = 0;
+  *accepted = ok;
+}
+
 __global__ void k_r_mic(CellDev s, const double* r, int n, double* out, int* accepted) {
   if (threadIdx.x || blockIdx.x) return;
   bool naive_ok = true;
@@ -1240,6 +1268,8 @@ extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells,
 // ------------------------------------------------------------------------------------
 // exported functions
 // ------------------------------------------------------------------------------------
+static int context_init(mbg_context_t ctx, int device, int sm_count);
+
 extern "C" {
 
 const char* mbg_last_error(void) { return g_last_error.c_str(); }
@@ -1263,8 +1293,18 @@ int mbg_context_create(int device, mbg_context_t* out) {
     return fail(MBG_ERR_UNSUPPORTED, "this build targets sm_100a (B200); device %d is sm_%d%d", device, prop.major,
                 prop.minor);
   mbg_context_t ctx = new mbg_context_s();
+  const int rc = context_init(ctx, device, prop.multiProcessorCount);
+  if (rc != MBG_OK) {
+    mbg_context_destroy(ctx);  // releases whatever was allocated before the failure
+    return rc;
+  }
+  *out = ctx;
+  return MBG_OK;
+}
+
+static int context_init(mbg_context_t ctx, int device, int sm_count) {
   ctx->device = device;
-  ctx->sm_count = prop.multiProcessorCount;
+  ctx->sm_count = sm_count;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   CUDA_TRY(cudaMallocHost(&ctx->h_totals, (2 + 2 * kMaxDeferred) * sizeof(long long)));
@@ -1288,25 +1328,24 @@ int mbg_context_create(int device, mbg_context_t* out) {
     if (!strcmp(v, "dmma_wave")) ctx->contraction = MBG_CONTRACT_DMMA_WAVE;
   }
   if (const char* v = getenv("MBG_MMA_CFG")) ctx->mma_cfg = atoi(v);
-  *out = ctx;
   return MBG_OK;
 }
 
 int mbg_context_destroy(mbg_context_t ctx) {
   if (!ctx) return MBG_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->tab.release();
   ctx->scr.release();
   for (DevBuf* b : {&ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->totals, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
                     &ctx->deferred_totals, &ctx->km_ints, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-  cudaEventDestroy(ctx->ev_call0);
-  cudaEventDestroy(ctx->ev_call1);
-  cudaFreeHost(ctx->h_totals);
-  cudaFreeHost(ctx->h_chunk);
-  cudaStreamDestroy(ctx->own_stream);
+  if (ctx->ev_call0) cudaEventDestroy(ctx->ev_call0);
+  if (ctx->ev_call1) cudaEventDestroy(ctx->ev_call1);
+  if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+  if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return MBG_OK;
 }
@@ -1403,6 +1442,14 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   m->sig = d->sig, m->c = d->c, m->std = d->std;
   m->use_E = d->alphas_E != nullptr;
   auto cleanup = [&]() { mbg_model_destroy(m); };
+#define MODEL_TRY(expr)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      cleanup();                                                                                          \
+      return fail(MBG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                                     \
+  } while (0)
   if (d->lattice) {
     m->use_lat = true;
     memcpy(m->lat, d->lattice, 9 * sizeof(double));
@@ -1417,9 +1464,9 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
     cleanup();
     return fail(MBG_ERR_NOMEM, "cudaMalloc for model failed");
   }
-  CUDA_TRY(cudaMemcpy(m->XA, xa.data(), xa.size() * sizeof(double2), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(m->iperm, iperm.data(), iperm.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(m->perm, fperm.data(), fperm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  MODEL_TRY(cudaMemcpy(m->XA, xa.data(), xa.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  MODEL_TRY(cudaMemcpy(m->iperm, iperm.data(), iperm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  MODEL_TRY(cudaMemcpy(m->perm, fperm.data(), fperm.size() * sizeof(int), cudaMemcpyHostToDevice));
   {
     // DMMA layout (matern_mma.cuh): centred descriptors, A scaled by 5/sig, per-row -|X'|^2/2 and -X'.A_s,
     // packed per tile of 64 rows; side arrays in column order (column j of a block <-> row tau(j)).
@@ -1457,8 +1504,8 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
       cleanup();
       return fail(MBG_ERR_NOMEM, "cudaMalloc for model failed");
     }
-    CUDA_TRY(cudaMemcpy(m->tiles_mma, tl.data(), tl.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(m->mu, mu.data(), (size_t)D * sizeof(double), cudaMemcpyHostToDevice));
+    MODEL_TRY(cudaMemcpy(m->tiles_mma, tl.data(), tl.size() * sizeof(double), cudaMemcpyHostToDevice));
+    MODEL_TRY(cudaMemcpy(m->mu, mu.data(), (size_t)D * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (m->use_E) {
     std::vector<double> aE(T_pad, 0.0);
@@ -1467,7 +1514,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
       cleanup();
       return fail(MBG_ERR_NOMEM, "cudaMalloc for model failed");
     }
-    CUDA_TRY(cudaMemcpy(m->alphaE, aE.data(), aE.size() * sizeof(double), cudaMemcpyHostToDevice));
+    MODEL_TRY(cudaMemcpy(m->alphaE, aE.data(), aE.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   // criteria
   CritDev& c = m->crit;
@@ -1493,6 +1540,7 @@ int mbg_model_create(mbg_context_t ctx, const mbg_model_desc* d, mbg_model_t* ou
   }
   *out = m;
   return MBG_OK;
+#undef MODEL_TRY
 }
 
 int mbg_model_destroy(mbg_model_t m) {
@@ -1813,6 +1861,27 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(values, ctx->outE.p, (size_t)n_R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MBG_OK;
+}
+
+int mbg_d_mic(mbg_context_t ctx, const double* cell, double cutoff, const double* d, int32_t n, int32_t check_cutoff,
+              double* out, int32_t* accepted) {
+  if (!ctx || !cell || !d || !out || !accepted) return fail(MBG_ERR_ARG, "NULL argument");
+  if (n < 1) return fail(MBG_ERR_ARG, "n < 1");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CellDev s;
+  TRY(fill_cell(s, cell, cutoff));
+  TRY(ctx->R.ensure((size_t)n * 3 * sizeof(double)));
+  TRY(ctx->outF.ensure((size_t)n * 3 * sizeof(double)));
+  TRY(ctx->totals.ensure(2 * sizeof(long long)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->R.p, d, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_d_mic<<<1, 32, 0, ctx->stream>>>(s, ctx->R.as<double>(), n, check_cutoff ? 1 : 0, ctx->outF.as<double>(), ctx->totals.as<int>());
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, ctx->outF.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *accepted = *reinterpret_cast<int*>(ctx->h_totals);
   return MBG_OK;
 }
 

@@ -4,6 +4,7 @@ from __future__ import annotations
 import ctypes as C
 import hashlib
 import itertools
+import weakref
 
 import numpy as np
 
@@ -166,6 +167,8 @@ class gdmlModel(Model):  # pylint: disable=invalid-name
             )
             return d, (R_desc, RdA, tpl, aE, eids, lat)
 
+        if key not in ctx._models:  # the device copy goes away with this object
+            weakref.finalize(self, ctx.drop_model, key)
         return ctx.model_handle(key, build)
 
     def save(self, path):

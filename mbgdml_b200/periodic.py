@@ -49,10 +49,12 @@ class Cell:
         return out if ok else None
 
     def d_mic(self, d, check_cutoff=True):
-        """periodic.py:61-84 for distance vectors ``d`` taken relative to a first atom at the origin."""
+        """periodic.py:61-84: minimum image of the vectors ``d``; with ``check_cutoff`` ``None`` when any pair distance
+        among the imaged vectors is >= cutoff."""
         d = np.asarray(d, dtype=np.float64)
+        assert d.ndim == 2
         cell, cutoff = self.native_cell()
-        out, ok = _native.get_context().r_mic(cell, cutoff, np.vstack((np.zeros((1, 3)), d)))
+        out, ok = _native.get_context().d_mic(cell, cutoff, d, check_cutoff=check_cutoff)
         if check_cutoff and not ok:
             return None
-        return out[1:]
+        return out

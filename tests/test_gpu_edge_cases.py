@@ -95,3 +95,22 @@ def test_tail_split_launch_shape():
     assert pred.last_stats[0][2] == 969
     Eo, Fo = orc.mbe_predict(oracle_models([md], [None]), Z, R, eids, cids)
     assert relerr(E, Eo) <= TOL and relerr(F, Fo) <= TOL
+
+
+def test_d_mic_operator_matches_reference_semantics():
+    """Cell.d_mic (periodic.py:61-84): the cut-off test runs over the pair distances of the imaged vectors only -- two
+    vectors longer than the cut-off but close to each other are accepted, and check_cutoff=False always returns them."""
+    from oracle import mbgdml_oracle as orc
+
+    rng = np.random.default_rng(0)
+    for cell_v in (np.eye(3) * 14.0, np.array([[12.6, 0.0, 0.0], [2.8, 12.1, 0.0], [-1.9, 3.1, 11.8]])):
+        cell, ocell = mb.Cell(cell_v, cutoff=5.0, pbc=True), orc.Cell(cell_v, cutoff=5.0)
+        far_but_close = np.array([[6.0, 0.5, 0.2], [6.3, 0.1, -0.4]])  # |d| > cutoff, |d0 - d1| < cutoff
+        for d in (far_but_close, far_but_close + cell_v[0] - 2 * cell_v[2], rng.uniform(-20, 20, (4, 3)), rng.uniform(-2, 2, (3, 3))):
+            got, want = cell.d_mic(d), ocell.d_mic(d)
+            assert (got is None) == (want is None)
+            if want is not None:
+                assert np.abs(got - want).max() <= 1e-12
+            free = cell.d_mic(d, check_cutoff=False)
+            assert np.abs(free - ocell.d_mic(d, check_cutoff=False)).max() <= 1e-12
+        assert cell.d_mic(far_but_close) is not None
