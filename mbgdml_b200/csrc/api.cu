@@ -1268,9 +1268,9 @@ extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells,
 // ------------------------------------------------------------------------------------
 // exported functions
 // ------------------------------------------------------------------------------------
-static int context_init(mbg_context_t ctx, int device, int sm_count);
-
 extern "C" {
+
+static int context_init(mbg_context_t ctx, int device, int sm_count);
 
 const char* mbg_last_error(void) { return g_last_error.c_str(); }
 int mbg_abi_version(void) { return MBG_ABI_VERSION; }
