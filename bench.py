@@ -246,7 +246,7 @@ def cpu_sample_size(w):
     return {"box140": 200000, "trimers64": 6000, "monomers": 100000, "mixed140": 60000}[w["name"]]
 
 
-def ncu_traffic(workload, n_frag_atoms, frames, use_dmma):
+def ncu_traffic(workload, n_frag_atoms, frames, contraction):
     """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
     committed `ncu --set full` capture of the same command (profiles/ncu_traffic.json): a STATIC figure that names
     the capture it came from -- (bytes, source) or (None, None)."""
@@ -256,7 +256,7 @@ def ncu_traffic(workload, n_frag_atoms, frames, use_dmma):
         return None, None
     for row in table:
         if (row["workload"] == workload and row["n_frag_atoms"] == n_frag_atoms and row["frames"] == frames
-                and row["contraction"] == ("dmma" if use_dmma else "fma")):
+                and row["contraction"] == contraction):
             return row["dram_bytes_per_launch"], "static: " + row.get("source", "ncu --set full capture, profiles/")
     return None, None
 
@@ -487,7 +487,8 @@ def run_gpu_arm(args):
         achieved = flop / (ms * 1e-3) / 1e12
         kname = (f"k_matern_pw<NA={best['n_frag_atoms']}>" if args.contraction in ("auto", "dmma") else
                  f"k_matern_mma<NA={best['n_frag_atoms']}>" if use_dmma else f"k_matern<NA={best['n_frag_atoms']}>")
-        traffic, traffic_source = ncu_traffic(args.workload, best["n_frag_atoms"], args.frames, use_dmma)
+        traffic, traffic_source = ncu_traffic(args.workload, best["n_frag_atoms"], args.frames,
+                                              {"auto": "dmma"}.get(args.contraction, args.contraction))
         roofline = {
             "bound": "tensor" if use_dmma else "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops if peak_tflops else None,
