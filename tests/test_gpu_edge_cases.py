@@ -105,7 +105,7 @@ def test_d_mic_operator_matches_reference_semantics():
     rng = np.random.default_rng(0)
     for cell_v in (np.eye(3) * 14.0, np.array([[12.6, 0.0, 0.0], [2.8, 12.1, 0.0], [-1.9, 3.1, 11.8]])):
         cell, ocell = mb.Cell(cell_v, cutoff=5.0, pbc=True), orc.Cell(cell_v, cutoff=5.0)
-        far_but_close = np.array([[6.0, 0.5, 0.2], [6.3, 0.1, -0.4]])  # |d| > cutoff, |d0 - d1| < cutoff
+        far_but_close = np.array([[6.0, 0.5, 0.2], [6.2, 0.1, -0.4]])  # |d| > cutoff, |d0 - d1| < cutoff (6.3 would tie two images)
         for d in (far_but_close, far_but_close + cell_v[0] - 2 * cell_v[2], rng.uniform(-20, 20, (4, 3)), rng.uniform(-2, 2, (3, 3))):
             got, want = cell.d_mic(d), ocell.d_mic(d)
             assert (got is None) == (want is None)
