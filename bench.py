@@ -393,6 +393,7 @@ def run_gpu_arm(args):
     use_dmma = args.contraction != "fma"
     peak_fma, clk_est = ctx.measure_fp64_peak() if rank == 0 else (0.0, 0.0)
     peak_dmma = ctx.measure_fp64_tensor_peak() if rank == 0 else 0.0
+    exp_sqrt_rate = ctx.measure_exp_sqrt_rate() if rank == 0 else 0.0
     # the roofline of a kernel is the peak of the pipe it runs on
     peak_tflops = peak_dmma if use_dmma else peak_fma
 
@@ -417,6 +418,24 @@ def run_gpu_arm(args):
     acc, enum = acc.cpu().numpy(), enum.cpu().numpy()
     frag_per_step = float(acc.sum())
     value = frag_per_step * args.steps / (ms_dev * 1e-3)
+
+    # the same step replayed from a captured CUDA graph (mbg_step_create / mbg_step_run_device): device-resident in/out
+    graph = None
+    if args.contraction in ("auto", "dmma"):
+        gstep = _engine.make_step(ctx, Z, eids, models, sources(), [pred._scalers_for(m) for m in models], cell, n_frames,
+                                  shard=(rank, world))
+
+        def step_graph():
+            gstep.run_device(R_dev.data_ptr(), buf[:n_frames].data_ptr(), buf[n_frames:].data_ptr())
+            if world > 1:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+
+        for _ in range(3):
+            step_graph()
+        ms_graph, _ = timed(step_graph, args.steps)
+        graph = {"ms_per_step": ms_graph / args.steps, "value": frag_per_step * args.steps / (ms_graph * 1e-3), "unit": UNIT,
+                 "what": "the step of `value` replayed as one CUDA graph launch (tables resident, no host round trip)"}
+        gstep.close()
 
     for _ in range(2):
         step_e2e()
@@ -504,6 +523,13 @@ def run_gpu_arm(args):
             "peak_fp64_fma_tflops": peak_fma, "peak_fp64_tensor_tflops": peak_dmma,
             "frac_of_fma_pipe_peak": achieved / peak_fma if peak_fma else None,
             "contract_share_of_step": sum(r["ms"] for r in recs) / (ms_dev / args.steps),
+            # transcendental side of the same kernel (one exp and one sqrt per (query, training row) pair)
+            "exp_sqrt_per_s": sum(r["n_fragments"] for r in dom) * args.n_train * best["n_perms"] / (ms * 1e-3),
+            "exp_sqrt_rate_measured": exp_sqrt_rate,
+            "exp_sqrt_frac": (sum(r["n_fragments"] for r in dom) * args.n_train * best["n_perms"] / (ms * 1e-3) / exp_sqrt_rate
+                              if exp_sqrt_rate else None),
+            "exp_sqrt_rate_source": "mbg_measure_exp_sqrt_rate: exp(-c sqrt(x)) with the CUDA math library, 4 chains per thread, "
+                                    "CUDA events, measured live",
         }
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -558,7 +584,7 @@ def run_gpu_arm(args):
             "l2": "flushed between steps (256 MiB fill, untimed); model tables are L2-resident by design within a step",
         },
         "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "multi_gpu_check": mg_check,
-        "strong": strong,
+        "strong": strong, "graph": graph,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(R_host.nbytes), "d2h_bytes_per_step": int(8 * n_frames * (1 + 3 * n_atoms))},
         "gpu_launches": int(nl.item()), "clocks": clocks,

@@ -185,9 +185,15 @@ int mbg_predict_decomp(mbg_context_t ctx, const mbg_system_desc *sys, const doub
  *   (stress.py:75-152) reuse one step. */
 typedef struct mbg_step_s *mbg_step_t;
 int mbg_step_create(mbg_context_t ctx, const mbg_system_desc *sys, int32_t n_frames, const mbg_job *jobs,
-                    int32_t n_jobs, uint32_t flags, mbg_step_t *step);
+                    int32_t n_jobs, uint32_t flags, int32_t shard_rank, int32_t shard_count, mbg_step_t *step);
 int mbg_step_run(mbg_step_t step, const double *R, const double *cells, const double *cutoffs, double *E, double *F,
                  double *virial, mbg_job_stats *stats);
+/* The same with R, E, F, virial resident on the device: enqueued on the context's stream, no synchronisation (the
+ * caller orders its own work on that stream; multi-GPU callers all-reduce the partial sums of their shard). */
+int mbg_step_run_device(mbg_step_t step, const double *dR, const double *cells, const double *cutoffs, double *dE,
+                        double *dF, double *dvirial);
+/* Counters of the most recent replay (after the stream has been synchronised). */
+int mbg_step_stats(mbg_step_t step, mbg_job_stats *stats);
 int mbg_step_destroy(mbg_step_t step);
 
 /* The accept decision predict_gdml takes for every candidate fragment before it evaluates the model
@@ -272,6 +278,10 @@ int mbg_measure_fp64_peak(mbg_context_t ctx, double *tflops, double *sm_clock_mh
 /* Measured peak of the FP64 tensor pipe (back-to-back mma.sync.m8n8k4.f64 on independent accumulators),
  * in TFLOP/s: the roofline denominator for the MBG_CONTRACT_DMMA kernel. */
 int mbg_measure_fp64_tensor_peak(mbg_context_t ctx, double *tflops);
+
+/* Measured rate of exp(-c sqrt(x)) evaluated with the CUDA math library (4 independent chains per thread), in
+ * evaluations per second: what the transcendental-bound 1-body workload (BASELINE config 2) is reported against. */
+int mbg_measure_exp_sqrt_rate(mbg_context_t ctx, double *evals_per_s);
 
 #ifdef __cplusplus
 }

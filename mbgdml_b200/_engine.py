@@ -163,7 +163,7 @@ class StepCache:
 
 
 def make_step(ctx, Z, entity_ids, models, comb_sources, scalers_per_model, periodic_cell, n_frames, compute_virial=False,
-              frame_cells=None):
+              frame_cells=None, shard=(0, 1)):
     """mbg_step_create for (system, models, scalers, frame count): see include/mbgdml_b200.h."""
     if frame_cells is not None:
         system = System(Z, entity_ids, None, need_masses=_needs_masses(models), frame_cells=frame_cells)
@@ -173,7 +173,7 @@ def make_step(ctx, Z, entity_ids, models, comb_sources, scalers_per_model, perio
     jobs = (_native.Job * len(models))()
     for k, (m, src, sc) in enumerate(zip(models, comb_sources, scalers_per_model)):
         jobs[k] = make_job(ctx, m, src, sc, keep)
-    return _native.Step(ctx, system.desc, int(n_frames), system.n_atoms, jobs, len(models), bool(compute_virial))
+    return _native.Step(ctx, system.desc, int(n_frames), system.n_atoms, jobs, len(models), bool(compute_virial), shard=shard)
 
 
 def predict_total(ctx, Z, R, entity_ids, models, comb_sources, scalers_per_model, periodic_cell,

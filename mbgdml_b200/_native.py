@@ -28,8 +28,8 @@ EXPORTED_SYMBOLS = [
     "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_step_create", "mbg_step_run",
-    "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
-    "mbg_from_r", "mbg_criteria_eval", "mbg_r_mic", "mbg_d_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak",
+    "mbg_step_run_device", "mbg_step_stats", "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
+    "mbg_from_r", "mbg_criteria_eval", "mbg_r_mic", "mbg_d_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak", "mbg_measure_exp_sqrt_rate",
     "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
 ]
 
@@ -105,7 +105,9 @@ def load_library():
         lib.mbg_predict_decomp.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_void_p, C.POINTER(Job), C.c_uint32,
                                            C.c_void_p, C.c_void_p, C.POINTER(JobStats)]
         lib.mbg_step_create.argtypes = [C.c_void_p, C.POINTER(SystemDesc), C.c_int32, C.POINTER(Job), C.c_int32, C.c_uint32,
-                                        C.POINTER(C.c_void_p)]
+                                        C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.mbg_step_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mbg_step_stats.argtypes = [C.c_void_p, C.POINTER(JobStats)]
         lib.mbg_step_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(JobStats)]
         lib.mbg_step_destroy.argtypes = [C.c_void_p]
@@ -124,6 +126,7 @@ def load_library():
         lib.mbg_mat52_rows.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int64, C.c_double, _dp, C.c_int64, _dp]
         lib.mbg_measure_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
         lib.mbg_measure_fp64_tensor_peak.argtypes = [C.c_void_p, _dp]
+        lib.mbg_measure_exp_sqrt_rate.argtypes = [C.c_void_p, _dp]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(lib, name)
             if name != "mbg_last_error":
@@ -236,6 +239,11 @@ class Context:
         t, f = C.c_double(0), C.c_double(0)
         check(self.lib.mbg_measure_fp64_peak(self.handle, C.byref(t), C.byref(f)))
         return t.value, f.value
+
+    def measure_exp_sqrt_rate(self):
+        t = C.c_double(0)
+        check(self.lib.mbg_measure_exp_sqrt_rate(self.handle, C.byref(t)))
+        return t.value
 
     def measure_fp64_tensor_peak(self):
         t = C.c_double(0)
@@ -369,12 +377,25 @@ class Context:
 class Step:
     """A prepared evaluation (mbg_step_create): tables on the device, the whole pipeline in one CUDA graph."""
 
-    def __init__(self, ctx, system_desc, n_frames, n_atoms, jobs, n_jobs, want_virial):
+    def __init__(self, ctx, system_desc, n_frames, n_atoms, jobs, n_jobs, want_virial, shard=(0, 1)):
         self.ctx, self.n_frames, self.n_atoms, self.n_jobs, self.want_virial = ctx, n_frames, n_atoms, n_jobs, want_virial
         h = C.c_void_p()
         check(ctx.lib.mbg_step_create(ctx.handle, C.byref(system_desc), n_frames, jobs, n_jobs,
-                                      FLAG_VIRIAL if want_virial else 0, C.byref(h)))
+                                      FLAG_VIRIAL if want_virial else 0, int(shard[0]), int(shard[1]), C.byref(h)))
         self.handle = h
+
+    def run_device(self, R_ptr, E_ptr, F_ptr, V_ptr=None, cells=None, cutoffs=None):
+        """Device pointers in and out; enqueued on the context's stream, not synchronised."""
+        cells = as_f64(cells) if cells is not None else None
+        cutoffs = as_f64(cutoffs) if cutoffs is not None else None
+        check(self.ctx.lib.mbg_step_run_device(
+            self.handle, R_ptr, cells.ctypes.data if cells is not None else None,
+            cutoffs.ctypes.data if cutoffs is not None else None, E_ptr, F_ptr, V_ptr))
+
+    def stats(self):
+        st = (JobStats * self.n_jobs)()
+        check(self.ctx.lib.mbg_step_stats(self.handle, st))
+        return [(s_.n_candidates, s_.n_enumerated, s_.n_accepted) for s_ in st]
 
     def run(self, R, cells=None, cutoffs=None):
         R = as_f64(R)

@@ -476,6 +476,20 @@ __global__ void k_dmma_peak(double* out, int iters, double seed) {
   if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
 }
 
+// exp(-c sqrt(x)) with the CUDA math library, 4 independent chains per thread: the "exp . sqrt rate" SURVEY 8(d) asks
+// the descriptor + kernel microbenchmark (config 2, D = 3: transcendental-bound) to be reported against
+__global__ void k_exp_sqrt_rate(double* out, int iters, double seed) {
+  double x[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = seed * 0.1 + k * 0.01 + threadIdx.x * 1e-4;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = exp(-2.23606797749979 * sqrt(x[k]) * 0.01) + 0.25;
+  }
+  const double s = x[0] + x[1] + x[2] + x[3];
+  if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
+}
+
 // generic (runtime-n) geometry kernels for the small API entry points
 __global__ void k_criteria_eval(int kind, int n, const double* masses, const int* group, int n_groups,
                                 const double* R, long long n_R, double* out) {
@@ -1118,16 +1132,17 @@ struct mbg_step_s {
   CellDev* h_cells = nullptr;
   long long* h_tot = nullptr;  // [n_jobs][2]
   size_t n_out = 0;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
+  int shard_rank = 0, shard_count = 1;
+  cudaGraph_t graph = nullptr, graph_dev = nullptr;  // with / without the host <-> device copies
+  cudaGraphExec_t exec = nullptr, exec_dev = nullptr;
 };
 
 // Everything one evaluation enqueues on the context's stream -- no host synchronisation, no allocation after the
 // first pass (sizes depend only on what mbg_step_create fixed).
-static int step_enqueue(mbg_step_t st) {
+static int step_enqueue(mbg_step_t st, bool host_io) {
   mbg_context_t ctx = st->ctx;
   const size_t nR = (size_t)st->n_frames * st->n_atoms * 3;
-  CUDA_TRY(cudaMemcpyAsync(st->dR.p, st->h_R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (host_io) CUDA_TRY(cudaMemcpyAsync(st->dR.p, st->h_R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (st->n_cells)
     CUDA_TRY(cudaMemcpyAsync(st->tab.cells.p, st->h_cells, (size_t)st->n_cells * sizeof(CellDev), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemsetAsync(st->dOut.p, 0, st->n_out * sizeof(double), ctx->stream));
@@ -1141,11 +1156,11 @@ static int step_enqueue(mbg_step_t st) {
   for (int k = 0; k < st->n_jobs; ++k) {
     if (st->jobs[k].cand_per_frame <= 0) continue;
     long long ncs = 0;
-    TRY(run_job_pw(ctx, st->scr, st->sys, st->jobs[k], st->models[k], st->dR.as<double>(), st->n_frames, 0, 1, st->want_virial,
-                   false, out, k, &ncs));
+    TRY(run_job_pw(ctx, st->scr, st->sys, st->jobs[k], st->models[k], st->dR.as<double>(), st->n_frames, st->shard_rank,
+                   st->shard_count, st->want_virial, false, out, k, &ncs));
     st->n_candidates[k] = ncs;
   }
-  CUDA_TRY(cudaMemcpyAsync(st->h_out, st->dOut.p, st->n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_io) CUDA_TRY(cudaMemcpyAsync(st->h_out, st->dOut.p, st->n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(st->h_tot, st->scr.job_totals.p, (size_t)std::max(st->n_jobs, 1) * 2 * sizeof(long long),
                            cudaMemcpyDeviceToHost, ctx->stream));
   return MBG_OK;
@@ -1157,6 +1172,8 @@ extern "C" int mbg_step_destroy(mbg_step_t st) {
   cudaStreamSynchronize(st->ctx->stream);
   if (st->exec) cudaGraphExecDestroy(st->exec);
   if (st->graph) cudaGraphDestroy(st->graph);
+  if (st->exec_dev) cudaGraphExecDestroy(st->exec_dev);
+  if (st->graph_dev) cudaGraphDestroy(st->graph_dev);
   st->tab.release();
   st->scr.release();
   st->dR.release();
@@ -1170,9 +1187,10 @@ extern "C" int mbg_step_destroy(mbg_step_t st) {
 }
 
 extern "C" int mbg_step_create(mbg_context_t ctx, const mbg_system_desc* sys, int32_t n_frames, const mbg_job* jobs,
-                               int32_t n_jobs, uint32_t flags, mbg_step_t* out_step) {
+                               int32_t n_jobs, uint32_t flags, int32_t shard_rank, int32_t shard_count, mbg_step_t* out_step) {
   if (!ctx || !sys || !jobs || !out_step) return fail(MBG_ERR_ARG, "NULL argument");
   if (n_frames < 1 || n_jobs < 1 || n_jobs > kMaxJobsPerCall) return fail(MBG_ERR_ARG, "bad frame / job count");
+  if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(MBG_ERR_ARG, "bad shard spec");
   if (flags & ~(uint32_t)MBG_FLAG_VIRIAL) return fail(MBG_ERR_UNSUPPORTED, "flag not supported by mbg_step_create");
   if (!uses_pw(ctx)) return fail(MBG_ERR_UNSUPPORTED, "prepared steps need the persistent contraction kernel (MBG_CONTRACT_DMMA / AUTO)");
   const bool want_virial = (flags & MBG_FLAG_VIRIAL) != 0;
@@ -1181,6 +1199,7 @@ extern "C" int mbg_step_create(mbg_context_t ctx, const mbg_system_desc* sys, in
   mbg_step_t st = new mbg_step_s();
   st->ctx = ctx;
   st->n_atoms = sys->n_atoms, st->n_frames = n_frames, st->n_jobs = n_jobs, st->want_virial = want_virial;
+  st->shard_rank = shard_rank, st->shard_count = shard_count;
   auto bail = [&](int rc) {
     ctx->capturing = false;
     mbg_step_destroy(st);
@@ -1222,16 +1241,20 @@ extern "C" int mbg_step_create(mbg_context_t ctx, const mbg_system_desc* sys, in
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(fail(MBG_ERR_CUDA, "table upload failed"));
   // pass 1 (not captured): sizes every scratch buffer; pass 2: the same sequence recorded into a graph
   ctx->capturing = true;
-  if ((rc = step_enqueue(st)) != MBG_OK) return bail(rc);
+  if ((rc = step_enqueue(st, true)) != MBG_OK) return bail(rc);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(fail(MBG_ERR_CUDA, "step warm-up failed: %s", cudaGetErrorString(cudaGetLastError())));
-  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
-    return bail(fail(MBG_ERR_CUDA, "cudaStreamBeginCapture failed (is the context's stream the legacy default stream?)"));
-  rc = step_enqueue(st);
-  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &st->graph);
+  for (int pass = 0; pass < 2; ++pass) {  // with and without the host <-> device copies of R and the results
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+      return bail(fail(MBG_ERR_CUDA, "cudaStreamBeginCapture failed (is the context's stream the legacy default stream?)"));
+    rc = step_enqueue(st, pass == 0);
+    cudaGraph_t& g = pass == 0 ? st->graph : st->graph_dev;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc != MBG_OK) return bail(rc);
+    if (ce != cudaSuccess || !g) return bail(fail(MBG_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce)));
+    if (cudaGraphInstantiate(pass == 0 ? &st->exec : &st->exec_dev, g, 0) != cudaSuccess)
+      return bail(fail(MBG_ERR_CUDA, "cudaGraphInstantiate failed"));
+  }
   ctx->capturing = false;
-  if (rc != MBG_OK) return bail(rc);
-  if (ce != cudaSuccess || !st->graph) return bail(fail(MBG_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce)));
-  if (cudaGraphInstantiate(&st->exec, st->graph, 0) != cudaSuccess) return bail(fail(MBG_ERR_CUDA, "cudaGraphInstantiate failed"));
   *out_step = st;
   return MBG_OK;
 }
@@ -1262,6 +1285,43 @@ extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells,
       stats[k].n_candidates = st->n_candidates[k];
       stats[k].n_accepted = st->h_tot[2 * k], stats[k].n_enumerated = st->h_tot[2 * k + 1];
     }
+  return MBG_OK;
+}
+
+// Device-resident variant: dR, dE, dF, dV are device pointers; everything is enqueued on the context's stream and the
+// call returns without synchronising (cells, when given, are host arrays as in mbg_step_run).
+extern "C" int mbg_step_run_device(mbg_step_t st, const double* dR, const double* cells, const double* cutoffs, double* dE,
+                                   double* dF, double* dV) {
+  if (!st || !dR || !dE || !dF) return fail(MBG_ERR_ARG, "NULL argument");
+  if (st->want_virial && !dV) return fail(MBG_ERR_ARG, "the step computes the virial: pass a virial buffer");
+  mbg_context_t ctx = st->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t nR = (size_t)st->n_frames * st->n_atoms * 3;
+  if (cells) {
+    if (!st->n_cells) return fail(MBG_ERR_ARG, "the step was created without a periodic cell");
+    if (!cutoffs) return fail(MBG_ERR_ARG, "cells without cutoffs");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the pinned cell table may still be read by the previous replay
+    for (int c = 0; c < st->n_cells; ++c)
+      if (memcmp(st->h_cells[c].cell, cells + 9 * (size_t)c, 9 * sizeof(double)) != 0 || st->h_cells[c].cutoff != cutoffs[c])
+        TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c]));
+  }
+  CUDA_TRY(cudaMemcpyAsync(st->dR.p, dR, nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(cudaGraphLaunch(st->exec_dev, ctx->stream));
+  const double* o = st->dOut.as<double>();
+  CUDA_TRY(cudaMemcpyAsync(dE, o, (size_t)st->n_frames * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(dF, o + st->n_frames, nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (st->want_virial)
+    CUDA_TRY(cudaMemcpyAsync(dV, o + st->n_frames + nR, (size_t)st->n_frames * 9 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MBG_OK;
+}
+
+// Counters of the most recent replay of a step (valid after the stream has been synchronised).
+extern "C" int mbg_step_stats(mbg_step_t st, mbg_job_stats* stats) {
+  if (!st || !stats) return fail(MBG_ERR_ARG, "NULL argument");
+  for (int k = 0; k < st->n_jobs; ++k) {
+    stats[k].n_candidates = st->n_candidates[k];
+    stats[k].n_accepted = st->h_tot[2 * k], stats[k].n_enumerated = st->h_tot[2 * k + 1];
+  }
   return MBG_OK;
 }
 
@@ -2226,6 +2286,31 @@ int mbg_mat52_rows(mbg_context_t ctx, int32_t dim_d, const double* r_desc, int64
   CUDA_TRY(cudaMemcpyAsync(out, a.out, nOut * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   end_call_timing(ctx);
+  return MBG_OK;
+}
+
+int mbg_measure_exp_sqrt_rate(mbg_context_t ctx, double* ops_per_s) {
+  if (!ctx || !ops_per_s) return fail(MBG_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(ctx->totals.ensure(2 * sizeof(long long)));
+  const int threads = 256, blocks = ctx->sm_count * 4, iters = 1 << 12;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    k_exp_sqrt_rate<<<blocks, threads, 0, ctx->stream>>>(ctx->totals.as<double>(), iters, 1.0 + rep);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::max(best, 4.0 * iters * threads * blocks / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ops_per_s = best;
   return MBG_OK;
 }
 

@@ -84,7 +84,8 @@ __host__ __device__ constexpr int pw_warp_doubles(int P) {
   const int maxf = pw_max_frag<NA, MT>(P);
   const int stage = pw_stage_rows(NA) * pw_stage_stride(NA);
   const int ys = YS ? MT * KS * 32 : 0;
-  return maxf * D + maxf * NA * 3 + maxf * (D + 1) + ((maxf + 1) / 2) + (ys > stage ? ys : stage);
+  const int recs = 2 * maxf + (maxf * (NA + 1) + 1) / 2;  // lambda, slot (8 bytes each); frame + atoms (4 bytes each)
+  return maxf * D + maxf * NA * 3 + maxf * (D + 1) + ((maxf + 1) / 2) + recs + (ys > stage ? ys : stage);
 }
 
 // NW = the launch bound (warps the kernel is compiled for), nw = warps actually launched (fewer when the per-warp
@@ -180,7 +181,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
   double* rs = xs + (size_t)maxf * D;                                   // [maxf][NA][3]
   double* Fd = rs + (size_t)maxf * NA * 3;                              // [maxf][D + 1]: F_d and E_raw per fragment
   int* bad = reinterpret_cast<int*>(Fd + (size_t)maxf * (D + 1));       // [maxf]
-  double* ysw = reinterpret_cast<double*>(bad) + (maxf + 1) / 2;        // YS: [MT][KS][32]; epilogue: [RP][D + 1]
+  // fragment records of the current item, read once from global memory (the epilogue needs them again)
+  double* r_lam = reinterpret_cast<double*>(bad) + (maxf + 1) / 2;      // [maxf] alchemical factor
+  long long* r_slot = reinterpret_cast<long long*>(r_lam + maxf);       // [maxf] row of the decomposed outputs
+  int* r_frame = reinterpret_cast<int*>(r_slot + maxf);                 // [maxf]
+  int* r_atoms = r_frame + maxf;                                        // [maxf][NA]
+  double* ysw = reinterpret_cast<double*>(r_frame) + (maxf * (NA + 1) + 1) / 2;  // YS: [MT][KS][32]; epilogue: [RP][RS]
 
   if (tid == 0) {
 #pragma unroll
@@ -298,20 +304,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
     const long long f_lo = q0 / P;                        // its first fragment ...
     const int p0 = (int)(q0 - f_lo * P);                  // ... and the permutation its first query applies
     const int nf = (p0 + n_act - 1) / P + 1;
-    for (int fl = lane; fl < nf; fl += 32) bad[fl] = 0;
+    for (int fl = lane; fl < nf; fl += 32) {
+      bad[fl] = 0;
+      r_frame[fl] = a.rec_frame[f_lo + fl], r_lam[fl] = a.rec_lambda[f_lo + fl], r_slot[fl] = a.rec_slot[f_lo + fl];
+    }
+    for (int idx = lane; idx < nf * NA; idx += 32) r_atoms[idx] = a.rec_atoms[f_lo * NA + idx];
     for (int idx = lane; idx < nf * (D + 1); idx += 32) Fd[idx] = 0.0;
     __syncwarp();
 #pragma unroll 1
     for (int idx = lane; idx < nf * NA; idx += 32) {
       const int fl = idx / NA, k = idx - fl * NA;
-      const long long frag = f_lo + fl;
-      const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
-      const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
+      const double* Rf = a.R + (long long)r_frame[fl] * 3ll * a.sys.n_atoms;
+      const double* p = Rf + 3ll * r_atoms[idx];
       double v[3] = {p[0], p[1], p[2]};
       if (a.sys.periodic) {
-        const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
+        const double* pf = Rf + 3ll * r_atoms[fl * NA];
         const double d[3] = {__dsub_rn(v[0], pf[0]), __dsub_rn(v[1], pf[1]), __dsub_rn(v[2], pf[2])};
-        const CellDev& cl = a.sys.cell_stride ? cell_of(a.sys, a.rec_frame[frag]) : *cell_s;
+        const CellDev& cl = a.sys.cell_stride ? cell_of(a.sys, r_frame[fl]) : *cell_s;
         if (!(mic_naive(cl, d, v) < cl.half_min_len)) bad[fl] = 1;
       }
       rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
@@ -322,13 +331,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
       for (int idx = lane; idx < nf * NA; idx += 32) {
         const int fl = idx / NA, k = idx - fl * NA;
         if (!bad[fl]) continue;
-        const long long frag = f_lo + fl;
-        const double* Rf = a.R + (long long)a.rec_frame[frag] * 3ll * a.sys.n_atoms;
-        const double* p = Rf + 3ll * a.rec_atoms[frag * NA + k];
-        const double* pf = Rf + 3ll * a.rec_atoms[frag * NA];
+        const double* Rf = a.R + (long long)r_frame[fl] * 3ll * a.sys.n_atoms;
+        const double* p = Rf + 3ll * r_atoms[idx];
+        const double* pf = Rf + 3ll * r_atoms[fl * NA];
         const double d[3] = {__dsub_rn(p[0], pf[0]), __dsub_rn(p[1], pf[1]), __dsub_rn(p[2], pf[2])};
         double v[3];
-        mic_general(a.sys.cell_stride ? cell_of(a.sys, a.rec_frame[frag]) : *cell_s, d, v);
+        mic_general(a.sys.cell_stride ? cell_of(a.sys, r_frame[fl]) : *cell_s, d, v);
         rs[idx * 3 + 0] = v[0], rs[idx * 3 + 1] = v[1], rs[idx * 3 + 2] = v[2];
       }
       __syncwarp();
@@ -647,16 +655,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
 #pragma unroll 1
     for (int idx = lane; idx < nfe * (NA * 3 + 1); idx += 32) {
       const int fl = idx / (NA * 3 + 1), rem = idx - fl * (NA * 3 + 1);
-      const long long frag = f_loe + fl;
-      const double lam = a.rec_lambda[frag];
+      const double lam = r_lam[fl];
       const double* Fdf = Fd + fl * (D + 1);
       const double* rf = rs + fl * NA * 3;
       const double* xf = xs + fl * D;
       if (rem == NA * 3) {
         // the integration constant is added once per fragment: by the item that holds its first query, slice 0
         const double e = (Fdf[D] * a.std + ((fl * P >= p0e && slice == 0) ? a.c : 0.0)) * lam;
-        double* dst = a.decomp ? a.E + ((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag])
-                               : a.E + a.rec_frame[frag];
+        double* dst = a.decomp ? a.E + ((long long)r_frame[fl] * a.n_slots_per_frame + r_slot[fl]) : a.E + r_frame[fl];
         atomicAdd(dst, e);
       } else {
         const int m = rem / 3, c = rem - m * 3;
@@ -677,15 +683,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
         f *= a.std * lam;
         double* dst =
             a.decomp
-                ? a.F + (((long long)a.rec_frame[frag] * a.n_slots_per_frame + a.rec_slot[frag]) * NA + m) * 3 + c
-                : a.F + ((long long)a.rec_frame[frag] * a.sys.n_atoms + a.rec_atoms[frag * NA + m]) * 3 + c;
+                ? a.F + (((long long)r_frame[fl] * a.n_slots_per_frame + r_slot[fl]) * NA + m) * 3 + c
+                : a.F + ((long long)r_frame[fl] * a.sys.n_atoms + r_atoms[fl * NA + m]) * 3 + c;
         atomicAdd(dst, f);
       }
     }
     if (a.want_virial) {  // stress.virial_atom_loop on the minimum-image coordinates (gdml_predict.py:266-267)
       for (int idx = lane; idx < nfe * 9; idx += 32) {
         const int fl = idx / 9, ij = idx - fl * 9, vi = ij / 3, vj = ij - vi * 3;
-        const long long frag = f_loe + fl;
         const double* Fdf = Fd + fl * (D + 1);
         const double* rf = rs + fl * NA * 3;
         const double* xf = xs + fl * D;
@@ -708,7 +713,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_matern_pw(const __grid_constant_
           }
           wv = fma(rf[m * 3 + vi], f, wv);
         }
-        atomicAdd(a.virial + (long long)a.rec_frame[frag] * 9 + ij, wv * a.std * a.rec_lambda[frag]);
+        atomicAdd(a.virial + (long long)r_frame[fl] * 9 + ij, wv * a.std * r_lam[fl]);
       }
     }
     __syncwarp();
