@@ -7,8 +7,8 @@ and the CPU-baseline / ``--impl reference`` legs of ``bench.py``.
 Every function cites the reference lines (paths relative to /root/reference)
 it follows.  The reference is pure Python/NumPy, so this restatement is
 validated here, in the build container, against the *unmodified* reference
-imported from /root/reference (see ``oracle/make_golden.py`` and
-``tests/test_oracle_vs_reference.py``) and against the reference's own
+imported from /root/reference (``oracle/make_golden.py`` asserts oracle ==
+reference on every fixture it writes) and against the reference's own
 known-answer tests; outputs of that run are committed under ``tests/golden/``.
 
 Pinned:    gen_combs, get_avail_entities, r_slice, descriptor/Jacobian,

@@ -1,6 +1,6 @@
 """Stub of `ray` (absent from this image) so the unmodified reference imports.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Only the serial
+TEST INFRASTRUCTURE ONLY (see oracle/reference.py).  Only the serial
 `use_ray=False` path of the reference is exercised; the few entry points the
 reference touches at import / construction time (mbe.py:28,673-693) are
 identity functions.
