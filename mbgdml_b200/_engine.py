@@ -124,42 +124,59 @@ def make_job(ctx, model, entity_combs, alchemy_scalers, keep):
     return job
 
 
-def step_key(Z, entity_ids, comp_ids, models, scalers_per_model, n_frames, periodic_cell, frame_cells, compute_virial):
-    """What a prepared step fixes: system, models (+ criteria), scalers, frame count, periodicity -- not the cell values."""
-    cell_kind = "frames" if frame_cells is not None else ("cell" if periodic_cell is not None else None)
-    return (np.asarray(Z).tobytes(), np.asarray(entity_ids).tobytes(), tuple(np.asarray(comp_ids).tolist()),
-            tuple((m._uid, m._criteria_key()) for m in models),
-            tuple(tuple((s.entity_id, s.order, s.native_factor()) for s in (sc or [])) for sc in scalers_per_model),
-            int(n_frames), cell_kind, bool(compute_virial))
+def _same_array(kept, new):
+    """Content comparison at memcmp speed (``kept`` is the cache's own copy, so in-place edits of the caller's array are
+    seen)."""
+    if kept.shape != new.shape or kept.dtype != new.dtype:
+        return False
+    if new.flags.c_contiguous and kept.dtype.kind in "iufUS" and kept.size:
+        return bool(np.array_equal(kept.reshape(-1).view(np.uint8), new.reshape(-1).view(np.uint8)))
+    return bool(np.array_equal(kept, new))
 
 
 class StepCache:
-    """Prepared steps of one predictor.  A step is built the second time a key is seen (a one-off evaluation does not pay
-    for the capture) and at most ``capacity`` of them are kept."""
+    """Prepared steps of one predictor.  A step is built the second time a description is seen (a one-off evaluation
+    does not pay for the capture) and at most ``capacity`` of them are kept.  What a step fixes: system (Z, entity_ids,
+    comp_ids), models (+ criteria), scalers, frame count, kind of periodicity, virial flag -- not the cell values."""
 
     def __init__(self, capacity=4):
-        self.capacity, self.seen, self.steps = capacity, {}, {}
+        self.capacity, self.entries = capacity, []
 
-    def get(self, key, build):
-        step = self.steps.get(key)
-        if step is not None:
-            return step
-        self.seen[key] = self.seen.get(key, 0) + 1
-        if self.seen[key] < 2:
-            if len(self.seen) > 64:
-                self.seen.clear()
-            return None
-        step = build()
-        if len(self.steps) >= self.capacity:
-            self.steps.pop(next(iter(self.steps))).close()
-        self.steps[key] = step
-        return step
+    @staticmethod
+    def small_key(models, scalers_per_model, n_frames, periodic_cell, frame_cells, compute_virial):
+        cell_kind = "frames" if frame_cells is not None else ("cell" if periodic_cell is not None else None)
+        return (tuple((m._uid, m._criteria_key()) for m in models),
+                tuple(tuple((s.entity_id, s.order, s.native_factor()) for s in (sc or [])) for sc in scalers_per_model),
+                int(n_frames), cell_kind, bool(compute_virial))
+
+    def get(self, Z, entity_ids, comp_ids, small, build):
+        Z, entity_ids, comp_ids = np.asarray(Z), np.asarray(entity_ids), np.asarray(comp_ids)
+        for e in self.entries:
+            if e["small"] == small and _same_array(e["Z"], Z) and _same_array(e["eids"], entity_ids) \
+                    and _same_array(e["cids"], comp_ids):
+                if e["step"] is None:
+                    e["step"] = build()  # second sighting
+                    live = [x for x in self.entries if x["step"] is not None]
+                    if len(live) > self.capacity:
+                        live[0]["step"].close()
+                        self.entries.remove(live[0])
+                return e["step"]
+        self.entries.append({"small": small, "Z": np.ascontiguousarray(Z).copy(), "eids": np.ascontiguousarray(entity_ids).copy(),
+                             "cids": np.ascontiguousarray(comp_ids).copy(), "step": None})
+        if len(self.entries) > 16:
+            old = self.entries.pop(0)
+            if old["step"] is not None:
+                old["step"].close()
+        return None
+
+    @property
+    def steps(self):
+        return [e["step"] for e in self.entries if e["step"] is not None]
 
     def clear(self):
-        for st in self.steps.values():
+        for st in self.steps:
             st.close()
-        self.steps.clear()
-        self.seen.clear()
+        self.entries = []
 
 
 def make_step(ctx, Z, entity_ids, models, comb_sources, scalers_per_model, periodic_cell, n_frames, compute_virial=False,

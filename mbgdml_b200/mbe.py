@@ -274,18 +274,20 @@ class mbePredict:  # pylint: disable=invalid-name
         """Fast path: every frame and every model in one native call (+ one all-reduce).  ``frame_cells`` =
         (cells (n_frames, 3, 3), cutoffs (n_frames,)) evaluates every frame under its own periodic cell."""
         ctx = _native.get_context()
-        sources = [gen_combs(self.get_avail_entities(comp_ids, m.comp_ids)) for m in self.models]
         scalers = [self._scalers_for(m) for m in self.models]
         cell = None if frame_cells is not None else self.periodic_cell
+
+        def sources():  # one gen_combs per model: the device enumerates from its sets
+            return [gen_combs(self.get_avail_entities(comp_ids, m.comp_ids)) for m in self.models]
+
         group = _shard_group(self.shard_group)
         if group is None:
             step = None
             if self.use_graph and not hasattr(R, "data_ptr"):
                 try:
-                    key = _engine.step_key(Z, entity_ids, comp_ids, self.models, scalers, R.shape[0], cell, frame_cells,
-                                           want_virial)
-                    step = self._steps.get(key, lambda: _engine.make_step(
-                        ctx, Z, entity_ids, self.models, sources, scalers, cell, R.shape[0], compute_virial=want_virial,
+                    small = _engine.StepCache.small_key(self.models, scalers, R.shape[0], cell, frame_cells, want_virial)
+                    step = self._steps.get(Z, entity_ids, comp_ids, small, lambda: _engine.make_step(
+                        ctx, Z, entity_ids, self.models, sources(), scalers, cell, R.shape[0], compute_virial=want_virial,
                         frame_cells=frame_cells))
                 except NotImplementedError:  # e.g. the FMA-pipe / wave-launched kernels are selected
                     self.use_graph, step = False, None
@@ -299,7 +301,7 @@ class mbePredict:  # pylint: disable=invalid-name
                     cells = cutoffs = None
                 E, F, V, stats = step.run(R, cells, cutoffs)
             else:
-                E, F, V, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers, cell,
+                E, F, V, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources(), scalers, cell,
                                                        compute_virial=want_virial, frame_cells=frame_cells)
             self.last_stats = stats
             return E, F, V
@@ -319,7 +321,7 @@ class mbePredict:  # pylint: disable=invalid-name
         cur = torch.cuda.current_stream(dev).cuda_stream
         prev = ctx.swap_stream(cur if cur != 0 else 1)
         try:
-            _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources, scalers,
+            _, _, _, stats = _engine.predict_total(ctx, Z, R, entity_ids, self.models, sources(), scalers,
                                                    cell, compute_virial=want_virial,
                                                    shard=(dist.get_rank(group), dist.get_world_size(group)),
                                                    device_out=(E_t, F_t, V_t), frame_cells=frame_cells)
