@@ -801,12 +801,30 @@ struct Outputs {
 };
 
 
-// Candidates of granules [g0, g0 + blocks) of one shard (every granule is full except the last one of the space).
-static long long shard_candidates(long long g0, long long blocks, int shard_rank, int shard_count, long long n_cand_total) {
-  if (blocks <= 0) return 0;
-  const long long last_lo = ((g0 + blocks - 1) * shard_count + shard_rank) * (long long)kCullThreads;
-  const long long last = std::max(0ll, std::min<long long>(kCullThreads, n_cand_total - last_lo));
-  return (blocks - 1) * (long long)kCullThreads + last;
+// Shard geometry (enumerate.cuh: global_candidate): granules of kShardGranule candidates dealt round-robin to the ranks;
+// a rank's own space is its granules back to back, processed in blocks of kCullThreads.
+static long long shard_local_granules(long long n_cand_total, int shard_rank, int shard_count) {
+  const long long n_g = (n_cand_total + kShardGranule - 1) / kShardGranule;
+  return n_g > shard_rank ? (n_g - shard_rank + shard_count - 1) / shard_count : 0;
+}
+static long long shard_blocks(long long n_cand_total, int shard_rank, int shard_count) {
+  constexpr int gpb = kCullThreads / kShardGranule;
+  return (shard_local_granules(n_cand_total, shard_rank, shard_count) + gpb - 1) / gpb;
+}
+// Candidates (< n_cand_total) covered by blocks [b0, b0 + blocks) of one shard: every granule is full except the last
+// granule of the whole space.
+static long long shard_candidates(long long b0, long long blocks, int shard_rank, int shard_count, long long n_cand_total) {
+  constexpr int gpb = kCullThreads / kShardGranule;
+  const long long n_loc = shard_local_granules(n_cand_total, shard_rank, shard_count);
+  const long long lo = std::min(b0 * gpb, n_loc), hi = std::min((b0 + blocks) * gpb, n_loc);
+  if (hi <= lo) return 0;
+  long long n = (hi - lo) * kShardGranule;
+  const long long n_g = (n_cand_total + kShardGranule - 1) / kShardGranule;
+  if ((n_g - 1) % shard_count == shard_rank) {  // the partial last granule belongs to this shard
+    const long long loc = (n_g - 1 - shard_rank) / shard_count;
+    if (loc >= lo && loc < hi) n -= n_g * kShardGranule - n_cand_total;
+  }
+  return n;
 }
 
 // Enumerate + cull + compact + contract one job with the persistent contraction kernel: no host synchronisation.
@@ -817,8 +835,7 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
                       int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
                       int job_slot, long long* n_cand_shard_out) {
   const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
-  const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads;
-  const long long my_granules = n_granules > shard_rank ? (n_granules - shard_rank + shard_count - 1) / shard_count : 0;
+  const long long my_granules = shard_blocks(n_cand_total, shard_rank, shard_count);  // blocks of this shard
   const int NA = j.n_frag_atoms;
   *n_cand_shard_out = shard_candidates(0, my_granules, shard_rank, shard_count, n_cand_total);
   if (my_granules == 0) return MBG_OK;
@@ -900,9 +917,8 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     return fail(MBG_ERR_UNSUPPORTED, "models carrying a lattice run on the MBG_CONTRACT_DMMA / AUTO kernel only");
   const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
   long long n_cand_shard = 0, n_enum = 0, n_acc = 0;
-  const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads;
-  const long long my_granules = n_granules > shard_rank ? (n_granules - shard_rank + shard_count - 1) / shard_count : 0;
-  const long long kChunk = 1ll << 18;  // granules per launch (67 M candidates, 64 MiB of flags)
+  const long long my_granules = shard_blocks(n_cand_total, shard_rank, shard_count);  // blocks of this shard
+  const long long kChunk = 1ll << 18;  // blocks per launch (67 M candidates, 64 MiB of flags)
   const long long kMaxRec = 1ll << 22; // contract at the latest when this many records are pending
   const int NA = j.n_frag_atoms;
 
@@ -978,10 +994,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->scr.blk_acc.as<int>(), ctx->scr.blk_enum.as<int>(), blocks,
                                                ctx->scr.blk_off.as<long long>(), totals);
     ctx->launches++;
-    for (long long b = 0; b < blocks; ++b) {
-      const long long lo = (b * shard_count + shard_rank) * kCullThreads;
-      n_cand_shard += std::max(0ll, std::min<long long>(kCullThreads, n_cand_total - lo));
-    }
+    n_cand_shard += shard_candidates(0, blocks, shard_rank, shard_count, n_cand_total);
     TRY(ctx->scr.rec_frame.ensure((size_t)n_cand_shard * sizeof(int)));
     TRY(ctx->scr.rec_atoms.ensure((size_t)n_cand_shard * NA * sizeof(int)));
     TRY(ctx->scr.rec_lambda.ensure((size_t)n_cand_shard * sizeof(double)));
@@ -1027,11 +1040,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
     const long long acc = ctx->h_totals[0];
     n_enum += ctx->h_totals[1];
     n_acc += acc;
-    for (long long b = 0; b < blocks; ++b) {  // candidates of this shard (last granule may be partial)
-      const long long granule = (g0 + b) * shard_count + shard_rank;
-      const long long lo = granule * kCullThreads;
-      n_cand_shard += std::max(0ll, std::min<long long>(kCullThreads, n_cand_total - lo));
-    }
+    n_cand_shard += shard_candidates(g0, blocks, shard_rank, shard_count, n_cand_total);
     if (acc == 0) continue;
     const long long need = rec_pending + acc;
     const bool fits = (size_t)need * sizeof(int) <= ctx->scr.rec_frame.cap && (size_t)need * NA * sizeof(int) <= ctx->scr.rec_atoms.cap &&

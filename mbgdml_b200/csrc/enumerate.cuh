@@ -7,8 +7,9 @@
 // accept it (descriptors.py:65-103).  Survivors are compacted IN CANDIDATE ORDER
 // (== the reference's emission order) into fragment records for the contraction kernel.
 //
-// Sharding: the global candidate space is cut into granules of kCullThreads candidates;
-// shard r of G owns granules r, r+G, r+2G, ...  (block-cyclic; no communication).
+// Sharding: the global candidate space is cut into granules of kShardGranule candidates;
+// shard r of G owns granules r, r+G, r+2G, ...  (block-cyclic; no communication).  A cull block of
+// kCullThreads threads covers kCullThreads / kShardGranule consecutive granules of its shard.
 #pragma once
 #include "geom.cuh"
 
@@ -20,7 +21,7 @@ struct CullArgs {
   JobDev job;
   const double* R;        // [n_frames][n_atoms][3]
   long long n_cand_total; // n_frames * cand_per_frame
-  long long granule0;     // first local granule of this launch
+  long long granule0;     // first block (kCullThreads candidates of this shard's own space) of this launch
   int shard_rank, shard_count;
   unsigned char* flags;   // [launch candidates] 0: dropped, 1: accepted, 2: ascending but rejected
   int* block_accept;      // [blocks] accepted per block
@@ -28,8 +29,9 @@ struct CullArgs {
 };
 
 __device__ __forceinline__ long long global_candidate(const CullArgs& a, int block, int tid) {
-  const long long granule = (a.granule0 + block) * (long long)a.shard_count + a.shard_rank;
-  return granule * kCullThreads + tid;
+  const long long local = (a.granule0 + block) * (long long)kCullThreads + tid;  // index in this shard's own space
+  const long long granule = (local / kShardGranule) * a.shard_count + a.shard_rank;
+  return granule * kShardGranule + local % kShardGranule;
 }
 
 // One thread per candidate: decode -> gather -> MIC/cut-off -> criteria -> flag.
