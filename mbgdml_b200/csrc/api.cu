@@ -2200,19 +2200,42 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
   a.K = dK, a.ld = (long long)rows;
   const long long n_blocks = closed ? (long long)T * (T + 1) / 2 : (long long)T * T;
   if (n_blocks > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: too many blocks for one launch");
+  // warp-per-pair kernel for narrow descriptors (D <= 15: measured 4.3x / 1.24x faster than CTA-per-pair for water
+  // monomers / dimers at T = 1000, 0.93x for trimers, where its 12 warps per SM are too few to hide the latency of
+  // the shared-memory chains: profiles/r2_train_kernels.md), else CTA per pair
+  int dev_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   void (*kern)(KernelMatArgs) = nullptr;
-  size_t smem = 0;
+  void (*kern_w)(KernelMatArgs, long long) = nullptr;
+  size_t smem = 0, smem_w4 = 0, smem_w = 0;
+  int nw = 0;
   switch (N) {
-#define X(NA_) case NA_: kern = k_kernel_mat<NA_>, smem = KmShape<NA_>::kBytes; break;
+#define X(NA_)                                                                                   \
+  case NA_:                                                                                      \
+    kern = k_kernel_mat<NA_>, smem = KmShape<NA_>::kBytes;                                       \
+    kern_w = k_kernel_mat_w<NA_>, smem_w4 = KmwShape<NA_>::bytes(4, P);                          \
+    for (nw = kKmwMaxWarps; nw > 4 && KmwShape<NA_>::bytes(nw, P) > (size_t)dev_smem; --nw) {}   \
+    smem_w = KmwShape<NA_>::bytes(nw, P);                                                        \
+    break;
     MBG_FOR_EACH_NA(X)
 #undef X
     default: return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: no kernel for %d atoms", N);
   }
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // MBG_MMA_CFG=4 / 5 (developer): always CTA per pair / always warp per pair when it fits
+  const bool per_warp = smem_w4 <= (size_t)dev_smem && ctx->mma_cfg != 4 && (D <= 15 || ctx->mma_cfg == 5);
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
-  cudaEventRecord(e0, ctx->stream);
-  kern<<<(unsigned)n_blocks, kKmThreads, smem, ctx->stream>>>(a);
-  cudaEventRecord(e1, ctx->stream);
+  if (per_warp) {
+    CUDA_TRY(cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    const long long ctas = std::min<long long>((n_blocks + nw - 1) / nw, (long long)ctx->sm_count * 4);
+    cudaEventRecord(e0, ctx->stream);
+    kern_w<<<(unsigned)ctas, nw * 32, smem_w, ctx->stream>>>(a, n_blocks);
+    cudaEventRecord(e1, ctx->stream);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(e0, ctx->stream);
+    kern<<<(unsigned)n_blocks, kKmThreads, smem, ctx->stream>>>(a);
+    cudaEventRecord(e1, ctx->stream);
+  }
   CUDA_TRY(cudaGetLastError());
   record_aux_launch(ctx, e0, e1, N, (long long)T * T, T, P, 2);
   if (!out_dev) {

@@ -216,6 +216,221 @@ __global__ void __launch_bounds__(kKmThreads) k_kernel_mat(const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Warp-per-pair form of the kernel-matrix assembly (round 2).  The CTA-per-pair kernel above spends its time in
+// ~20 CTA-wide barriers per pair around short, partly narrow phases (ncu: barrier + short-scoreboard stalls,
+// shared-memory wavefronts at 94 % of peak, FP64 pipe 17 %).  Here every WARP owns a pair (i, j) of training points
+// from start to finish -- only __syncwarp between phases -- with its own slice of shared memory, 8-12 warps per SM
+// overlap each other's latencies, and the rank-1 part K += 5 b_p u_p v_p^T runs on a register tile (lane (rg, cg)
+// owns RT x CT outputs: RT + CT shared-memory loads per RT CT FMAs).  Same arithmetic per pair as above.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kKmwPC = 8;         // permutations per chunk: 4 lanes per permutation in the norm phase
+constexpr int kKmwMaxWarps = 12;  // warps per CTA (fewer when the per-warp slices do not fit)
+
+template <int NA>
+struct KmwShape {
+  static constexpr int N = NA, D = NA * (NA - 1) / 2, N3 = 3 * NA;
+  static constexpr int RT = (N3 + 3) / 4, CT = (N3 + 7) / 8;  // register tile per lane: 4 row groups x 8 column groups
+  static constexpr int NE = (N3 + 31) / 32;                   // energy-constraint entries per lane
+  // doubles per warp: Xi, Xj, gi, gj, diff[PC][D], u / fu / v [PC][N3], W[D][N3], (fb, cc, kee, pad)[PC]
+  static constexpr int kWarpDoubles = 2 * D + 6 * D + kKmwPC * D + 3 * kKmwPC * N3 + D * N3 + 4 * kKmwPC;
+  __host__ __device__ static constexpr bool tables_in_smem(int P) { return D <= 255 && 2 * P * D <= 16 * 1024; }
+  __host__ __device__ static constexpr size_t bytes(int nw, int P) {
+    return (size_t)nw * kWarpDoubles * 8 + (tables_in_smem(P) ? (size_t)(2 * P * D + 7) / 8 * 8 : 0) + 2 * D * sizeof(int) + 16;
+  }
+};
+
+template <int NA>
+__global__ void __launch_bounds__(kKmwMaxWarps * 32) k_kernel_mat_w(const __grid_constant__ KernelMatArgs a, const long long n_pairs) {
+  using S = KmwShape<NA>;
+  constexpr int N = S::N, D = S::D, N3 = S::N3, RT = S::RT, CT = S::CT, NE = S::NE, PC = kKmwPC;
+  extern __shared__ __align__(16) unsigned char kmw_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int P = a.P;
+  const bool tabs = S::tables_in_smem(P);
+  double* wbase = reinterpret_cast<double*>(kmw_smem) + (size_t)warp * S::kWarpDoubles;
+  unsigned char* tab_s = reinterpret_cast<unsigned char*>(reinterpret_cast<double*>(kmw_smem) + (size_t)nw * S::kWarpDoubles);
+  int* pa = reinterpret_cast<int*>(tab_s + (tabs ? (size_t)(2 * P * D + 7) / 8 * 8 : 0));  // [D] larger atom of pair k
+  int* pb = pa + D;                                                                          // [D] smaller atom
+  double* Xi = wbase;
+  double* Xj = Xi + D;
+  double* gi = Xj + D;         // [D][3]
+  double* gj = gi + 3 * D;     // [D][3]
+  double* diff = gj + 3 * D;   // [PC][D]
+  double* u = diff + PC * D;   // [PC][3N]  J_i^T diff_p
+  double* fu = u + PC * N3;    // [PC][3N]  5 b_p u_p
+  double* v = fu + PC * N3;    // [PC][3N]  (J_j[pi_p])^T diff_p
+  double* W = v + PC * N3;     // [D][3N]
+  double* fb = W + D * N3;     // [PC] 5 b_p
+  double* cc = fb + PC;        // [PC] c_p
+  double* kee = cc + PC;       // [PC]
+
+  for (int k = tid; k < D; k += blockDim.x) {
+    int hi = 1;
+    while ((hi + 1) * hi / 2 <= k) ++hi;  // k = hi (hi - 1) / 2 + lo, lo < hi  (np.tril_indices order)
+    pa[k] = hi, pb[k] = k - hi * (hi - 1) / 2;
+  }
+  if (tabs)
+    for (int k = tid; k < P * D; k += blockDim.x) tab_s[k] = (unsigned char)a.pi[k], tab_s[P * D + k] = (unsigned char)a.ipi[k];
+  __syncthreads();
+  auto pi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[p * D + k] : a.pi[(size_t)p * D + k]; };
+  auto ipi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[P * D + p * D + k] : a.ipi[(size_t)p * D + k]; };
+
+  const double sig = a.sig, sqrt5 = sqrt(5.0);
+  const int rg = lane >> 3, cg = lane & 7;  // this lane's tile: rows rg RT + [0, RT), columns cg CT + [0, CT)
+  const size_t E0 = (size_t)a.T * N3;
+
+  for (long long b = (long long)blockIdx.x * nw + warp; b < n_pairs; b += (long long)gridDim.x * nw) {
+    int i, j;
+    if (a.symmetric) {  // b = i (i + 1) / 2 + j, j <= i
+      i = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+      while ((long long)(i + 1) * (i + 2) / 2 <= b) ++i;
+      while ((long long)i * (i + 1) / 2 > b) --i;
+      j = (int)(b - (long long)i * (i + 1) / 2);
+    } else {
+      i = (int)(b % a.T), j = (int)(b / a.T);
+    }
+    __syncwarp();  // the previous pair's reads of this warp's slice are done
+    for (int k = lane; k < D; k += 32) Xi[k] = a.X[(size_t)i * D + k], Xj[k] = a.X[(size_t)j * D + k];
+    for (int k = lane; k < 3 * D; k += 32) gi[k] = a.G[(size_t)i * 3 * D + k], gj[k] = a.G[(size_t)j * 3 * D + k];
+    for (int k = lane; k < D * N3; k += 32) W[k] = 0.0;
+    double acc[RT][CT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[r][c] = 0.0;
+    double erow[NE], ecol[NE], eacc = 0.0;  // -sum c_p v_p[e], +sum c_p u_p[e] for e = lane + 32 q; lane 0: -sum kee_p
+#pragma unroll
+    for (int q = 0; q < NE; ++q) erow[q] = 0.0, ecol[q] = 0.0;
+
+    for (int p0 = 0; p0 < P; p0 += PC) {
+      const int pc = min(PC, P - p0);
+      __syncwarp();
+      // A1: diff_p[k] = X_i[k] - X_j[pi_p(k)]
+      for (int idx = lane; idx < pc * D; idx += 32) {
+        const int pl = idx / D, k = idx - pl * D;
+        diff[idx] = Xi[k] - Xj[pi_at(p0 + pl, k)];
+      }
+      __syncwarp();
+      // A2: norms and radial factors, four lanes per permutation
+      {
+        const int pl = lane >> 2, part = lane & 3;
+        double s = 0.0;
+        if (pl < pc)
+          for (int k = part; k < D; k += 4) s = fma(diff[pl * D + k], diff[pl * D + k], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0 && pl < pc) {
+          const double n = sqrt5 * sqrt(s);
+          const double ex = exp(-n / sig);
+          const double bq = ex / (3.0 * sig * sig * sig * sig) * 5.0;
+          fb[pl] = 5.0 * bq;
+          cc[pl] = (sig * sig + sig * n) * bq;
+          kee[pl] = (1.0 + (n / sig) * (1.0 + n / (3.0 * sig))) * ex;
+        }
+      }
+      __syncwarp();
+      // A3: u_p = J_i^T diff_p, v_p = (J_j[pi_p])^T diff_p  -- one lane per (p, atom, axis)
+      for (int idx = lane; idx < pc * N3; idx += 32) {
+        const int pl = idx / N3, r = idx - pl * N3, at = r / 3, ax = r - at * 3;
+        const double* dp = diff + pl * D;
+        double su = 0.0, sv = 0.0;
+#pragma unroll
+        for (int x = 0; x < N; ++x) {
+          if (x == at) continue;
+          const int k = km_pair(at, x);
+          const double sgn = at < x ? 1.0 : -1.0;  // +g at the smaller atom of the pair, -g at the larger
+          su = fma(sgn * gi[k * 3 + ax], dp[k], su);
+          sv = fma(sgn * gj[k * 3 + ax], dp[ipi_at(p0 + pl, k)], sv);  // row k of J_j sits at position pi_p^-1(k) of J_j[pi_p]
+        }
+        u[idx] = su, fu[idx] = fb[pl] * su, v[idx] = sv;
+      }
+      // B1: W[k][c] += c_p J_j[pi_p(k)][c]  -- lane (k, axis) owns its row/axis: no conflicts
+      for (int idx = lane; idx < D * 3; idx += 32) {
+        const int k = idx / 3, ax = idx - k * 3;
+        for (int pl = 0; pl < pc; ++pl) {
+          const int k2 = pi_at(p0 + pl, k);
+          const double val = cc[pl] * gj[k2 * 3 + ax];
+          W[k * N3 + pb[k2] * 3 + ax] += val;
+          W[k * N3 + pa[k2] * 3 + ax] -= val;
+        }
+      }
+      __syncwarp();
+      // B2: rank-1 part on the register tile
+      for (int pl = 0; pl < pc; ++pl) {
+        double fr[RT], vc[CT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) fr[r] = (rg * RT + r < N3) ? fu[pl * N3 + rg * RT + r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) vc[c] = (cg * CT + c < N3) ? v[pl * N3 + cg * CT + c] : 0.0;
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[r][c] = fma(fr[r], vc[c], acc[r][c]);
+      }
+      if (a.use_E) {
+#pragma unroll
+        for (int q = 0; q < NE; ++q) {
+          const int e = lane + 32 * q;
+          if (e < N3)
+            for (int pl = 0; pl < pc; ++pl) erow[q] = fma(-cc[pl], v[pl * N3 + e], erow[q]), ecol[q] = fma(cc[pl], u[pl * N3 + e], ecol[q]);
+        }
+        if (lane == 0)
+          for (int pl = 0; pl < pc; ++pl) eacc -= kee[pl];
+      }
+    }
+    __syncwarp();
+    // C: K_ij[r][c] = acc - sum_{k containing atom(r)} J_i[k][r] W[k][c]; the block and (symmetric mode) its transpose
+    double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+    double* Kji = a.K + ((size_t)j * N3) * a.ld + (size_t)i * N3;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int row = rg * RT + r;
+      if (row >= N3) continue;
+      const int at = row / 3, ax = row - at * 3;
+      double s[CT];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) s[c] = acc[r][c];
+#pragma unroll
+      for (int x = 0; x < N; ++x) {
+        if (x == at) continue;
+        const int k = km_pair(at, x);
+        const double gq = (at < x ? -1.0 : 1.0) * gi[k * 3 + ax];
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (cg * CT + c < N3) s[c] = fma(gq, W[k * N3 + cg * CT + c], s[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int col = cg * CT + c;
+        if (col < N3) {
+          Kij[(size_t)row * a.ld + col] = s[c];
+          if (a.symmetric && i != j) Kji[(size_t)col * a.ld + row] = s[c];
+        }
+      }
+    }
+    if (a.use_E) {
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        const int e = lane + 32 * q;
+        if (e < N3) {
+          a.K[(E0 + i) * a.ld + (size_t)j * N3 + e] = erow[q];  // train.py:224-239
+          a.K[((size_t)j * N3 + e) * a.ld + E0 + i] = erow[q];  // train.py:262-287 (worker j' = T + i, block j)
+          if (a.symmetric && i != j) {  // the swapped pair: (J_i[pi_p])^T (X_j - X_i[pi_p]) = -u_q with pi_q = pi_p^-1
+            a.K[(E0 + j) * a.ld + (size_t)i * N3 + e] = ecol[q];
+            a.K[((size_t)i * N3 + e) * a.ld + E0 + j] = ecol[q];
+          }
+        }
+      }
+      if (lane == 0) {
+        a.K[(E0 + j) * a.ld + E0 + i] = eacc;  // train.py:287-289
+        if (a.symmetric && i != j) a.K[(E0 + i) * a.ld + E0 + j] = eacc;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Matern-5/2 covariance of query structures vs. the permuted training rows (analysis/models.py:31-139).
 // out[m][t P + p] = (1 + s d + 5 d^2 / (3 sig^2)) exp(-s d),  d = |x_m - X_t[pi_p]| = |x_m[pi_p^-1] - X_t|.
