@@ -16,6 +16,7 @@
 #include "matern.cuh"
 #include "matern_mma.cuh"
 #include "matern_pw.cuh"
+#include "matern_small.cuh"
 #include "mbe_accum.cuh"
 #include "kernel_mat.cuh"
 
@@ -407,6 +408,55 @@ static int launch_matern_pw(mbg_context_t ctx, Scratch& sc, int na, bool use_E, 
 #undef X
     default:
       return fail(MBG_ERR_UNSUPPORTED, "no contraction kernel for fragments of %d atoms", na);
+  }
+}
+
+// Thread-per-query FMA-pipe kernel for narrow descriptors (matern_small.cuh): fragments of 2-4 atoms.
+template <int NA, bool USE_E>
+static int launch_matern_small_t(mbg_context_t ctx, const MaternSmallArgs& a_in, int chunk_slot) {
+  MaternSmallArgs a = a_in;
+  int dev_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  a.rows_per_pass = small_rows_per_pass<NA>(a.T, a.P, (size_t)dev_smem);
+  if (a.rows_per_pass < 1) return fail(MBG_ERR_UNSUPPORTED, "model does not fit the narrow-descriptor kernel");
+  constexpr int D = NA * (NA - 1) / 2;
+  const size_t smem = small_fixed_bytes<NA>(a.P) + (size_t)a.rows_per_pass * (D * 16 + 8);
+  auto kern = k_matern_small<NA, USE_E>;
+  static thread_local size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const long long nq_max = a.n_frag * a.P;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, (nq_max + kSmallThreads - 1) / kSmallThreads));
+  if (ctx->capturing) {
+    kern<<<grid, kSmallThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MBG_OK;
+  }
+  cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+  kern<<<grid, kSmallThreads, smem, ctx->stream>>>(a);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches++;
+  ctx->n_contract++;
+  ctx->launch_recs.push_back({NA, a.n_frag, (a.T + kTileRows - 1) / kTileRows * kTileRows, a.P, 0.f, MBG_CONTRACT_DMMA});
+  ctx->rec_chunk_slot.resize(ctx->launch_recs.size(), -1);
+  ctx->rec_chunk_slot.back() = chunk_slot;
+  CUDA_TRY(cudaGetLastError());
+  return MBG_OK;
+}
+
+static int launch_matern_small(mbg_context_t ctx, int na, bool use_E, const MaternSmallArgs& a, int chunk_slot) {
+  switch (na) {
+#define X(N) \
+  case N:    \
+    return use_E ? launch_matern_small_t<N, true>(ctx, a, chunk_slot) : launch_matern_small_t<N, false>(ctx, a, chunk_slot);
+    X(2) X(3) X(4)
+#undef X
+    default:
+      return fail(MBG_ERR_UNSUPPORTED, "no narrow-descriptor kernel for fragments of %d atoms", na);
   }
 }
 
@@ -883,6 +933,24 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
       k_zero_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sc.rec_slot.as<long long>(), n_up, NA * 3,
                                                                          out.E, out.F, totals);
       ctx->launches++;
+    }
+    if (NA <= 4 && ctx->mma_cfg != 6) {  // narrow descriptors: thread-per-query FMA-pipe kernel (MBG_MMA_CFG=6: off)
+      MaternSmallArgs q;
+      q.sys = s, q.R = dR;
+      q.XA = m->XA, q.alphaE = m->alphaE, q.exp2_table = ctx->exp2_table_mma.as<double>();
+      q.iperm = m->iperm, q.perm = m->perm;
+      q.T = m->T, q.P = m->P, q.rows_per_pass = 0;
+      q.sig = m->sig, q.c = m->c, q.std = m->std;
+      q.n_frag = n_up, q.n_frag_dev = totals;
+      q.rec_frame = sc.rec_frame.as<int>(), q.rec_atoms = sc.rec_atoms.as<int>();
+      q.rec_lambda = sc.rec_lambda.as<double>(), q.rec_slot = sc.rec_slot.as<long long>();
+      q.n_slots_per_frame = (int)j.cand_per_frame, q.decomp = decomp ? 1 : 0, q.want_virial = want_virial ? 1 : 0;
+      q.E = out.E, q.F = out.F, q.virial = out.V;
+      q.use_lat = m->use_lat ? 1 : 0;
+      if (m->use_lat) memcpy(q.lat, m->lat, sizeof(q.lat)), memcpy(q.lat_inv, m->lat_inv, sizeof(q.lat_inv));
+      sc.n_pw_launch++;  // keeps the chunk slot of this launch its own
+      TRY(launch_matern_small(ctx, NA, m->use_E, q, slot));
+      continue;
     }
     MaternPwArgs a;
     a.sys = s;
