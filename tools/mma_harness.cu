@@ -9,6 +9,11 @@
 #include <cstdlib>
 #include <vector>
 
+#ifndef H_NA
+#define H_NA 9   // atoms per fragment
+#define H_P 48   // permutations
+#define H_MT 3   // m-tiles per warp
+#endif
 #include "../mbgdml_b200/csrc/common.cuh"
 #include "../mbgdml_b200/csrc/geom.cuh"
 #include "../mbgdml_b200/csrc/matern_mma.cuh"
@@ -29,7 +34,7 @@ static double frand() { return rand() / (double)RAND_MAX; }
 
 template <int MT, int NTHR, bool YS, int MINB = 1>
 static int run(const char* name, MaternMmaArgs a, int reps) {
-  constexpr int NA = 9;
+  constexpr int NA = H_NA, D = NA * (NA - 1) / 2;
   auto kern = k_matern_mma<NA, MT, NTHR, MINB, false, YS>;
   const size_t smem = mma_smem_bytes<NA, MT, YS>(NTHR, a.P);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -53,7 +58,7 @@ static int run(const char* name, MaternMmaArgs a, int reps) {
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
   }
-  const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * 36 + 10);
+  const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * D + 10);
   printf("%-28s grid %6u  smem %6zu  %8.3f ms  %6.2f TFLOP/s (algorithmic, T=1000 formula scaled by rows %d)\n", name, grid,
          smem, best, flop * (a.n_row_blocks * 8 / 1000.0) / best / 1e9, a.n_row_blocks * 8);
   return 0;
@@ -62,15 +67,15 @@ static int run(const char* name, MaternMmaArgs a, int reps) {
 // persistent per-warp kernel (matern_pw.cuh): one CTA per SM, work counters zeroed before every launch
 template <int MT, int NW, bool YS>
 static int run_pw(const char* name, const MaternMmaArgs& m, int reps, int sm_count, int nw_launch = NW) {
-  constexpr int NA = 9;
+  constexpr int NA = H_NA, D = NA * (NA - 1) / 2;
   MaternPwArgs a;
   memset(&a, 0, sizeof(a));
   a.sys = m.sys, a.R = m.R, a.tiles = m.tiles, a.mu = m.mu, a.exp2_table = m.exp2_table, a.iperm = m.iperm;
   {  // forward permutations from the inverse table
-    std::vector<int> ip((size_t)m.P * 36), fp((size_t)m.P * 36);
+    std::vector<int> ip((size_t)m.P * D), fp((size_t)m.P * D);
     CK(cudaMemcpy(ip.data(), m.iperm, ip.size() * 4, cudaMemcpyDeviceToHost));
     for (int p = 0; p < m.P; ++p)
-      for (int e = 0; e < 36; ++e) fp[p * 36 + ip[p * 36 + e]] = e;
+      for (int e = 0; e < D; ++e) fp[p * D + ip[p * D + e]] = e;
     int* dfp;
     CK(cudaMalloc(&dfp, fp.size() * 4));
     CK(cudaMemcpy(dfp, fp.data(), fp.size() * 4, cudaMemcpyHostToDevice));
@@ -115,7 +120,7 @@ static int run_pw(const char* name, const MaternMmaArgs& m, int reps, int sm_cou
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
   }
-  const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * 36 + 10);
+  const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * D + 10);
   printf("%-28s grid %6d  smem %6zu  %8.3f ms  %6.2f TFLOP/s   E(one launch) = %.9e\n", name, sm_count, smem, best,
          flop * (a.n_row_blocks * 8 / 1000.0) / best / 1e9, E);
 #ifdef PW_PROFILE
@@ -131,7 +136,7 @@ static int run_pw(const char* name, const MaternMmaArgs& m, int reps, int sm_cou
       }
     printf("   per warp (cycles, mean over %d warps): total %.0f  prologue %.0f  loop %.0f  epilogue %.0f  [acquire waits inside: %.0f]  items %.1f\n",
            n, tot / n, pro / n, loop / n, epi / n, acq / n, items / n);
-    printf("   per item: prologue %.0f  loop %.0f  epilogue %.0f (stage+reduce %.0f)  acquire wait %.0f cycles\n", pro / items, loop / items, epi / items, epi1 / items, acq / items);
+    printf("   per item: prologue %.0f  loop %.0f  epilogue %.0f (stage+reduce %.0f)  acquire %.0f cycles\n", pro / items, loop / items, epi / items, epi1 / items, acq / items);
     const long long* o = hp.data();
     for (int w = 0; w < nw_launch; ++w)
       printf("   CTA 0 warp %2d: total %lld pro %lld loop %lld epi %lld acq %lld items %lld\n", w, o[w * 8], o[w * 8 + 1], o[w * 8 + 2], o[w * 8 + 3], o[w * 8 + 4], o[w * 8 + 5]);
@@ -144,7 +149,7 @@ static int run_pw(const char* name, const MaternMmaArgs& m, int reps, int sm_cou
 int main(int argc, char** argv) {
   const long long n_frag = argc > 1 ? atoll(argv[1]) : 41664;
   const int T = argc > 2 ? atoi(argv[2]) : 1000;
-  constexpr int NA = 9, D = 36, P = 48;
+  constexpr int NA = H_NA, D = NA * (NA - 1) / 2, P = H_P, NM = NA / 3;
   const int n_atoms = 192;
   srand(1);
   std::vector<double> R((size_t)n_atoms * 3);
@@ -157,11 +162,15 @@ int main(int argc, char** argv) {
   std::vector<double> rec_lambda(n_frag, 1.0);
   std::vector<long long> rec_slot(n_frag);
   for (long long f = 0; f < n_frag; ++f) {
-    int m[3];
-    do {
-      m[0] = rand() % 64, m[1] = rand() % 64, m[2] = rand() % 64;
-    } while (m[0] == m[1] || m[0] == m[2] || m[1] == m[2]);
-    for (int k = 0; k < 3; ++k)
+    int m[NM];
+    for (int k = 0; k < NM; ++k) {
+      bool dup;
+      do {
+        m[k] = rand() % 64, dup = false;
+        for (int j = 0; j < k; ++j) dup |= m[j] == m[k];
+      } while (dup);
+    }
+    for (int k = 0; k < NM; ++k)
       for (int x = 0; x < 3; ++x) rec_atoms[f * NA + k * 3 + x] = m[k] * 3 + x;
     rec_slot[f] = f;
   }
@@ -216,7 +225,13 @@ int main(int argc, char** argv) {
 #ifdef EXP_NAME
   printf("experiment: %s\n", EXP_NAME);
 #endif
-#ifdef EXP_TWO_CTAS
+#if H_NA != 9
+  if (run<H_MT, 256, false>("wave 256 thr", a, 5)) return 1;
+  int sm_count_w = 0;
+  cudaDeviceGetAttribute(&sm_count_w, cudaDevAttrMultiProcessorCount, 0);
+  if (run_pw<H_MT, 8, false>("persistent 8 warps", a, 5, sm_count_w)) return 1;
+  return 0;
+#elif defined(EXP_TWO_CTAS)
   if (run<3, 192, true, 2>("MT=3 192 thr x 2 CTA/SM, y' smem", a, 5)) return 1;
 #else
   if (run<3, 256, false>("MT=3 256 thr", a, 5)) return 1;
