@@ -2215,6 +2215,19 @@ static void record_aux_launch(mbg_context_t ctx, cudaEvent_t e0, cudaEvent_t e1,
   ctx->launches++;
 }
 
+} // extern "C" (reopened below: the helper is a template)
+template <int NA>
+struct KmdPick {  // the tensor-pipe kernel-matrix kernel exists for fragments of up to 10 atoms (3N <= 32 lanes)
+  static void (*kern())(KernelMatArgs, long long) {
+    if constexpr (NA <= 10) return k_kernel_mat_d<NA>;
+    else return nullptr;
+  }
+  static size_t bytes(int nw, int P) {
+    if constexpr (NA <= 10) return KmdShape<NA>::bytes(nw, P);
+    else return ~(size_t)0;
+  }
+};
+extern "C" {
 int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double* R_desc,
                    const double* R_d_desc, const int64_t* tril_perms_lin, double sig, int32_t use_E_cstr,
                    uint32_t flags, double* K) {
@@ -2275,8 +2288,9 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
   CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   void (*kern)(KernelMatArgs) = nullptr;
   void (*kern_w)(KernelMatArgs, long long) = nullptr;
-  size_t smem = 0, smem_w4 = 0, smem_w = 0;
-  int nw = 0;
+  void (*kern_d)(KernelMatArgs, long long) = nullptr;
+  size_t smem = 0, smem_w4 = 0, smem_w = 0, smem_d = 0;
+  int nw = 0, nw_d = 0;
   switch (N) {
 #define X(NA_)                                                                                   \
   case NA_:                                                                                      \
@@ -2284,15 +2298,27 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
     kern_w = k_kernel_mat_w<NA_>, smem_w4 = KmwShape<NA_>::bytes(4, P);                          \
     for (nw = kKmwMaxWarps; nw > 4 && KmwShape<NA_>::bytes(nw, P) > (size_t)dev_smem; --nw) {}   \
     smem_w = KmwShape<NA_>::bytes(nw, P);                                                        \
+    kern_d = KmdPick<NA_>::kern();                                                               \
+    for (nw_d = kKmdMaxWarps; nw_d > 0 && KmdPick<NA_>::bytes(nw_d, P) > (size_t)dev_smem; --nw_d) {} \
+    smem_d = KmdPick<NA_>::bytes(nw_d, P);                                                       \
     break;
     MBG_FOR_EACH_NA(X)
 #undef X
     default: return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: no kernel for %d atoms", N);
   }
   // MBG_MMA_CFG=4 / 5 (developer): always CTA per pair / always warp per pair when it fits
-  const bool per_warp = smem_w4 <= (size_t)dev_smem && ctx->mma_cfg != 4 && (D <= 15 || ctx->mma_cfg == 5);
+  // tensor-pipe kernel (warp per pair, every sum a DMMA chain) for wider descriptors, up to 10 atoms; MBG_MMA_CFG=7
+  // (developer): whenever it exists
+  const bool tensor = kern_d && nw_d >= 4 && ctx->mma_cfg != 4 && ctx->mma_cfg != 5 && (D > 15 || ctx->mma_cfg == 7);
+  const bool per_warp = !tensor && smem_w4 <= (size_t)dev_smem && ctx->mma_cfg != 4 && (D <= 15 || ctx->mma_cfg == 5);
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
-  if (per_warp) {
+  if (tensor) {
+    CUDA_TRY(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+    const long long ctas = std::min<long long>((n_blocks + nw_d - 1) / nw_d, (long long)ctx->sm_count);
+    cudaEventRecord(e0, ctx->stream);
+    kern_d<<<(unsigned)ctas, nw_d * 32, smem_d, ctx->stream>>>(a, n_blocks);
+    cudaEventRecord(e1, ctx->stream);
+  } else if (per_warp) {
     CUDA_TRY(cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     const long long ctas = std::min<long long>((n_blocks + nw - 1) / nw, (long long)ctx->sm_count * 4);
     cudaEventRecord(e0, ctx->stream);

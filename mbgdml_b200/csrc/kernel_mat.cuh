@@ -432,6 +432,273 @@ __global__ void __launch_bounds__(kKmwMaxWarps * 32) k_kernel_mat_w(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Tensor-pipe form of the kernel-matrix assembly (round 2): a warp per pair, every D-wide or P-wide sum a chain of
+// DMMA m8n8k4 (the FP64 tensor pipe), no scatter.  With the DENSE Jacobians J_i, J_j (D x 3N, six non-zeros per
+// row, never stored: an operand fragment is a compare + select on the compressed G) and per 8 permutations (one
+// m-tile):
+//     U = Dif J_i            Dif[p][k] = X_i[k] - X_j[pi_p(k)]                    [8 x D] [D x 3N]
+//     V = Dif~ J_j           Dif~[p][k] = X_i[pi_p^-1(k)] - X_j[k]                (= (J_j[pi_p])^T diff_p, re-indexed)
+//     K += (5 b U)^T V                                                           [3N x 8] [8 x 3N]
+// and once per pair, with C[k][k'] = sum_{p: pi_p(k) = k'} c_p (D x D, built by row-owning lanes):
+//     W = C J_j              [D x D] [D x 3N]        K -= J_i^T W                [3N x D] [D x 3N]
+// Two passes over the permutations so that the accumulators of W and of K are never live together: pass 1 norms ->
+// b_p, c_p -> C -> W (to shared memory, over C), pass 2 U, V, rank-8 updates of K, then K -= J_i^T W.
+// Shared-memory strides are = 4 (mod 16) doubles: the (k = 4 kk + l, column 8 n + g) operand pattern of m8n8k4
+// then tiles the 32 banks exactly.  Same arithmetic as k_kernel_mat up to summation order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kKmdMaxWarps = 12;
+__host__ __device__ constexpr int kmd_pad4(int n) { return (n - 4 + 15) / 16 * 16 + 4; }  // smallest m >= n, m % 16 == 4
+__host__ __device__ constexpr int kmd_max(int a, int b) { return a > b ? a : b; }
+
+template <int NA>
+struct KmdShape {
+  static constexpr int N = NA, D = NA * (NA - 1) / 2, N3 = 3 * NA;
+  static constexpr int KS = (D + 3) / 4, NTc = (N3 + 7) / 8, MTk = (D + 7) / 8;
+  static constexpr int CS = kmd_pad4(4 * KS);   // row stride of C (columns k' < 4 KS)
+  static constexpr int WS = kmd_pad4(8 * NTc);  // row stride of W, U, V (columns < 8 NTc)
+  static constexpr int OS = N3 + 1;             // output staging
+  static constexpr int kRegion = kmd_max(kmd_max(MTk * 8 * CS, MTk * 8 * WS), N3 * OS);
+  __host__ __device__ static constexpr int p_pad(int P) { return (P + 7) / 8 * 8; }
+  // doubles per warp: Xi, Xj [4 KS]; gi, gj [D][3]; region (C, then W, then the output block); U, V [8][WS]; 5 b_p, c_p [P]
+  __host__ __device__ static constexpr int warp_doubles(int P) { return 8 * KS + 6 * D + kRegion + 16 * WS + 2 * p_pad(P); }
+  __host__ __device__ static constexpr bool tables_in_smem(int P) { return D <= 255 && 2 * P * D <= 16 * 1024; }
+  __host__ __device__ static constexpr size_t bytes(int nw, int P) {
+    return (size_t)nw * warp_doubles(P) * 8 + (tables_in_smem(P) ? (size_t)(2 * P * D + 7) / 8 * 8 : 0) + 16;
+  }
+};
+
+__device__ __forceinline__ void kmd_mma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NA>
+__global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __grid_constant__ KernelMatArgs a, const long long n_pairs) {
+  using S = KmdShape<NA>;
+  constexpr int D = S::D, N3 = S::N3, KS = S::KS, NTc = S::NTc, MTk = S::MTk, CS = S::CS, WS = S::WS, OS = S::OS;
+  static_assert(N3 <= 32, "one lane per energy-constraint entry");
+  extern __shared__ __align__(16) unsigned char kmd_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int g = lane >> 2, l = lane & 3;
+  const int P = a.P, Pp = S::p_pad(P);
+  const bool tabs = S::tables_in_smem(P);
+  double* wbase = reinterpret_cast<double*>(kmd_smem) + (size_t)warp * S::warp_doubles(P);
+  const unsigned char* tab_s = reinterpret_cast<unsigned char*>(reinterpret_cast<double*>(kmd_smem) + (size_t)nw * S::warp_doubles(P));
+  double* Xi = wbase;           // [4 KS], zero beyond D
+  double* Xj = Xi + 4 * KS;     // [4 KS]
+  double* gi = Xj + 4 * KS;     // [D][3]
+  double* gj = gi + 3 * D;      // [D][3]
+  double* reg = gj + 3 * D;     // C [8 MTk][CS] -> W [8 MTk][WS] -> output block [3N][OS]
+  double* Uc = reg + S::kRegion;  // [8][WS]  u_p of the current 8 permutations
+  double* Vc = Uc + 8 * WS;       // [8][WS]
+  double* fbs = Vc + 8 * WS;      // [Pp] 5 b_p (0 beyond P)
+  double* ccs = fbs + Pp;         // [Pp] c_p
+
+  if (tabs) {
+    unsigned char* t = const_cast<unsigned char*>(tab_s);
+    for (int k = tid; k < P * D; k += blockDim.x) t[k] = (unsigned char)a.pi[k], t[P * D + k] = (unsigned char)a.ipi[k];
+  }
+  __syncthreads();
+  auto pi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[p * D + k] : a.pi[(size_t)p * D + k]; };
+  auto ipi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[P * D + p * D + k] : a.ipi[(size_t)p * D + k]; };
+
+  // per-lane constants of the operand patterns: the two atoms of descriptor k = 4 kk + l, atom / axis of column 8 n + g
+  int pab[KS];  // larger atom | smaller atom << 8 | valid << 16
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    const int k = 4 * kk + l;
+    int hi = 1;
+    while ((hi + 1) * hi / 2 <= k) ++hi;
+    pab[kk] = k < D ? (hi | ((k - hi * (hi - 1) / 2) << 8) | 0x10000) : (0xff | (0xff << 8));
+  }
+  int cat[NTc];  // atom | axis << 8 of column 8 n + g (atom 0xfe beyond 3N: matches nothing)
+#pragma unroll
+  for (int n = 0; n < NTc; ++n) {
+    const int c = 8 * n + g;
+    cat[n] = c < N3 ? ((c / 3) | ((c % 3) << 8)) : 0xfe;
+  }
+  // J[k][column 8 n + g] for k = 4 kk + l from the compressed Jacobian G (+g at the smaller atom, -g at the larger)
+  auto jfrag = [&](const double* G3, const int kk, const int n) -> double {
+    const int at = cat[n] & 0xff, ax = cat[n] >> 8;
+    const int hi = pab[kk] & 0xff, lo = (pab[kk] >> 8) & 0xff;
+    const bool m_lo = at == lo, m_hi = at == hi;
+    double v = 0.0;
+    if (m_lo || m_hi) v = G3[(4 * kk + l) * 3 + ax];
+    return m_hi ? -v : v;
+  };
+
+  const double sig = a.sig, sqrt5 = sqrt(5.0);
+  const size_t E0 = (size_t)a.T * N3;
+
+  for (long long b = (long long)blockIdx.x * nw + warp; b < n_pairs; b += (long long)gridDim.x * nw) {
+    int i, j;
+    if (a.symmetric) {  // b = i (i + 1) / 2 + j, j <= i
+      i = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+      while ((long long)(i + 1) * (i + 2) / 2 <= b) ++i;
+      while ((long long)i * (i + 1) / 2 > b) --i;
+      j = (int)(b - (long long)i * (i + 1) / 2);
+    } else {
+      i = (int)(b % a.T), j = (int)(b / a.T);
+    }
+    __syncwarp();  // the previous pair's reads of this warp's slice are done
+    for (int k = lane; k < 4 * KS; k += 32) Xi[k] = k < D ? a.X[(size_t)i * D + k] : 0.0, Xj[k] = k < D ? a.X[(size_t)j * D + k] : 0.0;
+    for (int k = lane; k < 3 * D; k += 32) gi[k] = a.G[(size_t)i * 3 * D + k], gj[k] = a.G[(size_t)j * 3 * D + k];
+    for (int k = lane; k < MTk * 8 * CS; k += 32) reg[k] = 0.0;
+    __syncwarp();
+
+    // ---- pass 1: |diff_p|^2 -> 5 b_p, c_p, energy-energy term; four lanes per permutation ------------------------
+    double eacc = 0.0;
+    for (int p0 = 0; p0 < Pp; p0 += 8) {
+      const int p = p0 + g, pr = min(p, P - 1);
+      double s2 = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const int k = 4 * kk + l;
+        const double d = k < D ? Xi[k] - Xj[pi_at(pr, k)] : 0.0;
+        s2 = fma(d, d, s2);
+      }
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+      if (l == 0) {
+        const double n = sqrt5 * sqrt(s2);
+        const double ex = exp(-n / sig);
+        const double bq = ex / (3.0 * sig * sig * sig * sig) * 5.0;
+        const bool ok = p < P;
+        fbs[p] = ok ? 5.0 * bq : 0.0;
+        ccs[p] = ok ? (sig * sig + sig * n) * bq : 0.0;
+        if (ok) eacc -= (1.0 + (n / sig) * (1.0 + n / (3.0 * sig))) * ex;
+      }
+    }
+    __syncwarp();
+    // C[k][pi_p(k)] += c_p, row k owned by one lane
+    for (int k = lane; k < D; k += 32) {
+      double* row = reg + k * CS;
+      for (int p = 0; p < P; ++p) row[pi_at(p, k)] += ccs[p];
+    }
+    __syncwarp();
+    {  // W = C J_j (all of it in registers before the first store: W overwrites C)
+      double Wacc[MTk][NTc][2];
+#pragma unroll
+      for (int m = 0; m < MTk; ++m)
+#pragma unroll
+        for (int n = 0; n < NTc; ++n) Wacc[m][n][0] = 0.0, Wacc[m][n][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        double bj[NTc];
+#pragma unroll
+        for (int n = 0; n < NTc; ++n) bj[n] = jfrag(gj, kk, n);
+#pragma unroll
+        for (int m = 0; m < MTk; ++m) {
+          const double av = reg[(8 * m + g) * CS + 4 * kk + l];
+#pragma unroll
+          for (int n = 0; n < NTc; ++n) kmd_mma(Wacc[m][n][0], Wacc[m][n][1], av, bj[n]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < MTk; ++m)
+#pragma unroll
+        for (int n = 0; n < NTc; ++n)
+          *reinterpret_cast<double2*>(reg + (8 * m + g) * WS + 8 * n + 2 * l) = make_double2(Wacc[m][n][0], Wacc[m][n][1]);
+    }
+    __syncwarp();
+
+    // ---- pass 2: U, V of 8 permutations, rank-8 update of K -------------------------------------------------------
+    double Kacc[NTc][NTc][2];
+#pragma unroll
+    for (int m = 0; m < NTc; ++m)
+#pragma unroll
+      for (int n = 0; n < NTc; ++n) Kacc[m][n][0] = 0.0, Kacc[m][n][1] = 0.0;
+    double erow = 0.0, ecol = 0.0;  // lane e < 3N: -sum_p c_p v_p[e], +sum_p c_p u_p[e]
+    for (int p0 = 0; p0 < Pp; p0 += 8) {
+      const int pr = min(p0 + g, P - 1);
+      double Ua[NTc][2], Va[NTc][2];
+#pragma unroll
+      for (int n = 0; n < NTc; ++n) Ua[n][0] = 0.0, Ua[n][1] = 0.0, Va[n][0] = 0.0, Va[n][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const int k = 4 * kk + l;
+        const bool kv = k < D;
+        const double au = kv ? Xi[k] - Xj[pi_at(pr, k)] : 0.0;
+        const double av = kv ? Xi[ipi_at(pr, k)] - Xj[k] : 0.0;
+#pragma unroll
+        for (int n = 0; n < NTc; ++n) {
+          kmd_mma(Ua[n][0], Ua[n][1], au, jfrag(gi, kk, n));
+          kmd_mma(Va[n][0], Va[n][1], av, jfrag(gj, kk, n));
+        }
+      }
+      __syncwarp();  // the previous chunk's U, V are consumed
+#pragma unroll
+      for (int n = 0; n < NTc; ++n) {
+        *reinterpret_cast<double2*>(Uc + g * WS + 8 * n + 2 * l) = make_double2(Ua[n][0], Ua[n][1]);
+        *reinterpret_cast<double2*>(Vc + g * WS + 8 * n + 2 * l) = make_double2(Va[n][0], Va[n][1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int pl = 4 * k2 + l;
+        const double f = fbs[p0 + pl];
+        double ar[NTc], br[NTc];
+#pragma unroll
+        for (int m = 0; m < NTc; ++m) ar[m] = f * Uc[pl * WS + 8 * m + g], br[m] = Vc[pl * WS + 8 * m + g];
+#pragma unroll
+        for (int m = 0; m < NTc; ++m)
+#pragma unroll
+          for (int n = 0; n < NTc; ++n) kmd_mma(Kacc[m][n][0], Kacc[m][n][1], ar[m], br[n]);
+      }
+      if (a.use_E && lane < N3) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) erow = fma(-ccs[p0 + q], Vc[q * WS + lane], erow), ecol = fma(ccs[p0 + q], Uc[q * WS + lane], ecol);
+      }
+    }
+    // K -= J_i^T W
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      double ai[NTc], bw[NTc];
+#pragma unroll
+      for (int m = 0; m < NTc; ++m) ai[m] = -jfrag(gi, kk, m), bw[m] = reg[(4 * kk + l) * WS + 8 * m + g];
+#pragma unroll
+      for (int m = 0; m < NTc; ++m)
+#pragma unroll
+        for (int n = 0; n < NTc; ++n) kmd_mma(Kacc[m][n][0], Kacc[m][n][1], ai[m], bw[n]);
+    }
+    __syncwarp();  // W is consumed: the region becomes the output block
+#pragma unroll
+    for (int m = 0; m < NTc; ++m)
+#pragma unroll
+      for (int n = 0; n < NTc; ++n) {
+        const int r = 8 * m + g, c = 8 * n + 2 * l;
+        if (r < N3 && c < N3) reg[r * OS + c] = Kacc[m][n][0];
+        if (r < N3 && c + 1 < N3) reg[r * OS + c + 1] = Kacc[m][n][1];
+      }
+    __syncwarp();
+    double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+    double* Kji = a.K + ((size_t)j * N3) * a.ld + (size_t)i * N3;
+    for (int e = lane; e < N3 * N3; e += 32) {
+      const int r = e / N3, c = e - r * N3;
+      Kij[(size_t)r * a.ld + c] = reg[r * OS + c];
+      if (a.symmetric && i != j) Kji[(size_t)r * a.ld + c] = reg[c * OS + r];
+    }
+    if (a.use_E) {
+      eacc += __shfl_xor_sync(0xffffffffu, eacc, 4);
+      eacc += __shfl_xor_sync(0xffffffffu, eacc, 8);
+      eacc += __shfl_xor_sync(0xffffffffu, eacc, 16);
+      if (lane < N3) {
+        a.K[(E0 + i) * a.ld + (size_t)j * N3 + lane] = erow;  // train.py:224-239
+        a.K[((size_t)j * N3 + lane) * a.ld + E0 + i] = erow;  // train.py:262-287
+        if (a.symmetric && i != j) {
+          a.K[(E0 + j) * a.ld + (size_t)i * N3 + lane] = ecol;
+          a.K[((size_t)i * N3 + lane) * a.ld + E0 + j] = ecol;
+        }
+      }
+      if (lane == 0) {
+        a.K[(E0 + j) * a.ld + E0 + i] = eacc;  // train.py:287-289
+        if (a.symmetric && i != j) a.K[(E0 + i) * a.ld + E0 + j] = eacc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Matern-5/2 covariance of query structures vs. the permuted training rows (analysis/models.py:31-139).
 // out[m][t P + p] = (1 + s d + 5 d^2 / (3 sig^2)) exp(-s d),  d = |x_m - X_t[pi_p]| = |x_m[pi_p^-1] - X_t|.
 // One CTA per (query m, tile of kM52Rows training rows); thread <-> output (t, p), p fastest (coalesced).
