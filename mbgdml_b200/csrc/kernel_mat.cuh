@@ -459,6 +459,26 @@ struct KmdShape {
   static constexpr int OS = N3 + 1;             // output staging
   static constexpr int kRegion = kmd_max(kmd_max(MTk * 8 * CS, MTk * 8 * WS), N3 * OS);
   __host__ __device__ static constexpr int p_pad(int P) { return (P + 7) / 8 * 8; }
+  // bit kk NTc + n: the 4 x 8 fragment (descriptors 4 kk .. 4 kk + 3, columns 8 n .. 8 n + 7) of a dense Jacobian has a
+  // non-zero (row k <-> atoms hi > lo touches columns 3 hi .. 3 hi + 2 and 3 lo .. 3 lo + 2); trimers: 24 of 36
+  __host__ __device__ static constexpr unsigned long long nz_mask() {
+    unsigned long long m = 0;
+    for (int kk = 0; kk < KS; ++kk)
+      for (int n = 0; n < NTc; ++n) {
+        bool hit = false;
+        for (int k = 4 * kk; k < 4 * kk + 4 && k < D; ++k) {
+          int hi = 1;
+          while ((hi + 1) * hi / 2 <= k) ++hi;
+          const int lo = k - hi * (hi - 1) / 2;
+          for (int c = 8 * n; c < 8 * n + 8 && c < N3; ++c) hit = hit || c / 3 == hi || c / 3 == lo;
+        }
+        if (hit) m |= 1ull << (kk * NTc + n);
+      }
+    return m;
+  }
+  static constexpr unsigned long long kNz = nz_mask();
+  static_assert(KS * NTc <= 64, "fragment mask");
+  __host__ __device__ static constexpr bool nz(int kk, int n) { return (kNz >> (kk * NTc + n)) & 1ull; }
   // doubles per warp: Xi, Xj [4 KS]; gi, gj [D][3]; region (C, then W, then the output block); U, V [8][WS]; 5 b_p, c_p [P]
   __host__ __device__ static constexpr int warp_doubles(int P) { return 8 * KS + 6 * D + kRegion + 16 * WS + 2 * p_pad(P); }
   __host__ __device__ static constexpr bool tables_in_smem(int P) { return D <= 255 && 2 * P * D <= 16 * 1024; }
@@ -501,29 +521,30 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
   auto pi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[p * D + k] : a.pi[(size_t)p * D + k]; };
   auto ipi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[P * D + p * D + k] : a.ipi[(size_t)p * D + k]; };
 
-  // per-lane constants of the operand patterns: the two atoms of descriptor k = 4 kk + l, atom / axis of column 8 n + g
-  int pab[KS];  // larger atom | smaller atom << 8 | valid << 16
+  // Per-lane constants of the operand pattern J[k = 4 kk + l][column 8 n + g]: two bits per fragment (1: +G at the
+  // smaller atom of pair k, 2: -G at the larger, 0: zero) and the offset 3 l + axis of the column in a row of G.
+  unsigned long long codes[2] = {0ull, 0ull};
 #pragma unroll
   for (int kk = 0; kk < KS; ++kk) {
     const int k = 4 * kk + l;
     int hi = 1;
     while ((hi + 1) * hi / 2 <= k) ++hi;
-    pab[kk] = k < D ? (hi | ((k - hi * (hi - 1) / 2) << 8) | 0x10000) : (0xff | (0xff << 8));
-  }
-  int cat[NTc];  // atom | axis << 8 of column 8 n + g (atom 0xfe beyond 3N: matches nothing)
+    const int lo = k - hi * (hi - 1) / 2;
 #pragma unroll
-  for (int n = 0; n < NTc; ++n) {
-    const int c = 8 * n + g;
-    cat[n] = c < N3 ? ((c / 3) | ((c % 3) << 8)) : 0xfe;
+    for (int n = 0; n < NTc; ++n) {
+      const int c = 8 * n + g, at = c / 3;
+      if (k < D && c < N3 && S::nz(kk, n))
+        codes[(kk * NTc + n) >> 5] |= (unsigned long long)(at == lo ? 1 : (at == hi ? 2 : 0)) << (2 * ((kk * NTc + n) & 31));
+    }
   }
-  // J[k][column 8 n + g] for k = 4 kk + l from the compressed Jacobian G (+g at the smaller atom, -g at the larger)
-  auto jfrag = [&](const double* G3, const int kk, const int n) -> double {
-    const int at = cat[n] & 0xff, ax = cat[n] >> 8;
-    const int hi = pab[kk] & 0xff, lo = (pab[kk] >> 8) & 0xff;
-    const bool m_lo = at == lo, m_hi = at == hi;
+  int goff[NTc];
+#pragma unroll
+  for (int n = 0; n < NTc; ++n) goff[n] = 3 * l + (8 * n + g) % 3;
+  auto jfrag = [&](const double* G3, const int kk, const int n) -> double {  // kk, n: unrolled constants
+    const unsigned c = (unsigned)(codes[(kk * NTc + n) >> 5] >> (2 * ((kk * NTc + n) & 31))) & 3u;
     double v = 0.0;
-    if (m_lo || m_hi) v = G3[(4 * kk + l) * 3 + ax];
-    return m_hi ? -v : v;
+    if (c) v = G3[12 * kk + goff[n]];
+    return c == 2u ? -v : v;
   };
 
   const double sig = a.sig, sqrt5 = sqrt(5.0);
@@ -585,12 +606,13 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
       for (int kk = 0; kk < KS; ++kk) {
         double bj[NTc];
 #pragma unroll
-        for (int n = 0; n < NTc; ++n) bj[n] = jfrag(gj, kk, n);
+        for (int n = 0; n < NTc; ++n) bj[n] = S::nz(kk, n) ? jfrag(gj, kk, n) : 0.0;
 #pragma unroll
         for (int m = 0; m < MTk; ++m) {
           const double av = reg[(8 * m + g) * CS + 4 * kk + l];
 #pragma unroll
-          for (int n = 0; n < NTc; ++n) kmd_mma(Wacc[m][n][0], Wacc[m][n][1], av, bj[n]);
+          for (int n = 0; n < NTc; ++n)
+            if (S::nz(kk, n)) kmd_mma(Wacc[m][n][0], Wacc[m][n][1], av, bj[n]);
         }
       }
       __syncwarp();
@@ -621,10 +643,11 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
         const double au = kv ? Xi[k] - Xj[pi_at(pr, k)] : 0.0;
         const double av = kv ? Xi[ipi_at(pr, k)] - Xj[k] : 0.0;
 #pragma unroll
-        for (int n = 0; n < NTc; ++n) {
-          kmd_mma(Ua[n][0], Ua[n][1], au, jfrag(gi, kk, n));
-          kmd_mma(Va[n][0], Va[n][1], av, jfrag(gj, kk, n));
-        }
+        for (int n = 0; n < NTc; ++n)
+          if (S::nz(kk, n)) {
+            kmd_mma(Ua[n][0], Ua[n][1], au, jfrag(gi, kk, n));
+            kmd_mma(Va[n][0], Va[n][1], av, jfrag(gj, kk, n));
+          }
       }
       __syncwarp();  // the previous chunk's U, V are consumed
 #pragma unroll
@@ -655,11 +678,12 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
     for (int kk = 0; kk < KS; ++kk) {
       double ai[NTc], bw[NTc];
 #pragma unroll
-      for (int m = 0; m < NTc; ++m) ai[m] = -jfrag(gi, kk, m), bw[m] = reg[(4 * kk + l) * WS + 8 * m + g];
+      for (int m = 0; m < NTc; ++m) ai[m] = S::nz(kk, m) ? -jfrag(gi, kk, m) : 0.0, bw[m] = reg[(4 * kk + l) * WS + 8 * m + g];
 #pragma unroll
       for (int m = 0; m < NTc; ++m)
 #pragma unroll
-        for (int n = 0; n < NTc; ++n) kmd_mma(Kacc[m][n][0], Kacc[m][n][1], ai[m], bw[n]);
+        for (int n = 0; n < NTc; ++n)
+          if (S::nz(kk, m)) kmd_mma(Kacc[m][n][0], Kacc[m][n][1], ai[m], bw[n]);
     }
     __syncwarp();  // W is consumed: the region becomes the output block
 #pragma unroll
