@@ -122,7 +122,7 @@ struct mbg_context_s {
   Scratch scr;
   bool capturing = false;  // a step is being captured: no events, no launch records
   DevBuf R, outE, outF, outV, totals;
-  DevBuf km_in, km_ints, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
+  DevBuf km_in, km_ints, km_ints2, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
   std::vector<int> rec_chunk_slot;  // launch record -> chunk slot (fragment count resolved lazily), -1: count is exact
@@ -1475,7 +1475,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   ctx->tab.release();
   ctx->scr.release();
   for (DevBuf* b : {&ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->totals, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
-                    &ctx->deferred_totals, &ctx->km_ints, &ctx->km_out})
+                    &ctx->deferred_totals, &ctx->km_ints, &ctx->km_ints2, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ev_call0) cudaEventDestroy(ctx->ev_call0);
@@ -2223,7 +2223,7 @@ struct KmdPick {  // the tensor-pipe kernel-matrix kernel exists for fragments o
     else return nullptr;
   }
   static size_t bytes(int nw, int P) {
-    if constexpr (NA <= 10) return KmdShape<NA>::bytes(nw, P);
+    if constexpr (NA <= 10) return KmdShape<NA>::supported(P) ? KmdShape<NA>::bytes(nw, P) : ~(size_t)0;
     else return ~(size_t)0;
   }
 };
@@ -2279,6 +2279,7 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
   a.X = ctx->km_in.as<double>(), a.G = ctx->km_in.as<double>() + nX;
   a.pi = ctx->km_ints.as<int>(), a.ipi = ctx->km_ints.as<int>() + (size_t)P * D;
   a.K = dK, a.ld = (long long)rows;
+  a.srt_p = nullptr, a.srt_k = nullptr;
   const long long n_blocks = closed ? (long long)T * (T + 1) / 2 : (long long)T * T;
   if (n_blocks > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: too many blocks for one launch");
   // warp-per-pair kernel for narrow descriptors (D <= 15: measured 4.3x / 1.24x faster than CTA-per-pair for water
@@ -2309,10 +2310,22 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
   // MBG_MMA_CFG=4 / 5 (developer): always CTA per pair / always warp per pair when it fits
   // tensor-pipe kernel (warp per pair, every sum a DMMA chain) for wider descriptors, up to 10 atoms; MBG_MMA_CFG=7
   // (developer): whenever it exists
-  const bool tensor = kern_d && nw_d >= 4 && ctx->mma_cfg != 4 && ctx->mma_cfg != 5 && (D > 15 || ctx->mma_cfg == 7);
+  const bool tensor = kern_d && nw_d >= 4 && ctx->mma_cfg != 4 && ctx->mma_cfg != 5 && (D >= 10 || ctx->mma_cfg == 7);
   const bool per_warp = !tensor && smem_w4 <= (size_t)dev_smem && ctx->mma_cfg != 4 && (D <= 15 || ctx->mma_cfg == 5);
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   if (tensor) {
+    // per descriptor k: the permutations ordered by their image pi_p(k) (stable), for the scatter-free build of C
+    std::vector<int> srt((size_t)2 * P * D);
+    std::vector<int> order(P);
+    for (int k = 0; k < D; ++k) {
+      for (int q = 0; q < P; ++q) order[q] = q;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pi[(size_t)x * D + k] < pi[(size_t)y * D + k]; });
+      for (int t = 0; t < P; ++t) srt[(size_t)t * D + k] = order[t], srt[(size_t)P * D + (size_t)t * D + k] = pi[(size_t)order[t] * D + k];
+    }
+    TRY(ctx->km_ints2.ensure(srt.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->km_ints2.p, srt.data(), srt.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // srt is a local
+    a.srt_p = ctx->km_ints2.as<int>(), a.srt_k = ctx->km_ints2.as<int>() + (size_t)P * D;
     CUDA_TRY(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
     const long long ctas = std::min<long long>((n_blocks + nw_d - 1) / nw_d, (long long)ctx->sm_count);
     cudaEventRecord(e0, ctx->stream);

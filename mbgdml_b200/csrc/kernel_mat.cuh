@@ -37,6 +37,9 @@ struct KernelMatArgs {
   const int* ipi;    // [P][D]      pi_p^-1(k)
   double* K;         // [rows][rows], rows = T 3N (+ T)
   long long ld;      // rows
+  // tensor-pipe kernel only: for every descriptor k the permutations ordered by their image pi_p(k):
+  const int* srt_p;  // [P][D]  srt_p[t D + k] = the t-th permutation of row k
+  const int* srt_k;  // [P][D]  srt_k[t D + k] = its image pi_p(k) (ascending in t)
 };
 
 template <int NA>
@@ -457,7 +460,7 @@ struct KmdShape {
   static constexpr int CS = kmd_pad4(4 * KS);   // row stride of C (columns k' < 4 KS)
   static constexpr int WS = kmd_pad4(8 * NTc);  // row stride of W, U, V (columns < 8 NTc)
   static constexpr int OS = N3 + 1;             // output staging
-  static constexpr int kRegion = kmd_max(kmd_max(MTk * 8 * CS, MTk * 8 * WS), N3 * OS);
+  static constexpr int kRegion = kmd_max(kmd_max(4 * KS * CS, 4 * KS * WS), N3 * OS);  // rows k < 4 KS only
   __host__ __device__ static constexpr int p_pad(int P) { return (P + 7) / 8 * 8; }
   // bit kk NTc + n: the 4 x 8 fragment (descriptors 4 kk .. 4 kk + 3, columns 8 n .. 8 n + 7) of a dense Jacobian has a
   // non-zero (row k <-> atoms hi > lo touches columns 3 hi .. 3 hi + 2 and 3 lo .. 3 lo + 2); trimers: 24 of 36
@@ -481,9 +484,10 @@ struct KmdShape {
   __host__ __device__ static constexpr bool nz(int kk, int n) { return (kNz >> (kk * NTc + n)) & 1ull; }
   // doubles per warp: Xi, Xj [4 KS]; gi, gj [D][3]; region (C, then W, then the output block); U, V [8][WS]; 5 b_p, c_p [P]
   __host__ __device__ static constexpr int warp_doubles(int P) { return 8 * KS + 6 * D + kRegion + 16 * WS + 2 * p_pad(P); }
-  __host__ __device__ static constexpr bool tables_in_smem(int P) { return D <= 255 && 2 * P * D <= 16 * 1024; }
+  // the four byte tables (pi, pi^-1, srt_p, srt_k) live in shared memory: P <= 255 and 4 P D bytes
+  __host__ __device__ static constexpr bool supported(int P) { return P <= 255 && 4 * P * D <= 24 * 1024; }
   __host__ __device__ static constexpr size_t bytes(int nw, int P) {
-    return (size_t)nw * warp_doubles(P) * 8 + (tables_in_smem(P) ? (size_t)(2 * P * D + 7) / 8 * 8 : 0) + 16;
+    return (size_t)nw * warp_doubles(P) * 8 + (size_t)(4 * P * D + 7) / 8 * 8 + 16;
   }
 };
 
@@ -500,26 +504,27 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int g = lane >> 2, l = lane & 3;
   const int P = a.P, Pp = S::p_pad(P);
-  const bool tabs = S::tables_in_smem(P);
   double* wbase = reinterpret_cast<double*>(kmd_smem) + (size_t)warp * S::warp_doubles(P);
-  const unsigned char* tab_s = reinterpret_cast<unsigned char*>(reinterpret_cast<double*>(kmd_smem) + (size_t)nw * S::warp_doubles(P));
+  unsigned char* tab_s = reinterpret_cast<unsigned char*>(reinterpret_cast<double*>(kmd_smem) + (size_t)nw * S::warp_doubles(P));
   double* Xi = wbase;           // [4 KS], zero beyond D
   double* Xj = Xi + 4 * KS;     // [4 KS]
   double* gi = Xj + 4 * KS;     // [D][3]
   double* gj = gi + 3 * D;      // [D][3]
-  double* reg = gj + 3 * D;     // C [8 MTk][CS] -> W [8 MTk][WS] -> output block [3N][OS]
+  double* reg = gj + 3 * D;     // C [4 KS][CS] -> W [4 KS][WS] -> output block [3N][OS]
   double* Uc = reg + S::kRegion;  // [8][WS]  u_p of the current 8 permutations
   double* Vc = Uc + 8 * WS;       // [8][WS]
-  double* fbs = Vc + 8 * WS;      // [Pp] 5 b_p (0 beyond P)
+  double* fbs = Vc + 8 * WS;      // [Pp] |diff_p|^2, then 5 b_p (0 beyond P)
   double* ccs = fbs + Pp;         // [Pp] c_p
 
-  if (tabs) {
-    unsigned char* t = const_cast<unsigned char*>(tab_s);
-    for (int k = tid; k < P * D; k += blockDim.x) t[k] = (unsigned char)a.pi[k], t[P * D + k] = (unsigned char)a.ipi[k];
+  for (int k = tid; k < P * D; k += blockDim.x) {
+    tab_s[k] = (unsigned char)a.pi[k], tab_s[P * D + k] = (unsigned char)a.ipi[k];
+    tab_s[2 * P * D + k] = (unsigned char)a.srt_p[k], tab_s[3 * P * D + k] = (unsigned char)a.srt_k[k];
   }
   __syncthreads();
-  auto pi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[p * D + k] : a.pi[(size_t)p * D + k]; };
-  auto ipi_at = [&](const int p, const int k) -> int { return tabs ? (int)tab_s[P * D + p * D + k] : a.ipi[(size_t)p * D + k]; };
+  const unsigned char* pi_s = tab_s;
+  const unsigned char* ipi_s = tab_s + P * D;
+  const unsigned char* sp_s = tab_s + 2 * P * D;
+  const unsigned char* sk_s = tab_s + 3 * P * D;
 
   // Per-lane constants of the operand pattern J[k = 4 kk + l][column 8 n + g]: two bits per fragment (1: +G at the
   // smaller atom of pair k, 2: -G at the larger, 0: zero) and the offset 3 l + axis of the column in a row of G.
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
   };
 
   const double sig = a.sig, sqrt5 = sqrt(5.0);
+  const double inv_sig = 1.0 / sig, inv_3sig = 1.0 / (3.0 * sig), b_scale = 5.0 / (3.0 * sig * sig * sig * sig);
   const size_t E0 = (size_t)a.T * N3;
 
   for (long long b = (long long)blockIdx.x * nw + warp; b < n_pairs; b += (long long)gridDim.x * nw) {
@@ -563,37 +569,48 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
     __syncwarp();  // the previous pair's reads of this warp's slice are done
     for (int k = lane; k < 4 * KS; k += 32) Xi[k] = k < D ? a.X[(size_t)i * D + k] : 0.0, Xj[k] = k < D ? a.X[(size_t)j * D + k] : 0.0;
     for (int k = lane; k < 3 * D; k += 32) gi[k] = a.G[(size_t)i * 3 * D + k], gj[k] = a.G[(size_t)j * 3 * D + k];
-    for (int k = lane; k < MTk * 8 * CS; k += 32) reg[k] = 0.0;
+    for (int k = lane; k < 4 * KS * CS; k += 32) reg[k] = 0.0;
     __syncwarp();
 
-    // ---- pass 1: |diff_p|^2 -> 5 b_p, c_p, energy-energy term; four lanes per permutation ------------------------
-    double eacc = 0.0;
+    // ---- pass 1: |diff_p|^2 (four lanes per permutation), then 5 b_p, c_p and the energy-energy term per lane -----
     for (int p0 = 0; p0 < Pp; p0 += 8) {
-      const int p = p0 + g, pr = min(p, P - 1);
+      const unsigned char* pr = pi_s + min(p0 + g, P - 1) * D;
       double s2 = 0.0;
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
         const int k = 4 * kk + l;
-        const double d = k < D ? Xi[k] - Xj[pi_at(pr, k)] : 0.0;
+        const double d = k < D ? Xi[k] - Xj[pr[k]] : 0.0;
         s2 = fma(d, d, s2);
       }
       s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
       s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-      if (l == 0) {
-        const double n = sqrt5 * sqrt(s2);
-        const double ex = exp(-n / sig);
-        const double bq = ex / (3.0 * sig * sig * sig * sig) * 5.0;
-        const bool ok = p < P;
-        fbs[p] = ok ? 5.0 * bq : 0.0;
-        ccs[p] = ok ? (sig * sig + sig * n) * bq : 0.0;
-        if (ok) eacc -= (1.0 + (n / sig) * (1.0 + n / (3.0 * sig))) * ex;
-      }
+      if (l == 0) fbs[p0 + g] = s2;
     }
     __syncwarp();
-    // C[k][pi_p(k)] += c_p, row k owned by one lane
+    double eacc = 0.0;
+    for (int p = lane; p < Pp; p += 32) {
+      const double n = sqrt5 * sqrt(fbs[p]);
+      const double ex = exp(-n * inv_sig);
+      const double bq = ex * b_scale;  // 5 / (3 sig^4)
+      const bool ok = p < P;
+      fbs[p] = ok ? 5.0 * bq : 0.0;
+      ccs[p] = ok ? (sig * sig + sig * n) * bq : 0.0;
+      if (ok) eacc -= (1.0 + (n * inv_sig) * (1.0 + n * inv_3sig)) * ex;
+    }
+    __syncwarp();
+    // C[k][k'] = sum_{p: pi_p(k) = k'} c_p: the lane owning row k walks its permutations in the order of their images
+    // (host-sorted), sums each run in a register and stores it once -- no read-modify-write on shared memory
     for (int k = lane; k < D; k += 32) {
       double* row = reg + k * CS;
-      for (int p = 0; p < P; ++p) row[pi_at(p, k)] += ccs[p];
+      double acc = 0.0;
+      int prev = sk_s[k];
+      for (int t = 0; t < P; ++t) {
+        const int k2 = sk_s[t * D + k];
+        const double c = ccs[sp_s[t * D + k]];
+        if (k2 != prev) row[prev] = acc, acc = 0.0, prev = k2;
+        acc += c;
+      }
+      row[prev] = acc;
     }
     __syncwarp();
     {  // W = C J_j (all of it in registers before the first store: W overwrites C)
@@ -609,7 +626,7 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
         for (int n = 0; n < NTc; ++n) bj[n] = S::nz(kk, n) ? jfrag(gj, kk, n) : 0.0;
 #pragma unroll
         for (int m = 0; m < MTk; ++m) {
-          const double av = reg[(8 * m + g) * CS + 4 * kk + l];
+          const double av = (8 * m + g < 4 * KS) ? reg[(8 * m + g) * CS + 4 * kk + l] : 0.0;
 #pragma unroll
           for (int n = 0; n < NTc; ++n)
             if (S::nz(kk, n)) kmd_mma(Wacc[m][n][0], Wacc[m][n][1], av, bj[n]);
@@ -620,7 +637,7 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
       for (int m = 0; m < MTk; ++m)
 #pragma unroll
         for (int n = 0; n < NTc; ++n)
-          *reinterpret_cast<double2*>(reg + (8 * m + g) * WS + 8 * n + 2 * l) = make_double2(Wacc[m][n][0], Wacc[m][n][1]);
+          if (8 * m + g < 4 * KS) *reinterpret_cast<double2*>(reg + (8 * m + g) * WS + 8 * n + 2 * l) = make_double2(Wacc[m][n][0], Wacc[m][n][1]);
     }
     __syncwarp();
 
@@ -632,7 +649,8 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
       for (int n = 0; n < NTc; ++n) Kacc[m][n][0] = 0.0, Kacc[m][n][1] = 0.0;
     double erow = 0.0, ecol = 0.0;  // lane e < 3N: -sum_p c_p v_p[e], +sum_p c_p u_p[e]
     for (int p0 = 0; p0 < Pp; p0 += 8) {
-      const int pr = min(p0 + g, P - 1);
+      const unsigned char* pr = pi_s + min(p0 + g, P - 1) * D;
+      const unsigned char* ipr = ipi_s + min(p0 + g, P - 1) * D;
       double Ua[NTc][2], Va[NTc][2];
 #pragma unroll
       for (int n = 0; n < NTc; ++n) Ua[n][0] = 0.0, Ua[n][1] = 0.0, Va[n][0] = 0.0, Va[n][1] = 0.0;
@@ -640,8 +658,8 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
       for (int kk = 0; kk < KS; ++kk) {
         const int k = 4 * kk + l;
         const bool kv = k < D;
-        const double au = kv ? Xi[k] - Xj[pi_at(pr, k)] : 0.0;
-        const double av = kv ? Xi[ipi_at(pr, k)] - Xj[k] : 0.0;
+        const double au = kv ? Xi[k] - Xj[pr[k]] : 0.0;
+        const double av = kv ? Xi[ipr[k]] - Xj[k] : 0.0;
 #pragma unroll
         for (int n = 0; n < NTc; ++n)
           if (S::nz(kk, n)) {
@@ -703,9 +721,8 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
       if (a.symmetric && i != j) Kji[(size_t)r * a.ld + c] = reg[c * OS + r];
     }
     if (a.use_E) {
-      eacc += __shfl_xor_sync(0xffffffffu, eacc, 4);
-      eacc += __shfl_xor_sync(0xffffffffu, eacc, 8);
-      eacc += __shfl_xor_sync(0xffffffffu, eacc, 16);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) eacc += __shfl_xor_sync(0xffffffffu, eacc, o);
       if (lane < N3) {
         a.K[(E0 + i) * a.ld + (size_t)j * N3 + lane] = erow;  // train.py:224-239
         a.K[((size_t)j * N3 + lane) * a.ld + E0 + i] = erow;  // train.py:262-287
