@@ -459,8 +459,8 @@ struct KmdShape {
   static constexpr int KS = (D + 3) / 4, NTc = (N3 + 7) / 8, MTk = (D + 7) / 8;
   static constexpr int CS = kmd_pad4(4 * KS);   // row stride of C (columns k' < 4 KS)
   static constexpr int WS = kmd_pad4(8 * NTc);  // row stride of W, U, V (columns < 8 NTc)
-  static constexpr int OS = N3 + 1;             // output staging
-  static constexpr int kRegion = kmd_max(kmd_max(4 * KS * CS, 4 * KS * WS), N3 * OS);  // rows k < 4 KS only
+  static constexpr int OS = N3 | 1;             // output staging: odd stride, rows and columns both conflict-free
+  static constexpr int kRegion = (kmd_max(kmd_max(4 * KS * CS, 4 * KS * WS), N3 * OS) + 1) & ~1;  // rows k < 4 KS only; even: 16-byte alignment of what follows
   __host__ __device__ static constexpr int p_pad(int P) { return (P + 7) / 8 * 8; }
   // bit kk NTc + n: the 4 x 8 fragment (descriptors 4 kk .. 4 kk + 3, columns 8 n .. 8 n + 7) of a dense Jacobian has a
   // non-zero (row k <-> atoms hi > lo touches columns 3 hi .. 3 hi + 2 and 3 lo .. 3 lo + 2); trimers: 24 of 36
@@ -556,6 +556,8 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
   const double inv_sig = 1.0 / sig, inv_3sig = 1.0 / (3.0 * sig), b_scale = 5.0 / (3.0 * sig * sig * sig * sig);
   const size_t E0 = (size_t)a.T * N3;
 
+  // pairs strided over the warps: the warps of a CTA work on neighbouring blocks of K at any time (measured: a
+  // contiguous range per warp, which would keep X_i, G_i in shared memory, is 3 % slower: 1776 separate write streams)
   for (long long b = (long long)blockIdx.x * nw + warp; b < n_pairs; b += (long long)gridDim.x * nw) {
     int i, j;
     if (a.symmetric) {  // b = i (i + 1) / 2 + j, j <= i
