@@ -526,9 +526,11 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
   const unsigned char* sp_s = tab_s + 2 * P * D;
   const unsigned char* sk_s = tab_s + 3 * P * D;
 
-  // Per-lane constants of the operand pattern J[k = 4 kk + l][column 8 n + g]: two bits per fragment (1: +G at the
-  // smaller atom of pair k, 2: -G at the larger, 0: zero) and the offset 3 l + axis of the column in a row of G.
-  unsigned long long codes[2] = {0ull, 0ull};
+  // Per-lane constants of the operand pattern J[k = 4 kk + l][column 8 n + g]: per fragment f = kk NTc + n one bit
+  // "non-zero" (the column's atom is one of the two atoms of pair k) and one bit "negative" (it is the larger one:
+  // -G there, +G at the smaller), and the offset 3 l + axis of the column in a row of G.  The sign is applied to
+  // the high word with integer logic: a DADD per fragment on the pipe the DMMAs need costs more than it looks.
+  unsigned long long nzw = 0ull, sgw = 0ull;
 #pragma unroll
   for (int kk = 0; kk < KS; ++kk) {
     const int k = 4 * kk + l;
@@ -538,18 +540,21 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
 #pragma unroll
     for (int n = 0; n < NTc; ++n) {
       const int c = 8 * n + g, at = c / 3;
-      if (k < D && c < N3 && S::nz(kk, n))
-        codes[(kk * NTc + n) >> 5] |= (unsigned long long)(at == lo ? 1 : (at == hi ? 2 : 0)) << (2 * ((kk * NTc + n) & 31));
+      if (k < D && c < N3 && S::nz(kk, n)) {
+        if (at == lo || at == hi) nzw |= 1ull << (kk * NTc + n);
+        if (at == hi) sgw |= 1ull << (kk * NTc + n);
+      }
     }
   }
   int goff[NTc];
 #pragma unroll
   for (int n = 0; n < NTc; ++n) goff[n] = 3 * l + (8 * n + g) % 3;
   auto jfrag = [&](const double* G3, const int kk, const int n) -> double {  // kk, n: unrolled constants
-    const unsigned c = (unsigned)(codes[(kk * NTc + n) >> 5] >> (2 * ((kk * NTc + n) & 31))) & 3u;
+    const int f = kk * NTc + n;
     double v = 0.0;
-    if (c) v = G3[12 * kk + goff[n]];
-    return c == 2u ? -v : v;
+    if ((nzw >> f) & 1ull) v = G3[12 * kk + goff[n]];
+    const int hw = __double2hiint(v) ^ (int)(((unsigned)(sgw >> f) & 1u) << 31);
+    return __hiloint2double(hw, __double2loint(v));
   };
 
   const double sig = a.sig, sqrt5 = sqrt(5.0);
@@ -602,7 +607,8 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
     __syncwarp();
     // C[k][k'] = sum_{p: pi_p(k) = k'} c_p: the lane owning row k walks its permutations in the order of their images
     // (host-sorted), sums each run in a register and stores it once -- no read-modify-write on shared memory
-    for (int k = lane; k < D; k += 32) {
+    if (lane < D) {
+      const int k = lane;
       double* row = reg + k * CS;
       double acc = 0.0;
       int prev = sk_s[k];
@@ -613,6 +619,24 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
         acc += c;
       }
       row[prev] = acc;
+    }
+    if (D > 32) {  // rows 32 .. D - 1: LPR lanes per row, each a slice of the sorted list; runs cut by a slice meet in an atomic
+      constexpr int XR = D > 32 ? D - 32 : 1;
+      constexpr int LPR = XR <= 1 ? 32 : XR <= 2 ? 16 : XR <= 4 ? 8 : XR <= 8 ? 4 : XR <= 16 ? 2 : 1;
+      const int k = 32 + lane / LPR, q = lane % LPR, len = (P + LPR - 1) / LPR;
+      const int t0 = q * len, t1 = min(P, t0 + len);
+      if (k < D && t0 < t1) {
+        double* row = reg + k * CS;
+        double acc = 0.0;
+        int prev = sk_s[t0 * D + k];
+        for (int t = t0; t < t1; ++t) {
+          const int k2 = sk_s[t * D + k];
+          const double c = ccs[sp_s[t * D + k]];
+          if (k2 != prev) atomicAdd(row + prev, acc), acc = 0.0, prev = k2;
+          acc += c;
+        }
+        atomicAdd(row + prev, acc);
+      }
     }
     __syncwarp();
     {  // W = C J_j (all of it in registers before the first store: W overwrites C)
