@@ -1193,6 +1193,8 @@ static void resolve_timing(mbg_context_t ctx) {
 // ------------------------------------------------------------------------------------
 // Prepared steps: fixed (system, jobs, frame count), device-resident tables, the whole evaluation in one CUDA graph
 // ------------------------------------------------------------------------------------
+constexpr size_t kStepDirectCopyBytes = 1u << 20;  // mbg_step_run: coordinate sets from this size on skip the pinned mirrors
+
 struct mbg_step_s {
   mbg_context_t ctx = nullptr;
   int n_atoms = 0, n_frames = 0, n_jobs = 0, n_cells = 0;
@@ -1343,7 +1345,11 @@ extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells,
   mbg_context_t ctx = st->ctx;
   CUDA_TRY(cudaSetDevice(ctx->device));
   const size_t nR = (size_t)st->n_frames * st->n_atoms * 3;
-  memcpy(st->h_R, R, nR * sizeof(double));
+  // Small systems (MD frames) go through the step's own pinned mirrors inside ONE graph launch (lowest latency);
+  // large coordinate sets are copied straight between the caller's buffers and the device around the device-only
+  // graph: two host memcpy passes over megabytes cost more than the extra stream operations.
+  const bool direct = nR * sizeof(double) >= kStepDirectCopyBytes;
+  if (!direct) memcpy(st->h_R, R, nR * sizeof(double));
   if (cells) {
     if (!st->n_cells) return fail(MBG_ERR_ARG, "the step was created without a periodic cell");
     if (!cutoffs) return fail(MBG_ERR_ARG, "cells without cutoffs");
@@ -1351,12 +1357,22 @@ extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells,
       if (memcmp(st->h_cells[c].cell, cells + 9 * (size_t)c, 9 * sizeof(double)) != 0 || st->h_cells[c].cutoff != cutoffs[c])
         TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c]));
   }
-  CUDA_TRY(cudaGraphLaunch(st->exec, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->launches += 0;  // (graph launches replay the kernels counted at capture time)
-  memcpy(E, st->h_out, (size_t)st->n_frames * sizeof(double));
-  memcpy(F, st->h_out + st->n_frames, nR * sizeof(double));
-  if (st->want_virial) memcpy(virial, st->h_out + st->n_frames + nR, (size_t)st->n_frames * 9 * sizeof(double));
+  if (direct) {
+    const double* o = st->dOut.as<double>();
+    CUDA_TRY(cudaMemcpyAsync(st->dR.p, R, nR * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaGraphLaunch(st->exec_dev, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(E, o, (size_t)st->n_frames * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(F, o + st->n_frames, nR * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (st->want_virial)
+      CUDA_TRY(cudaMemcpyAsync(virial, o + st->n_frames + nR, (size_t)st->n_frames * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  } else {
+    CUDA_TRY(cudaGraphLaunch(st->exec, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(E, st->h_out, (size_t)st->n_frames * sizeof(double));
+    memcpy(F, st->h_out + st->n_frames, nR * sizeof(double));
+    if (st->want_virial) memcpy(virial, st->h_out + st->n_frames + nR, (size_t)st->n_frames * 9 * sizeof(double));
+  }
   if (stats)
     for (int k = 0; k < st->n_jobs; ++k) {
       stats[k].n_candidates = st->n_candidates[k];
