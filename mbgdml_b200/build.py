@@ -14,6 +14,9 @@ SOURCES = ["api.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",
+    # the CUDA runtime as a shared library (the process usually has one already: torch's): the shipped binary then
+    # carries only the runtime entry points it calls
+    "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 
