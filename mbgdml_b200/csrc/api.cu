@@ -349,6 +349,8 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
 }
 
 
+constexpr long long kSmallMinQueries = 48 * 1024;  // k_matern_small from this many queries (fragments x permutations) on
+
 // Persistent per-warp form of the tensor-pipe contraction (matern_pw.cuh): always one CTA per SM; the kernel reads
 // the fragment count on the device, so the launch shape never depends on it.
 template <int NA, int MT, int NW, bool USE_E, bool YS>
@@ -934,7 +936,11 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
                                                                          out.E, out.F, totals);
       ctx->launches++;
     }
-    if (NA <= 4 && ctx->mma_cfg != 6) {  // narrow descriptors: thread-per-query FMA-pipe kernel (MBG_MMA_CFG=6: off)
+    // Narrow descriptors: thread-per-query FMA-pipe kernel (MBG_MMA_CFG=6: off).  A thread walks all T P training rows
+    // for its query, a latency floor of ~0.19 ms (T P = 2000) that only pays once there are enough queries to fill
+    // the machine: below kSmallMinQueries (upper bound of this launch) the persistent tensor-pipe kernel is quicker
+    // (16 monomers: 0.03 ms; measured crossover ~47 k queries).
+    if (NA <= 4 && ctx->mma_cfg != 6 && (n_up * m->P >= kSmallMinQueries || ctx->mma_cfg == 8)) {  // 8 (developer): always
       MaternSmallArgs q;
       q.sys = s, q.R = dR;
       q.XA = m->XA, q.alphaE = m->alphaE, q.exp2_table = ctx->exp2_table_mma.as<double>();
