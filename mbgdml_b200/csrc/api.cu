@@ -2377,13 +2377,14 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
 
 static int launch_mat52(mbg_context_t ctx, Mat52Args a, int64_t n_q, int na_rec) {
   if (n_q > 65535) return fail(MBG_ERR_UNSUPPORTED, "covariance: more than 65535 query structures per call");
-  a.stage_perms = mat52_smem_bytes(a.D, a.P, true) <= 96 * 1024 ? 1 : 0;  // two CTAs per SM at least
-  const size_t smem = mat52_smem_bytes(a.D, a.P, a.stage_perms != 0);
+  a.rows_per_tile = mat52_rows_per_tile(a.D, a.P, a.T);
+  a.stage_perms = mat52_smem_bytes(a.D, a.P, true, a.rows_per_tile) <= 96 * 1024 ? 1 : 0;  // two CTAs per SM at least
+  const size_t smem = mat52_smem_bytes(a.D, a.P, a.stage_perms != 0, a.rows_per_tile);
   if (smem > 200 * 1024) return fail(MBG_ERR_UNSUPPORTED, "covariance: descriptor dimension %d too large", a.D);
   CUDA_TRY(cudaFuncSetAttribute(k_mat52, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
   cudaEventRecord(e0, ctx->stream);
-  k_mat52<<<dim3((a.T + kM52Rows - 1) / kM52Rows, (unsigned)n_q), kM52Threads, smem, ctx->stream>>>(a);
+  k_mat52<<<dim3((a.T + a.rows_per_tile - 1) / a.rows_per_tile, (unsigned)n_q), kM52Threads, smem, ctx->stream>>>(a);
   cudaEventRecord(e1, ctx->stream);
   CUDA_TRY(cudaGetLastError());
   record_aux_launch(ctx, e0, e1, na_rec, (long long)n_q * a.T * a.P, a.T, a.P, 3);

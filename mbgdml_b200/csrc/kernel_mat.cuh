@@ -783,24 +783,36 @@ struct Mat52Args {
   int x_elem_stride;
   const int* iperm;       // [P][D] pi_p^-1, or NULL for the identity (P must be 1)
   int stage_perms;        // 1: the P permuted copies of the query fit shared memory (mat52_smem_bytes)
+  int rows_per_tile;      // training rows per CTA (>= kM52Rows; more for narrow descriptors / few permutations, so that a
+                          // CTA has ~2000 outputs per query whatever the fragment size)
   double* out;            // [n_q][T * P]
 };
 
 // bytes of shared memory: query descriptor, row tile, and (when it fits) the P permuted copies of the query
-__host__ __device__ inline size_t mat52_smem_bytes(int D, int P, bool stage_perms) {
-  return ((size_t)D + (size_t)kM52Rows * (D + 1) + (stage_perms ? (size_t)P * (D | 1) : 0)) * sizeof(double);
+__host__ __device__ inline size_t mat52_smem_bytes(int D, int P, bool stage_perms, int rows_per_tile = kM52Rows) {
+  return ((size_t)D + (size_t)rows_per_tile * (D + 1) + (stage_perms ? (size_t)P * (D | 1) : 0)) * sizeof(double);
+}
+// rows per CTA: ~2048 outputs per query and CTA, the row tile at most 48 KB
+__host__ inline int mat52_rows_per_tile(int D, int P, int T) {
+  int rows = (2048 + P - 1) / P;
+  rows = rows < kM52Rows ? kM52Rows : rows;
+  const int cap = (48 * 1024) / ((D + 1) * 8);
+  rows = rows > cap ? cap : rows;
+  rows = rows < kM52Rows ? kM52Rows : rows;
+  return rows > T ? (T > kM52Rows ? T : kM52Rows) : rows;
 }
 
 __global__ void __launch_bounds__(kM52Threads) k_mat52(const __grid_constant__ Mat52Args a) {
   extern __shared__ __align__(16) unsigned char m52_smem[];
   const int D = a.D, P = a.P, N = a.n_atoms;
-  const int m = blockIdx.y, t0 = blockIdx.x * kM52Rows;
-  const int nrow = min(kM52Rows, a.T - t0);
+  const int RPT = a.rows_per_tile;
+  const int m = blockIdx.y, t0 = blockIdx.x * RPT;
+  const int nrow = min(RPT, a.T - t0);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int DQ = D | 1;                              // odd pitch: lanes with consecutive p hit different banks
   double* xq = reinterpret_cast<double*>(m52_smem);  // [D]
-  double* Xs = xq + D;                               // [kM52Rows][D + 1]
-  double* yq = Xs + kM52Rows * (D + 1);              // [P][DQ] permuted queries y_p[e] = x[pi_p^-1(e)] (stage_perms)
+  double* Xs = xq + D;                               // [RPT][D + 1]
+  double* yq = Xs + RPT * (D + 1);                   // [P][DQ] permuted queries y_p[e] = x[pi_p^-1(e)] (stage_perms)
   for (int k = tid; k < D; k += nt) {
     if (a.q_is_desc) {
       xq[k] = a.Q[(size_t)m * D + k];
@@ -829,25 +841,46 @@ __global__ void __launch_bounds__(kM52Threads) k_mat52(const __grid_constant__ M
   }
   const double sig = a.sig;
   const double s5 = sqrt(5.0) / sig, q2 = 5.0 / (3.0 * sig * sig);
-  for (int idx = tid; idx < nrow * P; idx += nt) {
-    const int tl = idx / P, p = idx - tl * P;
-    const double* xr = Xs + tl * (D + 1);
-    double s = 0.0;
+  // thread <-> (4 consecutive training rows, permutation p): the permuted query element is read once for 4 outputs
+  // (the kernel is bound by shared-memory wavefronts: ncu r2, 88 % of peak with one row per thread)
+  constexpr int RB = 4;
+  const int ngrp = (nrow + RB - 1) / RB;
+  for (int idx = tid; idx < ngrp * P; idx += nt) {
+    const int tg = idx / P, p = idx - tg * P;
+    const int tl0 = tg * RB;
+    const double* xr[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) xr[r] = Xs + min(tl0 + r, nrow - 1) * (D + 1);
+    double s[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) s[r] = 0.0;
     if (a.stage_perms) {
       const double* yp = yq + p * DQ;
       for (int e = 0; e < D; ++e) {
-        const double d = yp[e] - xr[e];
-        s = fma(d, d, s);
+        const double y = yp[e];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const double d = y - xr[r][e];
+          s[r] = fma(d, d, s[r]);
+        }
       }
     } else {
       const int* ip = a.iperm ? a.iperm + (size_t)p * D : nullptr;
       for (int e = 0; e < D; ++e) {
-        const double d = xq[ip ? ip[e] : e] - xr[e];
-        s = fma(d, d, s);
+        const double y = xq[ip ? ip[e] : e];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const double d = y - xr[r][e];
+          s[r] = fma(d, d, s[r]);
+        }
       }
     }
-    const double d = sqrt(s);
-    a.out[(size_t)m * a.T * P + (size_t)(t0 + tl) * P + p] = (1.0 + s5 * d + q2 * s) * exp(-s5 * d);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (tl0 + r >= nrow) break;
+      const double d = sqrt(s[r]);
+      a.out[(size_t)m * a.T * P + (size_t)(t0 + tl0 + r) * P + p] = (1.0 + s5 * d + q2 * s[r]) * exp(-s5 * d);
+    }
   }
 }
 
