@@ -261,6 +261,15 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
                    const double *R_d_desc, const int64_t *tril_perms_lin, double sig, int32_t use_E_cstr,
                    uint32_t flags, double *K);
 
+/* GDMLTrain._assemble_kernel_mat with a column subset (col_idxs, train.py:1105-1115, 1187-1245; what the iterative
+ * solver's preconditioner asks for): the column BLOCKS col_blocks[n_col_blocks] (training points j, any order, no
+ * energy constraints) against all training points i  ->  K[n_train*3*n_atoms][n_col_blocks*3*n_atoms] row-major,
+ * block (i, jj) = the (i, col_blocks[jj]) block of the full matrix.  The Python mirror gathers individual columns from
+ * it on the device.  Flags: MBG_FLAG_OUT_ON_DEVICE. */
+int mbg_kernel_mat_cols(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double *R_desc,
+                        const double *R_d_desc, const int64_t *tril_perms_lin, double sig, const int32_t *col_blocks,
+                        int32_t n_col_blocks, uint32_t flags, double *K);
+
 /* analysis.models.gdml_mat52 (reference mbgdml/analysis/models.py:84-139): Matern-5/2 covariances between
  * n_R structures R[n_R][model n_atoms][3] and the T*P permuted training descriptors of `model`, in the row
  * order of gdmlModel.R_desc_perms (row t*P + p, gdml_model.py:109-113): out[n_R][T*P].

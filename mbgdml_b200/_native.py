@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_step_create", "mbg_step_run",
     "mbg_step_run_device", "mbg_step_stats", "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
     "mbg_from_r", "mbg_criteria_eval", "mbg_r_mic", "mbg_d_mic", "mbg_mbe_accumulate", "mbg_measure_fp64_peak", "mbg_measure_fp64_tensor_peak", "mbg_measure_exp_sqrt_rate",
-    "mbg_kernel_mat", "mbg_mat52", "mbg_mat52_rows",
+    "mbg_kernel_mat", "mbg_kernel_mat_cols", "mbg_mat52", "mbg_mat52_rows",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -122,6 +122,8 @@ def load_library():
                                            C.c_int32, _ip, _ip, _dp, _dp, C.c_int64, C.c_double, _dp, _dp, C.c_int64]
         lib.mbg_kernel_mat.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _lp, C.c_double, C.c_int32,
                                        C.c_uint32, C.c_void_p]
+        lib.mbg_kernel_mat_cols.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _lp, C.c_double, _ip,
+                                            C.c_int32, C.c_uint32, C.c_void_p]
         lib.mbg_mat52.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p]
         lib.mbg_mat52_rows.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int64, C.c_double, _dp, C.c_int64, _dp]
         lib.mbg_measure_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
@@ -337,6 +339,27 @@ class Context:
             K, dst, flags = None, int(out), FLAG_OUT_ON_DEVICE
         check(self.lib.mbg_kernel_mat(self.handle, n_atoms, T, P, ptr(R_desc, _dp), ptr(R_d_desc, _dp), ptr(tpl, _lp),
                                       float(sig), int(bool(use_E_cstr)), flags, C.c_void_p(dst)))
+        return K
+
+    def kernel_mat_cols(self, R_desc, R_d_desc, tril_perms_lin, sig, col_blocks, out=None):
+        """The column blocks ``col_blocks`` (training points) of the force-field kernel matrix against all training
+        points: [T 3N][len(col_blocks) 3N] (mbg_kernel_mat_cols).  ``out``: optional device pointer."""
+        R_desc, R_d_desc = as_f64(R_desc), as_f64(R_d_desc)
+        tpl = np.ascontiguousarray(tril_perms_lin, dtype=np.int64)
+        blocks = np.ascontiguousarray(col_blocks, dtype=np.int32)
+        T, D = R_desc.shape
+        n_atoms = int((1 + np.sqrt(8 * D + 1)) / 2)
+        if n_atoms * (n_atoms - 1) // 2 != D or R_d_desc.shape != (T, D, 3) or tpl.size % D:
+            raise ValueError("R_desc (T, D), R_d_desc (T, D, 3) and tril_perms_lin (P*D,) have inconsistent shapes")
+        P = tpl.size // D
+        if out is None:
+            K = np.empty((T * 3 * n_atoms, blocks.size * 3 * n_atoms))
+            dst, flags = K.ctypes.data, 0
+        else:
+            K, dst, flags = None, int(out), FLAG_OUT_ON_DEVICE
+        check(self.lib.mbg_kernel_mat_cols(self.handle, n_atoms, T, P, ptr(R_desc, _dp), ptr(R_d_desc, _dp), ptr(tpl, _lp),
+                                           float(sig), ptr(blocks, _ip), int(blocks.size), flags,
+                                           C.c_void_p(dst)))
         return K
 
     def mat52(self, model_handle, R, n_rows):

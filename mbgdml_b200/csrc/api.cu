@@ -122,7 +122,7 @@ struct mbg_context_s {
   Scratch scr;
   bool capturing = false;  // a step is being captured: no events, no launch records
   DevBuf R, outE, outF, outV, totals;
-  DevBuf km_in, km_ints, km_ints2, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
+  DevBuf km_in, km_ints, km_ints2, km_jlist, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
   std::vector<int> rec_chunk_slot;  // launch record -> chunk slot (fragment count resolved lazily), -1: count is exact
@@ -1497,7 +1497,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   ctx->tab.release();
   ctx->scr.release();
   for (DevBuf* b : {&ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->totals, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
-                    &ctx->deferred_totals, &ctx->km_ints, &ctx->km_ints2, &ctx->km_out})
+                    &ctx->deferred_totals, &ctx->km_ints, &ctx->km_ints2, &ctx->km_jlist, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ev_call0) cudaEventDestroy(ctx->ev_call0);
@@ -2250,10 +2250,16 @@ struct KmdPick {  // the tensor-pipe kernel-matrix kernel exists for fragments o
   }
 };
 extern "C" {
-int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double* R_desc,
-                   const double* R_d_desc, const int64_t* tril_perms_lin, double sig, int32_t use_E_cstr,
-                   uint32_t flags, double* K) {
+static int kernel_mat_impl(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double* R_desc,
+                           const double* R_d_desc, const int64_t* tril_perms_lin, double sig, int32_t use_E_cstr,
+                           const int32_t* j_list, int32_t n_j, uint32_t flags, double* K) {
   if (!ctx || !R_desc || !R_d_desc || !tril_perms_lin || !K) return fail(MBG_ERR_ARG, "NULL argument");
+  if (j_list) {
+    if (use_E_cstr) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: column subsets with energy constraints");
+    if (n_j < 1) return fail(MBG_ERR_ARG, "empty column-block list");
+    for (int k = 0; k < n_j; ++k)
+      if (j_list[k] < 0 || j_list[k] >= n_train) return fail(MBG_ERR_ARG, "column block %d out of range", (int)j_list[k]);
+  }
   if (n_atoms < 2 || n_atoms > 18) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: n_atoms=%d outside 2..18", n_atoms);
   if (n_train < 1 || n_perms < 1) return fail(MBG_ERR_ARG, "n_train and n_perms must be positive");
   if (!(sig > 0)) return fail(MBG_ERR_ARG, "sig must be positive");
@@ -2276,6 +2282,7 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
     }
   }
   const size_t rows = (size_t)T * N3 + (use_E_cstr ? T : 0);
+  const size_t cols = j_list ? (size_t)n_j * N3 : rows;
   const size_t nX = (size_t)T * D, nG = (size_t)T * D * 3;
   begin_call(ctx);
   TRY(ctx->km_in.ensure((nX + nG) * sizeof(double)));
@@ -2286,7 +2293,7 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
   double* dK = K;
   const bool out_dev = (flags & MBG_FLAG_OUT_ON_DEVICE) != 0;
   if (!out_dev) {
-    TRY(ctx->km_out.ensure(rows * rows * sizeof(double)));
+    TRY(ctx->km_out.ensure(rows * cols * sizeof(double)));
     dK = ctx->km_out.as<double>();
   }
   // closed under inversion?  (pi_q == pi_p^-1 for some q, for every p)
@@ -2297,12 +2304,19 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
     closed = found;
   }
   KernelMatArgs a;
+  if (j_list) closed = false;  // every (i, j in list) block is computed on its own
   a.T = T, a.P = P, a.sig = sig, a.use_E = use_E_cstr ? 1 : 0, a.symmetric = closed ? 1 : 0;
   a.X = ctx->km_in.as<double>(), a.G = ctx->km_in.as<double>() + nX;
   a.pi = ctx->km_ints.as<int>(), a.ipi = ctx->km_ints.as<int>() + (size_t)P * D;
-  a.K = dK, a.ld = (long long)rows;
+  a.K = dK, a.ld = (long long)cols;
   a.srt_p = nullptr, a.srt_k = nullptr;
-  const long long n_blocks = closed ? (long long)T * (T + 1) / 2 : (long long)T * T;
+  a.j_list = nullptr, a.n_j = 0;
+  if (j_list) {
+    TRY(ctx->km_jlist.ensure((size_t)n_j * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->km_jlist.p, j_list, (size_t)n_j * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    a.j_list = ctx->km_jlist.as<int>(), a.n_j = n_j;
+  }
+  const long long n_blocks = closed ? (long long)T * (T + 1) / 2 : (long long)T * (j_list ? n_j : T);
   if (n_blocks > 0x7fffffffLL) return fail(MBG_ERR_UNSUPPORTED, "kernel matrix: too many blocks for one launch");
   // warp-per-pair kernel for narrow descriptors (D <= 15: measured 4.3x / 1.24x faster than CTA-per-pair for water
   // monomers / dimers at T = 1000, 0.93x for trimers, where its 12 warps per SM are too few to hide the latency of
@@ -2366,13 +2380,28 @@ int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t 
     cudaEventRecord(e1, ctx->stream);
   }
   CUDA_TRY(cudaGetLastError());
-  record_aux_launch(ctx, e0, e1, N, (long long)T * T, T, P, 2);
+  record_aux_launch(ctx, e0, e1, N, (long long)T * (j_list ? n_j : T), T, P, 2);
   if (!out_dev) {
-    CUDA_TRY(cudaMemcpyAsync(K, dK, rows * rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(K, dK, rows * cols * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  } else if (j_list) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // j_list is the caller's memory
   }
   end_call_timing(ctx);
   return MBG_OK;
+}
+
+int mbg_kernel_mat(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double* R_desc,
+                   const double* R_d_desc, const int64_t* tril_perms_lin, double sig, int32_t use_E_cstr,
+                   uint32_t flags, double* K) {
+  return kernel_mat_impl(ctx, n_atoms, n_train, n_perms, R_desc, R_d_desc, tril_perms_lin, sig, use_E_cstr, nullptr, 0, flags, K);
+}
+
+int mbg_kernel_mat_cols(mbg_context_t ctx, int32_t n_atoms, int32_t n_train, int32_t n_perms, const double* R_desc,
+                        const double* R_d_desc, const int64_t* tril_perms_lin, double sig, const int32_t* col_blocks,
+                        int32_t n_col_blocks, uint32_t flags, double* K) {
+  if (!col_blocks) return fail(MBG_ERR_ARG, "NULL argument");
+  return kernel_mat_impl(ctx, n_atoms, n_train, n_perms, R_desc, R_d_desc, tril_perms_lin, sig, 0, col_blocks, n_col_blocks, flags, K);
 }
 
 static int launch_mat52(mbg_context_t ctx, Mat52Args a, int64_t n_q, int na_rec) {

@@ -40,6 +40,10 @@ struct KernelMatArgs {
   // tensor-pipe kernel only: for every descriptor k the permutations ordered by their image pi_p(k):
   const int* srt_p;  // [P][D]  srt_p[t D + k] = the t-th permutation of row k
   const int* srt_k;  // [P][D]  srt_k[t D + k] = its image pi_p(k) (ascending in t)
+  // column-block subset (mbg_kernel_mat_cols): pairs (i, j_list[jj]) for all i, block written at column block jj of a
+  // [T 3N][n_j 3N] matrix; NULL for the full matrix.  Never with use_E or symmetric.
+  const int* j_list;
+  int n_j;
 };
 
 template <int NA>
@@ -70,6 +74,8 @@ __global__ void __launch_bounds__(kKmThreads) k_kernel_mat(const __grid_constant
   } else {
     i = blockIdx.x % a.T, j = blockIdx.x / a.T;
   }
+  const int jc = j;  // column block of the output
+  if (a.j_list) j = a.j_list[j];
   const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* Xi = reinterpret_cast<double*>(km_smem);
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(kKmThreads) k_kernel_mat(const __grid_constant
     }
   }
   __syncthreads();
-  double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+  double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)jc * N3;
   double* Kji = a.K + ((size_t)j * N3) * a.ld + (size_t)i * N3;
   for (int e = tid; e < N3 * N3; e += NT) {
     const int r = e / N3, c = e - r * N3;
@@ -294,6 +300,8 @@ __global__ void __launch_bounds__(kKmwMaxWarps * 32) k_kernel_mat_w(const __grid
     } else {
       i = (int)(b % a.T), j = (int)(b / a.T);
     }
+    const int jc = j;  // column block of the output
+    if (a.j_list) j = a.j_list[j];
     __syncwarp();  // the previous pair's reads of this warp's slice are done
     for (int k = lane; k < D; k += 32) Xi[k] = a.X[(size_t)i * D + k], Xj[k] = a.X[(size_t)j * D + k];
     for (int k = lane; k < 3 * D; k += 32) gi[k] = a.G[(size_t)i * 3 * D + k], gj[k] = a.G[(size_t)j * 3 * D + k];
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__(kKmwMaxWarps * 32) k_kernel_mat_w(const __grid
     }
     __syncwarp();
     // C: K_ij[r][c] = acc - sum_{k containing atom(r)} J_i[k][r] W[k][c]; the block and (symmetric mode) its transpose
-    double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+    double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)jc * N3;
     double* Kji = a.K + ((size_t)j * N3) * a.ld + (size_t)i * N3;
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -573,6 +581,8 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
     } else {
       i = (int)(b % a.T), j = (int)(b / a.T);
     }
+    const int jc = j;  // column block of the output
+    if (a.j_list) j = a.j_list[j];
     __syncwarp();  // the previous pair's reads of this warp's slice are done
     for (int k = lane; k < 4 * KS; k += 32) Xi[k] = k < D ? a.X[(size_t)i * D + k] : 0.0, Xj[k] = k < D ? a.X[(size_t)j * D + k] : 0.0;
     for (int k = lane; k < 3 * D; k += 32) gi[k] = a.G[(size_t)i * 3 * D + k], gj[k] = a.G[(size_t)j * 3 * D + k];
@@ -739,7 +749,7 @@ __global__ void __launch_bounds__(kKmdMaxWarps * 32, 1) k_kernel_mat_d(const __g
         if (r < N3 && c + 1 < N3) reg[r * OS + c + 1] = Kacc[m][n][1];
       }
     __syncwarp();
-    double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)j * N3;
+    double* Kij = a.K + ((size_t)i * N3) * a.ld + (size_t)jc * N3;
     double* Kji = a.K + ((size_t)j * N3) * a.ld + (size_t)i * N3;
     for (int e = lane; e < N3 * N3; e += 32) {
       const int r = e / N3, c = e - r * N3;

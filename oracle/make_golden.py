@@ -517,10 +517,59 @@ def case_lattice():
     np.savez_compressed(os.path.join(GOLD, "lattice_model.npz"), **out)
 
 
+def case_train_kernel_cols():
+    """Column subsets of the kernel matrix (`col_idxs`, _gdml/train.py:1105-1115, 1187-1245): the live reference's
+    outputs for the index forms its callers use -- a leading slice of training points (exploit_sym + cols_m_limit), a
+    slice of training points that does not start at 0, and sorted index arrays (with and without energy-constraint
+    columns).  A slice that is not a whole number of training points makes the reference compare a Python list with
+    an int (train.py:1217) and raise TypeError, so that form has no golden."""
+    from mbgdml._gdml.train import GDMLTrain  # the reference
+
+    trainer = GDMLTrain(max_processes=1)
+    comp, T, sig = ["h2o", "h2o"], 7, 20.0
+    rng = np.random.default_rng(411)
+    Rt = syn.fragment_geometries(rng, comp, T)
+    n = Rt.shape[1]
+    desc = Desc(n, max_processes=1)
+    R_desc, R_d_desc = desc.from_R(Rt.reshape(T, -1))
+    tpl = orc.tril_perms_lin_from_perms(syn.fragment_perms(comp))
+    out = {"R_desc": R_desc, "R_d_desc": R_d_desc, "tril_perms_lin": tpl, "sig": np.array(sig)}
+    dim_i = 3 * n
+    forms = {
+        "lead": (np.s_[: 3 * dim_i], False, 0),
+        "mid": (np.s_[2 * dim_i: 5 * dim_i], False, 0),
+        "idx": (np.array([1, 5, 17, 18, 19, 20, 53, 100, 125]), False, 2),
+        "idxE": (np.array([0, 2, 40, 41, 90, T * dim_i, T * dim_i + 3, T * dim_i + 6]), True, 0),
+        "leadE": (np.s_[: 2 * dim_i], True, 1),
+    }
+    for name, (cols, use_E, extra) in forms.items():
+        K_full = np.array(trainer._assemble_kernel_mat(R_desc, R_d_desc, tpl, sig, desc, use_E_cstr=use_E))
+        try:
+            K_sub = np.array(trainer._assemble_kernel_mat(R_desc, R_d_desc, tpl, sig, desc, use_E_cstr=use_E, col_idxs=cols,
+                                                          alloc_extra_rows=extra))
+        except (ValueError, TypeError, IndexError) as exc:
+            print(f"  reference fails on col_idxs form {name!r}: {type(exc).__name__}: {exc}")
+            continue
+        want = K_full[:, cols]
+        assert K_sub.shape == (K_full.shape[0] + extra, want.shape[1]), (name, K_sub.shape, want.shape)
+        check(f"kernel_mat cols {name}: reference subset == reference full[:, cols]", K_sub[: K_full.shape[0]], want, tol=1e-13)
+        if isinstance(cols, slice):
+            out[f"{name}_slice"] = np.array([cols.start or 0, cols.stop])
+        else:
+            out[f"{name}_cols"] = cols
+        out[f"{name}_use_E"] = np.array(int(use_E))
+        out[f"{name}_extra"] = np.array(extra)
+        out[f"{name}_K"] = K_sub[: K_full.shape[0]]
+    np.savez_compressed(os.path.join(GOLD, "train_kernel_cols.npz"), **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="raise", under="ignore")
     if "--only-lattice" in sys.argv:
         print("lattice models"); case_lattice()
+        sys.exit(0)
+    if "--only-train-cols" in sys.argv:
+        print("train kernel, column subsets"); case_train_kernel_cols()
         sys.exit(0)
     print("gen_combs"); case_gen_combs()
     print("fragment kernel"); case_desc_and_kernel()
@@ -531,5 +580,6 @@ if __name__ == "__main__":
     print("mbe_contrib"); case_mbe_contrib()
     print("train kernel"); case_train_kernel()
     print("lattice models"); case_lattice()
+    print("train kernel, column subsets"); case_train_kernel_cols()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden fixtures written: %.1f KB" % (total / 1024))

@@ -110,6 +110,36 @@ def test_gpu_kernel_mat_golden(name):
 
 
 @pytest.mark.gpu
+def test_gpu_kernel_mat_column_subsets_golden():
+    """`col_idxs` (train.py:1105-1115, 1187-1245) against the live reference's outputs (tests/golden/train_kernel_cols.npz,
+    oracle/make_golden.py:case_train_kernel_cols): a leading slice of training points, sorted index arrays without and
+    with energy-constraint columns, `alloc_extra_rows`; and, for every form incl. the one the reference itself fails
+    on (a slice of training points that does not start at 0), the defining property K_sub == K_full[:, cols]."""
+    from mbgdml_b200._gdml.train import assemble_kernel_mat
+
+    g = load("train_kernel_cols.npz")
+    args = (g["R_desc"], g["R_d_desc"], g["tril_perms_lin"], float(g["sig"]))
+    T, D = g["R_desc"].shape
+    dim_i = 3 * int((1 + np.sqrt(8 * D + 1)) / 2)
+    for name in ("lead", "idx", "idxE", "leadE"):
+        cols = np.s_[int(g[f"{name}_slice"][0]):int(g[f"{name}_slice"][1])] if f"{name}_slice" in g else g[f"{name}_cols"]
+        use_E, extra = bool(g[f"{name}_use_E"]), int(g[f"{name}_extra"])
+        K = assemble_kernel_mat(*args, use_E_cstr=use_E, col_idxs=cols, alloc_extra_rows=extra)
+        ref = g[f"{name}_K"]
+        assert K.shape == (ref.shape[0] + extra, ref.shape[1]), name
+        assert relerr(K[: ref.shape[0]], ref) <= TOL, name
+        if extra:
+            assert not K[ref.shape[0]:].any()
+    K_full = assemble_kernel_mat(*args)
+    for cols in (np.s_[2 * dim_i: 5 * dim_i], np.s_[5:40:3], np.array([0, 17, 18, 35, 36, T * dim_i - 1]), np.s_[: dim_i]):
+        assert relerr(assemble_kernel_mat(*args, col_idxs=cols), K_full[:, cols]) <= 1e-12
+    with pytest.raises(ValueError):
+        assemble_kernel_mat(*args, col_idxs=np.arange(T * dim_i + 1))
+    with pytest.raises(AssertionError):
+        assemble_kernel_mat(*args, col_idxs=np.array([5, 3]))
+
+
+@pytest.mark.gpu
 def test_gpu_kernel_mat_reference_fixture():
     """CUDA path vs. the reference's own tests/data/train/1h2o/K.npy."""
     from mbgdml_b200._gdml.train import assemble_kernel_mat
