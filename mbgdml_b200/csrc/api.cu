@@ -413,6 +413,64 @@ static int launch_matern_pw(mbg_context_t ctx, Scratch& sc, int na, bool use_E, 
   }
 }
 
+// Wide fragments (13-18 atoms: one m-tile per warp) behind the sync-free API: the CTA-cooperative kernel in its
+// persistent mode (matern_mma.cuh).  With one m-tile per warp and two warps per scheduler a per-warp worker cannot
+// hide its own prologue / epilogue (profiles/r2_pw_tuning.md section 5: k_matern_pw runs 5-8 % behind here), a CTA
+// that does them with all its threads can.
+template <int NA, bool USE_E>
+static int launch_matern_mma_persistent_t(mbg_context_t ctx, Scratch& sc, const MaternMmaArgs& a_in, int chunk_slot) {
+  constexpr int MT = 1, NTHR = 256;
+  MaternMmaArgs a = a_in;
+  int dev_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  auto kern = k_matern_mma<NA, MT, NTHR, 1, USE_E, false>;
+  const size_t smem = mma_smem_bytes<NA, MT, false>(NTHR, a.P);
+  if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
+  static thread_local size_t attr_smem = 0;  // per instantiation
+  static thread_local int occ = 0;
+  if (smem > attr_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHR, smem) != cudaSuccess || occ < 1) occ = 1;
+  }
+  const int n_tiles_data = (a.n_row_blocks + mma_tile_rows(NA) / 8 - 1) / (mma_tile_rows(NA) / 8);
+  a.persistent = 1, a.max_slices = 1;
+  while (a.max_slices * 2 <= 32 && a.max_slices * 4 <= n_tiles_data) a.max_slices *= 2;  // >= 2 tiles per slice
+  a.tiles_per_slice = a.T_pad / mma_tile_rows(NA), a.main_ctas = 0x7fffffff, a.tail_slices = 1, a.tail_tiles_per_slice = a.tiles_per_slice;
+  sc.n_pw_launch++;  // keeps the chunk slot of this launch its own
+  const unsigned grid = (unsigned)(ctx->sm_count * occ);
+  if (ctx->capturing) {  // inside a captured step: no timing events, no records
+    kern<<<grid, NTHR, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MBG_OK;
+  }
+  cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+  kern<<<grid, NTHR, smem, ctx->stream>>>(a);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches++;
+  ctx->n_contract++;
+  ctx->launch_recs.push_back({NA, a.n_frag, a.T_pad, a.P, 0.f, MBG_CONTRACT_DMMA});
+  ctx->rec_chunk_slot.resize(ctx->launch_recs.size(), -1);
+  ctx->rec_chunk_slot.back() = chunk_slot;
+  CUDA_TRY(cudaGetLastError());
+  return MBG_OK;
+}
+
+static int launch_matern_mma_persistent(mbg_context_t ctx, Scratch& sc, int na, bool use_E, const MaternMmaArgs& a, int chunk_slot) {
+  switch (na) {
+#define X(N)                                                                                             \
+  case N:                                                                                                \
+    return use_E ? launch_matern_mma_persistent_t<N, true>(ctx, sc, a, chunk_slot)                       \
+                 : launch_matern_mma_persistent_t<N, false>(ctx, sc, a, chunk_slot);
+    X(13) X(14) X(15) X(16) X(17) X(18)
+#undef X
+    default:
+      return fail(MBG_ERR_UNSUPPORTED, "no persistent CTA kernel for fragments of %d atoms", na);
+  }
+}
+
 // Thread-per-query FMA-pipe kernel for narrow descriptors (matern_small.cuh): fragments of 2-4 atoms.
 template <int NA, bool USE_E>
 static int launch_matern_small_t(mbg_context_t ctx, const MaternSmallArgs& a_in, int chunk_slot) {
@@ -958,6 +1016,22 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
       TRY(launch_matern_small(ctx, NA, m->use_E, q, slot));
       continue;
     }
+    if (NA >= 13 && !m->use_lat && ctx->mma_cfg != 9) {  // wide fragments: CTA-cooperative persistent kernel (9: off)
+      MaternMmaArgs w;
+      memset(&w, 0, sizeof(w));
+      w.sys = s, w.R = dR;
+      w.tiles = m->tiles_mma, w.mu = m->mu, w.iperm = m->iperm;
+      w.exp2_table = ctx->exp2_table_mma.as<double>();
+      w.T_pad = m->T_pad, w.P = m->P, w.n_row_blocks = (m->T + 7) / 8;
+      w.sig = m->sig, w.c = m->c, w.std = m->std;
+      w.n_frag = n_up, w.n_frag_dev = totals;
+      w.rec_frame = sc.rec_frame.as<int>(), w.rec_atoms = sc.rec_atoms.as<int>();
+      w.rec_lambda = sc.rec_lambda.as<double>(), w.rec_slot = sc.rec_slot.as<long long>();
+      w.n_slots_per_frame = (int)j.cand_per_frame, w.decomp = decomp ? 1 : 0, w.want_virial = want_virial ? 1 : 0;
+      w.E = out.E, w.F = out.F, w.virial = out.V;
+      TRY(launch_matern_mma_persistent(ctx, sc, NA, m->use_E, w, slot));
+      continue;
+    }
     MaternPwArgs a;
     a.sys = s;
     a.R = dR;
@@ -1022,6 +1096,7 @@ static int run_job(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mb
       a.decomp = decomp ? 1 : 0;
       a.want_virial = want_virial ? 1 : 0;
       a.E = out.E, a.F = out.F, a.virial = out.V;
+      a.persistent = 0, a.max_slices = 1;
       TRY(launch_matern_mma(ctx, NA, m->use_E, a));
       rec_pending = 0;
       return MBG_OK;

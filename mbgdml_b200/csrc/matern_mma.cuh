@@ -91,6 +91,10 @@ struct MaternMmaArgs {
   // remaining batches -- the last, partial wave of a launch -- are each split into tail_slices CTAs of
   // tail_tiles_per_slice tiles, so the tail takes 1 / tail_slices of a wave.  tail_slices <= 1: no splitting.
   int main_ctas, tail_slices, tail_tiles_per_slice;
+  // Persistent mode (wide fragments behind the sync-free API): gridDim.x resident CTAs walk the (query batch, row
+  // slice) units of the launch round-robin; the fragment count is read on the device and the number of row slices is
+  // chosen there (as many as it takes to give every CTA a unit, at most max_slices).  gridDim.y = 1.
+  int persistent, max_slices;
   double sig, c, std;
   long long n_frag;
   const long long* n_frag_dev;  // optional: the accepted count still on the device (n_frag is then an upper bound)
@@ -212,8 +216,51 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
 
   const long long n_frag = a.n_frag_dev ? min(a.n_frag, *a.n_frag_dev) : a.n_frag;
   const long long nq = n_frag * P;
+  // Persistent mode: CTA c takes the units u = c, c + gridDim.x, ...  Fewer batches than CTAs: every batch is cut
+  // into p_sl row slices (u = batch * p_sl + slice).  Otherwise the batches of the full rounds are units of their own
+  // (u = batch < p_main) and, when the last round would be less than half full, its batches are cut into p_sl slices
+  // that together fill the CTAs once (u = p_main + (batch - p_main) * p_sl + slice) -- the tail splitting the host
+  // does for the wave-launched form, from the count on the device.
+  long long n_units = 0, p_main = 0;
+  int p_sl = 1, p_tps = a.T_pad / TR;
+  if (a.persistent) {
+    const long long n_batches = (nq + qc - 1) / qc, G = gridDim.x;
+    const int n_tiles_all = a.T_pad / TR, n_tiles_data = (a.n_row_blocks + BPT - 1) / BPT;
+    const int cap = min(a.max_slices, max(1, n_tiles_data / 2));  // at least two tiles per slice
+    if (n_batches < G) {  // rounds x (tiles per slice + ~5 tiles' worth of prologue and epilogue), smallest wins
+      double best = 1e300;
+      for (int cand = 1; cand <= cap; cand *= 2) {
+        const double cost = (double)((n_batches * cand + G - 1) / G) * ((n_tiles_data + cand - 1) / cand + 5);
+        if (cost < best * 0.97) best = cost, p_sl = cand;
+      }
+    } else {
+      p_main = n_batches / G * G;
+      const long long r = n_batches - p_main;
+      if (r > 0 && 2 * r <= G) p_sl = (int)min((long long)cap, G / r);
+      else p_main = n_batches;
+    }
+    p_tps = (n_tiles_all + p_sl - 1) / p_sl;
+    p_sl = (n_tiles_data + p_tps - 1) / p_tps;  // slices that hold data
+    n_units = p_main + (n_batches - p_main) * p_sl;
+  }
+  for (long long unit = blockIdx.x;; unit += gridDim.x) {  // one pass unless persistent
   int batch = blockIdx.x, slice = blockIdx.y, tps = a.tiles_per_slice;
-  if (a.tail_slices > 1 && batch >= a.main_ctas) {  // tail CTA: (batch, slice) packed in blockIdx.x
+  if (a.persistent) {
+    if (unit >= n_units) return;
+    if (unit < p_main) {
+      batch = (int)unit, slice = 0, tps = a.T_pad / TR;
+    } else {
+      const long long t = unit - p_main;
+      batch = (int)(p_main + t / p_sl), slice = (int)(t % p_sl), tps = p_tps;
+    }
+    if (unit != blockIdx.x) {  // not the first unit: everybody is done with the previous one; the barriers start over
+      __syncthreads();
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2 * ST + 1; ++s) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+      }
+    }
+  } else if (a.tail_slices > 1 && batch >= a.main_ctas) {  // tail CTA: (batch, slice) packed in blockIdx.x
     const int t = batch - a.main_ctas;
     batch = a.main_ctas + t / a.tail_slices, slice = t - (t / a.tail_slices) * a.tail_slices, tps = a.tail_tiles_per_slice;
   }
@@ -683,6 +730,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_matern_mma(const __grid_constant
       atomicAdd(a.virial + (long long)a.rec_frame[frag] * 9 + ij, wv * a.std * a.rec_lambda[frag]);
     }
   }
+  if (!a.persistent) return;
+  }  // units
 }
 
 }  // namespace mbg

@@ -33,16 +33,22 @@ using namespace mbg;
 static double frand() { return rand() / (double)RAND_MAX; }
 
 template <int MT, int NTHR, bool YS, int MINB = 1>
-static int run(const char* name, MaternMmaArgs a, int reps) {
+static int run(const char* name, MaternMmaArgs a, int reps, bool persistent = false) {
   constexpr int NA = H_NA, D = NA * (NA - 1) / 2;
   auto kern = k_matern_mma<NA, MT, NTHR, MINB, false, YS>;
   const size_t smem = mma_smem_bytes<NA, MT, YS>(NTHR, a.P);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nq = a.n_frag * a.P;
   const int qc = mma_queries_per_cta<NA, MT>(NTHR);
-  const unsigned grid = (unsigned)((nq + qc - 1) / qc);
+  unsigned grid = (unsigned)((nq + qc - 1) / qc);
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHR, smem);
+  if (persistent) {  // resident CTAs walk the batches; the kernel picks the row slices
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    grid = (unsigned)(sms * occ), a.persistent = 1, a.max_slices = 16;
+  }
+  CK(cudaMemset(a.E, 0, 8));
   printf("[occupancy %d CTA/SM] ", occ);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0), cudaEventCreate(&e1);
@@ -59,8 +65,10 @@ static int run(const char* name, MaternMmaArgs a, int reps) {
     if (ms < best) best = ms;
   }
   const double flop = (double)a.n_frag * 1000.0 * a.P * (9 * D + 10);
-  printf("%-28s grid %6u  smem %6zu  %8.3f ms  %6.2f TFLOP/s (algorithmic, T=1000 formula scaled by rows %d)\n", name, grid,
-         smem, best, flop * (a.n_row_blocks * 8 / 1000.0) / best / 1e9, a.n_row_blocks * 8);
+  double E_sum;
+  CK(cudaMemcpy(&E_sum, a.E, 8, cudaMemcpyDeviceToHost));
+  printf("%-28s grid %6u  smem %6zu  %8.3f ms  %6.2f TFLOP/s (algorithmic, T=1000 formula scaled by rows %d)  E(%d launches) = %.9e\n", name, grid,
+         smem, best, flop * (a.n_row_blocks * 8 / 1000.0) / best / 1e9, a.n_row_blocks * 8, reps + 1, E_sum);
   return 0;
 }
 
@@ -227,6 +235,7 @@ int main(int argc, char** argv) {
 #endif
 #if H_NA != 9
   if (run<H_MT, 256, false>("wave 256 thr", a, 5)) return 1;
+  if (run<H_MT, 256, false>("wave 256 thr, persistent", a, 5, true)) return 1;
   int sm_count_w = 0;
   cudaDeviceGetAttribute(&sm_count_w, cudaDevAttrMultiProcessorCount, 0);
   if (run_pw<H_MT, 8, false>("persistent 8 warps", a, 5, sm_count_w)) return 1;
@@ -246,6 +255,7 @@ int main(int argc, char** argv) {
 #endif
   int sm_count = 0;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
+  if (run<3, 384, true>("CTA kernel, persistent mode", a, 5, true)) return 1;
   if (run_pw<3, 12, true>("persistent 12 warps, y' smem", a, 5, sm_count)) return 1;
 #ifdef EXP_16W
   if (run_pw<2, 16, true>("persistent 16 warps MT=2 ys", a, 5, sm_count)) return 1;
