@@ -349,6 +349,7 @@ static int launch_matern_mma(mbg_context_t ctx, int na, bool use_E, const Matern
 }
 
 
+constexpr long long kCtaMaxCandidates = 1 << 20;  // run_job_pw: 9- to 12-atom launches up to this many candidates use the CTA kernel
 constexpr long long kSmallMinQueries = 48 * 1024;  // k_matern_small from this many queries (fragments x permutations) on
 
 // Persistent per-warp form of the tensor-pipe contraction (matern_pw.cuh): always one CTA per SM; the kernel reads
@@ -417,14 +418,13 @@ static int launch_matern_pw(mbg_context_t ctx, Scratch& sc, int na, bool use_E, 
 // persistent mode (matern_mma.cuh).  With one m-tile per warp and two warps per scheduler a per-warp worker cannot
 // hide its own prologue / epilogue (profiles/r2_pw_tuning.md section 5: k_matern_pw runs 5-8 % behind here), a CTA
 // that does them with all its threads can.
-template <int NA, bool USE_E>
+template <int NA, int MT, int NTHR, bool USE_E, bool YS>
 static int launch_matern_mma_persistent_t(mbg_context_t ctx, Scratch& sc, const MaternMmaArgs& a_in, int chunk_slot) {
-  constexpr int MT = 1, NTHR = 256;
   MaternMmaArgs a = a_in;
   int dev_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-  auto kern = k_matern_mma<NA, MT, NTHR, 1, USE_E, false>;
-  const size_t smem = mma_smem_bytes<NA, MT, false>(NTHR, a.P);
+  auto kern = k_matern_mma<NA, MT, NTHR, 1, USE_E, YS>;
+  const size_t smem = mma_smem_bytes<NA, MT, YS>(NTHR, a.P);
   if (smem > (size_t)dev_smem) return fail(MBG_ERR_UNSUPPORTED, "contraction tile does not fit shared memory");
   static thread_local size_t attr_smem = 0;  // per instantiation
   static thread_local int occ = 0;
@@ -459,12 +459,16 @@ static int launch_matern_mma_persistent_t(mbg_context_t ctx, Scratch& sc, const 
 }
 
 static int launch_matern_mma_persistent(mbg_context_t ctx, Scratch& sc, int na, bool use_E, const MaternMmaArgs& a, int chunk_slot) {
+  // the shapes of the wave-launched kernel (launch_matern_mma): 12 warps with y' in shared memory for 9 atoms
+  if (na == 9 && !use_E) return launch_matern_mma_persistent_t<9, 3, 384, false, true>(ctx, sc, a, chunk_slot);
   switch (na) {
 #define X(N)                                                                                             \
-  case N:                                                                                                \
-    return use_E ? launch_matern_mma_persistent_t<N, true>(ctx, sc, a, chunk_slot)                       \
-                 : launch_matern_mma_persistent_t<N, false>(ctx, sc, a, chunk_slot);
-    X(13) X(14) X(15) X(16) X(17) X(18)
+  case N: {                                                                                              \
+    constexpr int MT = (N >= 13) ? 1 : (N >= 10) ? 2 : 3;                                                \
+    return use_E ? launch_matern_mma_persistent_t<N, MT, 256, true, false>(ctx, sc, a, chunk_slot)       \
+                 : launch_matern_mma_persistent_t<N, MT, 256, false, false>(ctx, sc, a, chunk_slot);     \
+  }
+    X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18)
 #undef X
     default:
       return fail(MBG_ERR_UNSUPPORTED, "no persistent CTA kernel for fragments of %d atoms", na);
@@ -1016,7 +1020,13 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
       TRY(launch_matern_small(ctx, NA, m->use_E, q, slot));
       continue;
     }
-    if (NA >= 13 && !m->use_lat && ctx->mma_cfg != 9) {  // wide fragments: CTA-cooperative persistent kernel (9: off)
+    // CTA-cooperative persistent kernel (MBG_MMA_CFG=9: off): always for wide fragments (13-18 atoms), and for 9-12
+    // atoms when the launch can only be mid-size -- at most kCtaMaxCandidates candidates (a frame or two of an MD
+    // box), at least four rounds of batches if all were accepted: there its device-side tail splitting is worth 2.7 %
+    // (one 140-H2O frame 11.03 -> 10.73 ms), while large launches (-1.7 %) and small ones stay on the per-warp kernel.
+    const long long bound_batches = n_up * m->P / (NA == 9 ? 288 : 128);
+    const bool mid_size = NA >= 9 && n_up <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count;
+    if ((NA >= 13 || mid_size) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {
       MaternMmaArgs w;
       memset(&w, 0, sizeof(w));
       w.sys = s, w.R = dR;
