@@ -1024,8 +1024,12 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
     // atoms when the launch can only be mid-size -- at most kCtaMaxCandidates candidates (a frame or two of an MD
     // box), at least four rounds of batches if all were accepted: there its device-side tail splitting is worth 2.7 %
     // (one 140-H2O frame 11.03 -> 10.73 ms), while large launches (-1.7 %) and small ones stay on the per-warp kernel.
+    // Without a criteria and without a cell nothing is culled (heterogeneous product spaces aside) and the candidates
+    // ARE the count: the window is then 8 .. 96 rounds of batches.
     const long long bound_batches = n_up * m->P / (NA == 9 ? 288 : 128);
-    const bool mid_size = NA >= 9 && n_up <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count;
+    const bool culled = m->crit.kind != 0 || s.periodic || !(j.homogeneous || j.explicit_combs);
+    const bool mid_size = NA >= 9 && (culled ? n_up <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count
+                                             : bound_batches >= 8ll * ctx->sm_count && bound_batches <= 96ll * ctx->sm_count);
     if ((NA >= 13 || mid_size) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {
       MaternMmaArgs w;
       memset(&w, 0, sizeof(w));
