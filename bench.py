@@ -538,6 +538,7 @@ def run_gpu_arm(args):
             "peak_fp64_fma_tflops": peak_fma, "peak_fp64_tensor_tflops": peak_dmma,
             "frac_of_fma_pipe_peak": achieved / peak_fma if peak_fma else None,
             "contract_share_of_step": sum(r["ms"] for r in recs) / (ms_dev / args.steps),
+            "contract_share_of_graph_step": (sum(r["ms"] for r in recs) / graph["ms_per_step"]) if graph else None,
             # transcendental side of the same kernel (one exp and one sqrt per (query, training row) pair)
             "exp_sqrt_per_s": sum(r["n_fragments"] for r in dom) * args.n_train * best["n_perms"] / (ms * 1e-3),
             "exp_sqrt_rate_measured": exp_sqrt_rate,
