@@ -1030,7 +1030,7 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
     const bool culled = m->crit.kind != 0 || s.periodic || !(j.homogeneous || j.explicit_combs);
     const bool mid_size = NA >= 9 && (culled ? n_up <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count
                                              : bound_batches >= 8ll * ctx->sm_count && bound_batches <= 96ll * ctx->sm_count);
-    if ((NA >= 13 || mid_size) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {
+    if ((NA >= 13 || mid_size || (NA >= 9 && ctx->mma_cfg == 10)) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {  // 10 (developer): always from 9 atoms on
       MaternMmaArgs w;
       memset(&w, 0, sizeof(w));
       w.sys = s, w.R = dR;
