@@ -42,6 +42,12 @@ extern "C" {
                                fragment count on the device: no host round trip inside a call    (csrc/matern_pw.cuh)  */
 #define MBG_CONTRACT_DMMA_WAVE 3 /* the same arithmetic, wave-launched one CTA per query batch   (csrc/matern_mma.cuh) */
 
+/* Candidate generation (mbg_context_set_culling). */
+#define MBG_CULL_AUTO 0     /* MBG_CULL_PAIRLIST from 2^23 candidates per job on (where it applies), else MBG_CULL_FULL */
+#define MBG_CULL_FULL 1     /* every tuple of utils.gen_combs is unranked and tested, as the reference does (csrc/enumerate.cuh) */
+#define MBG_CULL_PAIRLIST 2 /* per-frame pair list first, only tuples of mutually admissible pairs are tested: same accepted
+                               set, same order, cost ~ accepted fragments instead of C(n, order)          (csrc/pairlist.cuh) */
+
 #define MBG_MAX_ORDER 8       /* entities per fragment */
 #define MBG_MAX_FRAG_ATOMS 24 /* atoms per fragment */
 #define MBG_MAX_ALCHEMY 16    /* alchemical scalers per job */
@@ -143,6 +149,12 @@ int mbg_context_synchronize(mbg_context_t ctx);
 /* Choose the kernel that evaluates _predict_gdml_wkr (gdml_predict.py:94-142): MBG_CONTRACT_*.  Both give the
  * same results to rounding; the choice exists so that the benchmark can time one against the other. */
 int mbg_context_set_contraction(mbg_context_t ctx, int kind);
+/* Choose how mbg_predict / mbg_accept_mask generate the candidates of a homogeneous 2- or 3-body job (the tuples of
+ * utils.gen_combs, utils.py:449-489, that the reference feeds to the slice -> r_mic -> criteria loop,
+ * gdml_predict.py:210-235): MBG_CULL_*.  The accepted fragments and their order do not depend on the choice.  In a
+ * plain call the pair list costs one device -> host read of a count per job; a prepared step (mbg_step_*) takes the
+ * choice in force when it is created and keeps the count on the device. */
+int mbg_context_set_culling(mbg_context_t ctx, int kind);
 /* Launch counters since context creation: number of kernels this library launched. */
 int mbg_context_launch_count(mbg_context_t ctx, int64_t *n_launches);
 /* Device time (ms, CUDA events on the context's stream) of the Matern contraction launches and of

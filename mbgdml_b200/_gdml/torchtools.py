@@ -79,3 +79,69 @@ class GDMLTorchPredict(nn.Module):
                                                [self._model], src, [[]], None)
             Es, Fs = torch.from_numpy(E), torch.from_numpy(F)
         return (Es, Fs) if return_E else (Fs,)
+
+
+class GDMLTorchAssemble(nn.Module):
+    """Kernel-matrix assembly with the reference's torch front-end (torchtools.py:72-398): ``J`` lists the column
+    blocks of the final matrix -- training-point indices ``j`` (``j >= n_train``: the energy-constraint column
+    ``j % n_train``), or tuples ``(first column in out, j, partials kept)`` for "fancy" column subsets, as
+    ``GDMLTrain._assemble_kernel_mat`` builds them (train.py:1190-1245) -- and ``forward(J_indx)`` fills the columns
+    of ``out`` (NumPy array or tensor, rows x columns of the final matrix) that the selected entries own.  The blocks
+    come from the device kernels behind ``assemble_kernel_mat`` (csrc/kernel_mat.cuh): one launch per ``forward``
+    instead of one einsum chain per column block."""
+
+    def __init__(self, J, tril_perms_lin, sig, use_E_cstr, R_desc_torch, R_d_desc_torch, out, callback=None):
+        super().__init__()
+        self.callback = callback
+        self.n_train, self.dim_d = R_d_desc_torch.shape[:2]
+        self.n_atoms = int((1 + np.sqrt(8 * self.dim_d + 1)) / 2)
+        self.dim_i = 3 * self.n_atoms
+        self.sig = float(sig)
+        self.tril_perms_lin = np.asarray(tril_perms_lin)
+        self.n_perms = len(self.tril_perms_lin) // self.dim_d
+        self.use_E_cstr = bool(use_E_cstr)
+        self._R_desc = self._host(R_desc_torch)
+        self._R_d_desc = self._host(R_d_desc_torch)
+        self.J = list(J)
+        self.out = out
+
+    @staticmethod
+    def _host(x):
+        return np.ascontiguousarray(x.detach().cpu().numpy() if hasattr(x, "detach") else x, dtype=np.float64)
+
+    def _columns(self, entry):
+        """(columns of ``out``, columns of the full matrix) of one entry of ``J`` (torchtools.py:119-153)."""
+        n_ff = self.n_train * self.dim_i
+        if isinstance(entry, tuple):
+            K_j, j, keep = entry
+            j = int(j)
+            if j < self.n_train:
+                keep = np.arange(self.dim_i)[keep] if isinstance(keep, slice) else np.asarray(keep, dtype=np.int64)
+                return int(K_j) + np.arange(len(keep)), j * self.dim_i + keep
+            return np.array([int(K_j)]), np.array([n_ff + j % self.n_train])
+        j = int(entry)
+        if j < self.n_train:
+            cols = j * self.dim_i + np.arange(self.dim_i)
+            return cols, cols
+        col = np.array([n_ff + j % self.n_train])
+        return col, col
+
+    def forward(self, J_indx):
+        from .train import assemble_kernel_mat
+
+        picked = [self._columns(self.J[int(i)]) for i in J_indx]
+        if not picked:
+            return
+        dst = np.concatenate([p[0] for p in picked])
+        src = np.concatenate([p[1] for p in picked])
+        order = np.argsort(src, kind="stable")
+        K = assemble_kernel_mat(self._R_desc, self._R_d_desc, self.tril_perms_lin, self.sig,
+                                use_E_cstr=self.use_E_cstr, col_idxs=src[order])
+        if hasattr(self.out, "detach"):
+            idx = torch.from_numpy(dst[order]).to(self.out.device)
+            self.out[:, idx] = torch.from_numpy(K).to(device=self.out.device, dtype=self.out.dtype)
+        else:
+            self.out[:, dst[order]] = K
+        if self.callback is not None:
+            for d, _ in picked:
+                self.callback(len(d))

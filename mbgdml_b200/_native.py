@@ -21,11 +21,12 @@ CRIT_NONE, CRIT_COM_DISTANCE_SUM, CRIT_MAX_ATOM_PAIR_DIST = 0, 1, 2
 BOUND_UPPER, BOUND_LOWER, BOUND_RANGE = 0, 1, 2
 FLAG_R_ON_DEVICE, FLAG_OUT_ON_DEVICE, FLAG_VIRIAL, FLAG_ACCUMULATE = 1, 2, 4, 8
 CONTRACT_AUTO, CONTRACT_FMA, CONTRACT_DMMA, CONTRACT_DMMA_WAVE = 0, 1, 2, 3
+CULL_AUTO, CULL_FULL, CULL_PAIRLIST = 0, 1, 2
 
 # every symbol include/mbgdml_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mbg_last_error", "mbg_abi_version", "mbg_device_count", "mbg_context_create", "mbg_context_destroy",
-    "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
+    "mbg_context_set_stream", "mbg_context_set_contraction", "mbg_context_set_culling", "mbg_context_synchronize", "mbg_context_launch_count", "mbg_context_last_timing",
     "mbg_context_last_launches",
     "mbg_model_create", "mbg_model_destroy", "mbg_predict", "mbg_predict_decomp", "mbg_step_create", "mbg_step_run",
     "mbg_step_run_device", "mbg_step_stats", "mbg_step_destroy", "mbg_accept_mask", "mbg_enumerate",
@@ -93,6 +94,7 @@ def load_library():
         lib.mbg_context_destroy.argtypes = [C.c_void_p]
         lib.mbg_context_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.mbg_context_set_contraction.argtypes = [C.c_void_p, C.c_int]
+        lib.mbg_context_set_culling.argtypes = [C.c_void_p, C.c_int]
         lib.mbg_context_synchronize.argtypes = [C.c_void_p]
         lib.mbg_context_launch_count.argtypes = [C.c_void_p, _lp]
         lib.mbg_context_last_timing.argtypes = [C.c_void_p, _dp, _dp, _lp]
@@ -209,6 +211,12 @@ class Context:
         """'auto' | 'fma' | 'dmma' | 'dmma_wave': which kernel evaluates the Matern contraction."""
         code = {"auto": CONTRACT_AUTO, "fma": CONTRACT_FMA, "dmma": CONTRACT_DMMA, "dmma_wave": CONTRACT_DMMA_WAVE}[kind] if isinstance(kind, str) else kind
         check(self.lib.mbg_context_set_contraction(self.handle, int(code)))
+
+    def set_culling(self, kind):
+        """'auto' | 'full' | 'pairlist': how the candidates of homogeneous 2-/3-body jobs are generated (same accepted
+        fragments either way; the pair list scales with the accepted count instead of C(n, order))."""
+        code = {"auto": CULL_AUTO, "full": CULL_FULL, "pairlist": CULL_PAIRLIST}[kind] if isinstance(kind, str) else kind
+        check(self.lib.mbg_context_set_culling(self.handle, int(code)))
 
     def synchronize(self):
         check(self.lib.mbg_context_synchronize(self.handle))

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "enumerate.cuh"
+#include "pairlist.cuh"
 #include "hostmath.h"
 #include "matern.cuh"
 #include "matern_mma.cuh"
@@ -96,6 +97,7 @@ struct Tables {
 struct Scratch {
   DevBuf flags, blk_acc, blk_enum, blk_off;
   DevBuf rec_frame, rec_atoms, rec_lambda, rec_slot;
+  DevBuf nl_adj, nl_deg, nl_cnt, nl_off;  // pair list of the job being culled (pairlist.cuh)
   // persistent-kernel path: per-launch device counters and counts (no host round trip inside a call)
   DevBuf pw_counters;   // [kMaxPwLaunches][kPwMaxSlices] dynamic work counters, zeroed at the start of a call
   DevBuf chunk_totals;  // [kMaxPwLaunches][2] (accepted, enumerated) of every cull chunk = n_frag_dev of its contraction
@@ -104,7 +106,7 @@ struct Scratch {
   int init();
   void release() {
     for (DevBuf* b : {&flags, &blk_acc, &blk_enum, &blk_off, &rec_frame, &rec_atoms, &rec_lambda, &rec_slot, &pw_counters,
-                      &chunk_totals, &job_totals})
+                      &chunk_totals, &job_totals, &nl_adj, &nl_deg, &nl_cnt, &nl_off})
       b->release();
   }
 };
@@ -117,11 +119,12 @@ struct mbg_context_s {
   int64_t launches = 0;
   int contraction = MBG_CONTRACT_AUTO;  // which contraction kernel mbg_predict uses
   int mma_cfg = 0;                      // developer builds: MT*1000 + threads of the trimer DMMA kernel
+  int culling = MBG_CULL_AUTO;          // candidate generation of homogeneous 2-/3-body jobs
   // scratch
   Tables tab;
   Scratch scr;
   bool capturing = false;  // a step is being captured: no events, no launch records
-  DevBuf R, outE, outF, outV, totals;
+  DevBuf R, outE, outF, outV, totals, mask_buf;
   DevBuf km_in, km_ints, km_ints2, km_jlist, km_out;  // kernel-matrix / covariance scratch (kernel_mat.cuh)
   DevBuf exp2_table;      // 2^(j/64), j = 0..63      (FMA-pipe kernel)
   DevBuf exp2_table_mma;  // 2^(j/4096), j = 0..4095  (DMMA kernel)
@@ -196,11 +199,12 @@ static bool na_supported(int na) {
   }
 }
 
-static int launch_cull(mbg_context_t ctx, int na, int blocks, const CullArgs& a) {
+static int launch_cull(mbg_context_t ctx, int na, int blocks, const CullArgs& a, const PairListDev* nl = nullptr) {
   switch (na) {
 #define X(N) \
   case N:    \
-    k_cull<N><<<blocks, kCullThreads, 0, ctx->stream>>>(a); \
+    if (nl) k_cull_nl<N><<<blocks, kCullThreads, 0, ctx->stream>>>(a, *nl); \
+    else k_cull<N><<<blocks, kCullThreads, 0, ctx->stream>>>(a); \
     break;
     MBG_FOR_EACH_NA(X)
 #undef X
@@ -733,6 +737,7 @@ static int fill_cell(CellDev& s, const double* cell, double cutoff) {
   if (!hostmath::inverse3(s.rcell, s.rcell_inv)) return fail(MBG_ERR_ARG, "reduced cell is singular");
   const bool ortho = cell[1] == 0 && cell[2] == 0 && cell[3] == 0 && cell[5] == 0 && cell[6] == 0 && cell[7] == 0;
   s.fast_reject = (ortho && cutoff <= s.half_min_len) ? 1 : 0;
+  s.ortho = ortho ? 1 : 0;
   return MBG_OK;
 }
 
@@ -941,6 +946,67 @@ static long long shard_candidates(long long b0, long long blocks, int shard_rank
   return n;
 }
 
+// Pair-list candidate generation (pairlist.cuh): does it apply to this job, and with which pair condition?
+constexpr long long kPairListMinCand = 1ll << 23;  // MBG_CULL_AUTO: candidates per job (all frames) from which it is used
+static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, int n_frames,
+                              long long n_cand_total, int* mode, double* thr) {
+  if (ctx->culling == MBG_CULL_FULL) return false;
+  if (!j.homogeneous || j.explicit_combs || (j.order != 2 && j.order != 3)) return false;
+  if (ctx->culling == MBG_CULL_AUTO && n_cand_total < kPairListMinCand) return false;
+  if ((long long)n_frames * j.n_set >= (1ll << 30)) return false;
+  const CritDev& c = m->crit;
+  const bool upper = c.kind != MBG_CRIT_NONE && (c.bound == MBG_BOUND_UPPER || c.bound == MBG_BOUND_RANGE);
+  *thr = std::numeric_limits<double>::infinity();
+  if (s.periodic) {
+    *mode = 0;
+    if (upper && c.kind == MBG_CRIT_MAX_ATOM_PAIR_DIST) *thr = c.hi;
+    return true;
+  }
+  if (!upper) return false;
+  *thr = c.hi;
+  if (c.kind == MBG_CRIT_MAX_ATOM_PAIR_DIST) {
+    *mode = 2;
+    return true;
+  }
+  // com_distance_sum: the criterion's groups must be the fragment's entities (one group per slot)
+  if (c.n_groups != j.order || j.n_frag_atoms % j.order) return false;
+  const int per = j.n_frag_atoms / j.order;
+  for (int a = 0; a < j.n_frag_atoms; ++a)
+    if (c.group[a] != c.group[a / per * per]) return false;
+  for (int p = 0; p < j.order; ++p)
+    for (int q = p + 1; q < j.order; ++q)
+      if (c.group[p * per] == c.group[q * per]) return false;
+  *mode = 1;
+  return true;
+}
+
+// Build the pair list of a job on the context's stream.  A plain call brings the reduced candidate count to the host
+// (the one synchronisation of this path: it sizes the cull launches and the record buffers by what can be accepted);
+// inside a prepared step (captured graph) the count stays on the device, *n_reduced = -1, and the launches that follow
+// keep the full space as their bound.
+static int build_pair_list(mbg_context_t ctx, Scratch& sc, const SysDev& s, const JobDev& j, const double* dR, int n_frames,
+                           int mode, double thr, PairListDev& nl, long long* n_reduced) {
+  nl.W = (j.n_set + 63) / 64;
+  nl.n_rows = n_frames * j.n_set;
+  nl.mode = mode, nl.thr = thr;
+  TRY(sc.nl_adj.ensure((size_t)nl.n_rows * nl.W * sizeof(unsigned long long)));
+  TRY(sc.nl_deg.ensure((size_t)nl.n_rows * sizeof(int)));
+  TRY(sc.nl_cnt.ensure((size_t)nl.n_rows * sizeof(long long)));
+  TRY(sc.nl_off.ensure(((size_t)nl.n_rows + 1) * sizeof(long long)));
+  nl.adj = sc.nl_adj.as<unsigned long long>(), nl.deg = sc.nl_deg.as<int>();
+  nl.row_cnt = sc.nl_cnt.as<long long>(), nl.row_off = sc.nl_off.as<long long>();
+  k_pair_bits<<<(nl.n_rows + kPairWarps - 1) / kPairWarps, kPairWarps * 32, 0, ctx->stream>>>(s, j, nl, dR);
+  k_scan_rows<<<1, 1024, 0, ctx->stream>>>(nl.row_cnt, nl.n_rows, nl.row_off);
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  *n_reduced = -1;
+  if (ctx->capturing) return MBG_OK;
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_totals, nl.row_off + nl.n_rows, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *n_reduced = ctx->h_totals[0];
+  return MBG_OK;
+}
+
 // Enumerate + cull + compact + contract one job with the persistent contraction kernel: no host synchronisation.
 // Records and flags are sized for the candidates of a chunk (an upper bound of what it accepts); every kernel
 // downstream of the scan reads the accepted count from the device.  The counts for `stats` stay on the device
@@ -948,11 +1014,30 @@ static long long shard_candidates(long long b0, long long blocks, int shard_rank
 static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const JobDev& j, const mbg_model_t m, const double* dR,
                       int n_frames, int shard_rank, int shard_count, bool want_virial, bool decomp, const Outputs& out,
                       int job_slot, long long* n_cand_shard_out) {
-  const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
-  const long long my_granules = shard_blocks(n_cand_total, shard_rank, shard_count);  // blocks of this shard
+  long long n_cand_total = (long long)n_frames * j.cand_per_frame;
+  long long my_granules = shard_blocks(n_cand_total, shard_rank, shard_count);  // blocks of this shard
   const int NA = j.n_frag_atoms;
   *n_cand_shard_out = shard_candidates(0, my_granules, shard_rank, shard_count, n_cand_total);
   if (my_granules == 0) return MBG_OK;
+  // Large homogeneous jobs: cull the pair-list candidates instead of all C(n, order) tuples.  From here on the
+  // "candidate space" that is sharded, chunked and flagged is the reduced one; records come out the same.
+  PairListDev nl;
+  memset(&nl, 0, sizeof(nl));
+  int nl_mode = 0;
+  double nl_thr = 0;
+  const bool use_nl = !decomp && pair_list_applies(ctx, s, j, m, n_frames, n_cand_total, &nl_mode, &nl_thr);
+  if (use_nl) {
+    const long long n_enum_shard = *n_cand_shard_out;  // every tuple of a homogeneous job is ascending
+    long long n_reduced = 0;
+    TRY(build_pair_list(ctx, sc, s, j, dR, n_frames, nl_mode, nl_thr, nl, &n_reduced));
+    k_add_total<<<1, 1, 0, ctx->stream>>>(sc.job_totals.as<long long>() + 2 * (size_t)job_slot + 1, n_enum_shard);
+    ctx->launches++;
+    if (n_reduced >= 0) {
+      n_cand_total = n_reduced;
+      my_granules = shard_blocks(n_cand_total, shard_rank, shard_count);
+      if (my_granules == 0) return MBG_OK;
+    }
+  }
   const size_t rec_bytes = 4 + 4 * (size_t)NA + 8 + 8;
   long long chunk = (long long)((1ull << 30) / (kCullThreads * rec_bytes));  // <= 1 GiB of records per chunk
   chunk = std::min(std::max(chunk, 1ll << 10), std::min(1ll << 18, my_granules));
@@ -976,7 +1061,7 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
     ca.shard_rank = shard_rank, ca.shard_count = shard_count;
     ca.flags = sc.flags.as<unsigned char>();
     ca.block_accept = sc.blk_acc.as<int>(), ca.block_enum = sc.blk_enum.as<int>();
-    TRY(launch_cull(ctx, NA, blocks, ca));
+    TRY(launch_cull(ctx, NA, blocks, ca, use_nl ? &nl : nullptr));
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(sc.blk_acc.as<int>(), sc.blk_enum.as<int>(), blocks,
                                                sc.blk_off.as<long long>(), totals, job_tot);
     CompactArgs pa;
@@ -988,7 +1073,8 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
     pa.rec_base = 0;
     pa.rec_frame = sc.rec_frame.as<int>(), pa.rec_atoms = sc.rec_atoms.as<int>();
     pa.rec_lambda = sc.rec_lambda.as<double>(), pa.rec_slot = sc.rec_slot.as<long long>();
-    k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
+    if (use_nl) k_compact_nl<<<blocks, kCullThreads, 0, ctx->stream>>>(pa, nl);
+    else k_compact<<<blocks, kCullThreads, 0, ctx->stream>>>(pa);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     const long long n_up = shard_candidates(g0, blocks, shard_rank, shard_count, n_cand_total);
@@ -1576,6 +1662,10 @@ static int context_init(mbg_context_t ctx, int device, int sm_count) {
     if (!strcmp(v, "dmma_wave")) ctx->contraction = MBG_CONTRACT_DMMA_WAVE;
   }
   if (const char* v = getenv("MBG_MMA_CFG")) ctx->mma_cfg = atoi(v);
+  if (const char* v = getenv("MBG_CULL")) {  // developer override; mbg_context_set_culling wins
+    if (!strcmp(v, "full")) ctx->culling = MBG_CULL_FULL;
+    if (!strcmp(v, "pairlist")) ctx->culling = MBG_CULL_PAIRLIST;
+  }
   return MBG_OK;
 }
 
@@ -1586,7 +1676,7 @@ int mbg_context_destroy(mbg_context_t ctx) {
   ctx->tab.release();
   ctx->scr.release();
   for (DevBuf* b : {&ctx->R, &ctx->outE, &ctx->outF, &ctx->outV, &ctx->totals, &ctx->exp2_table, &ctx->exp2_table_mma, &ctx->km_in,
-                    &ctx->deferred_totals, &ctx->km_ints, &ctx->km_ints2, &ctx->km_jlist, &ctx->km_out})
+                    &ctx->deferred_totals, &ctx->mask_buf, &ctx->km_ints, &ctx->km_ints2, &ctx->km_jlist, &ctx->km_out})
     b->release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ev_call0) cudaEventDestroy(ctx->ev_call0);
@@ -1616,6 +1706,14 @@ int mbg_context_set_contraction(mbg_context_t ctx, int kind) {
   if (kind != MBG_CONTRACT_AUTO && kind != MBG_CONTRACT_FMA && kind != MBG_CONTRACT_DMMA && kind != MBG_CONTRACT_DMMA_WAVE)
     return fail(MBG_ERR_ARG, "unknown contraction kind %d", kind);
   ctx->contraction = kind;
+  return MBG_OK;
+}
+
+int mbg_context_set_culling(mbg_context_t ctx, int kind) {
+  if (!ctx) return fail(MBG_ERR_ARG, "ctx is NULL");
+  if (kind != MBG_CULL_AUTO && kind != MBG_CULL_FULL && kind != MBG_CULL_PAIRLIST)
+    return fail(MBG_ERR_ARG, "unknown culling kind %d", kind);
+  ctx->culling = kind;
   return MBG_OK;
 }
 
@@ -1994,7 +2092,40 @@ int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc* sys, const double*
     dR = ctx->R.as<double>();
   }
   const long long n_cand_total = (long long)n_frames * j.cand_per_frame;
-  const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads, kChunk = 1ll << 18;
+  const long long kChunk = 1ll << 18;
+  int nl_mode = 0;
+  double nl_thr = 0;
+  if (n_cand_total <= (1ll << 31) && pair_list_applies(ctx, s, j, m, n_frames, n_cand_total, &nl_mode, &nl_thr)) {
+    // Through the pair list: every tuple of a homogeneous job is ascending (flag 2); the accepted ones of the reduced
+    // space set their byte of the full-space mask by their combination rank.
+    PairListDev nl;
+    memset(&nl, 0, sizeof(nl));
+    long long n_reduced = 0;
+    TRY(build_pair_list(ctx, ctx->scr, s, j, dR, n_frames, nl_mode, nl_thr, nl, &n_reduced));
+    TRY(ctx->mask_buf.ensure((size_t)n_cand_total));
+    CUDA_TRY(cudaMemsetAsync(ctx->mask_buf.p, 2, (size_t)n_cand_total, ctx->stream));
+    const long long n_blocks = (n_reduced + kCullThreads - 1) / kCullThreads;
+    for (long long g0 = 0; g0 < n_blocks; g0 += kChunk) {
+      const int blocks = (int)std::min(kChunk, n_blocks - g0);
+      TRY(ctx->scr.flags.ensure((size_t)blocks * kCullThreads));
+      TRY(ctx->scr.blk_acc.ensure((size_t)blocks * sizeof(int)));
+      TRY(ctx->scr.blk_enum.ensure((size_t)blocks * sizeof(int)));
+      CullArgs ca;
+      ca.sys = s, ca.crit = m->crit, ca.job = j, ca.R = dR;
+      ca.n_cand_total = n_reduced, ca.granule0 = g0;
+      ca.shard_rank = 0, ca.shard_count = 1;
+      ca.flags = ctx->scr.flags.as<unsigned char>();
+      ca.block_accept = ctx->scr.blk_acc.as<int>(), ca.block_enum = ctx->scr.blk_enum.as<int>();
+      TRY(launch_cull(ctx, m->n_atoms, blocks, ca, &nl));
+      k_mask_nl<<<blocks, kCullThreads, 0, ctx->stream>>>(ca, nl, ctx->mask_buf.as<unsigned char>(), 0, n_cand_total);
+      ctx->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(mask, ctx->mask_buf.p, (size_t)n_cand_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MBG_OK;
+  }
+  const long long n_granules = (n_cand_total + kCullThreads - 1) / kCullThreads;
   for (long long g0 = 0; g0 < n_granules; g0 += kChunk) {
     const int blocks = (int)std::min(kChunk, n_granules - g0);
     TRY(ctx->scr.flags.ensure((size_t)blocks * kCullThreads));

@@ -23,7 +23,7 @@ struct CellDev {
   double half_min_len;            // 0.5 * min |cell vector|
   double cutoff;                  // Cell.cutoff
   int fast_reject;                // orthorhombic cell and cutoff <= half_min_len: a naive image beyond L_min/2 implies rejection
-  int pad;
+  int ortho;                      // orthorhombic cell: the naive image is the exact minimum image (pairlist.cuh)
 };
 
 // The supersystem on device.

@@ -140,6 +140,39 @@ def test_gpu_kernel_mat_column_subsets_golden():
 
 
 @pytest.mark.gpu
+def test_gpu_torch_assemble_front_end():
+    """``GDMLTorchAssemble`` (torchtools.py:72-398) as ``GDMLTrain._assemble_kernel_mat`` drives it (train.py:1190-1288):
+    sequential column blocks incl. energy-constraint columns in two ``forward`` calls, and the tuple form of a
+    "fancy" column subset, each against the columns of the full matrix."""
+    import torch
+
+    from mbgdml_b200._gdml.torchtools import GDMLTorchAssemble
+    from mbgdml_b200._gdml.train import assemble_kernel_mat
+
+    g = load("train_kernel_cols.npz")
+    R_desc, R_d_desc, tpl, sig = g["R_desc"], g["R_d_desc"], g["tril_perms_lin"], float(g["sig"])
+    T, D = R_desc.shape
+    dim_i = 3 * int((1 + np.sqrt(8 * D + 1)) / 2)
+    for use_E in (False, True):
+        K_full = assemble_kernel_mat(R_desc, R_d_desc, tpl, sig, use_E_cstr=use_E)
+        n_rows = K_full.shape[0]
+        J = list(range(T + (T if use_E else 0)))
+        out, done = np.full((n_rows, n_rows), np.nan), []
+        asm = GDMLTorchAssemble(J, tpl, sig, use_E, torch.from_numpy(R_desc), torch.from_numpy(R_d_desc), out=out,
+                                callback=done.append)
+        asm.forward(torch.arange(0, len(J), 2))
+        assert np.isnan(out).any()
+        asm.forward(torch.arange(1, len(J), 2))
+        assert relerr(out, K_full) <= 1e-12 and sum(done) == n_rows
+        # fancy indexing: partials 1, 4 of point 0, all of point 2, partial 7 of point 5 (+ energy column 3)
+        cols = np.concatenate([[1, 4], 2 * dim_i + np.arange(dim_i), [5 * dim_i + 7], [T * dim_i + 3] if use_E else []]).astype(int)
+        J = [(0, 0, [1, 4]), (2, 2, list(range(dim_i))), (2 + dim_i, 5, [7])] + ([(3 + dim_i, T * dim_i + 3, [0])] if use_E else [])
+        out = torch.full((n_rows, len(cols)), float("nan"), dtype=torch.float64, device="cuda")
+        GDMLTorchAssemble(J, tpl, sig, use_E, torch.from_numpy(R_desc).cuda(), torch.from_numpy(R_d_desc).cuda(), out=out).forward(range(len(J)))
+        assert relerr(out.cpu().numpy(), K_full[:, cols]) <= 1e-12
+
+
+@pytest.mark.gpu
 def test_gpu_kernel_mat_reference_fixture():
     """CUDA path vs. the reference's own tests/data/train/1h2o/K.npy."""
     from mbgdml_b200._gdml.train import assemble_kernel_mat
