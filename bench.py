@@ -303,6 +303,46 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def candidate_generation_record(ctx, n_mol=1000):
+    """How the enumerate -> cull -> compact stage scales beyond the benchmark box (outside the timed region): one frame
+    of n_mol waters at the box's density, cut-off 8 A, 2-body < 6.0 / 3-body < 10.0, through the full enumeration
+    (every C(n, 3) tuple, as the reference does) and through the pair list (csrc/pairlist.cuh).  `ms_*` = device time of
+    everything but the contraction; the accept masks of all candidates are compared byte for byte."""
+    import math
+
+    import mbgdml_b200 as mb
+    from mbgdml_b200 import _engine, synthetic
+    from mbgdml_b200.predictors import accept_mask
+
+    dicts = [synthetic.make_model(["h2o"] * k, n_train=8, sig=[100.0, 400.0][k - 2], seed=k) for k in (2, 3)]
+    models = [mb.gdmlModel(dict(d), criteria=mb.Criteria(mb.com_distance_sum, {"entity_ids": d["entity_ids"]}, c))
+              for d, c in zip(dicts, [6.0, 10.0])]
+    box = 16.12 * (n_mol / 140) ** (1 / 3)
+    Z, R, eids, cids, cell_v = synthetic.make_periodic_box(n_mol=n_mol, box=box, n_frames=1, seed=0, frame_sigma=0.1)
+    cell = mb.Cell(cell_v, cutoff=8.0, pbc=True)
+    pred = mb.mbePredict(models, mb.predict_gdml, periodic_cell=cell)
+    rec = {"workload": f"{n_mol} H2O, one frame, L = {box:.2f} A, cut-off 8 A, com_distance_sum 6.0 / 10.0",
+           "candidates": [math.comb(n_mol, 2), math.comb(n_mol, 3)]}
+    masks = {}
+    try:
+        for kind in ("full", "pairlist"):
+            ctx.set_culling(kind)
+            best = None
+            for _ in range(3):
+                srcs = [mb.gen_combs(pred.get_avail_entities(cids, m.comp_ids)) for m in models]
+                _, _, _, stats = _engine.predict_total(ctx, Z, R, eids, models, srcs, [[], []], cell)
+                t = ctx.last_timing()["ms_other"]
+                best = t if best is None else min(best, t)
+            rec[f"ms_{kind}"] = round(best, 4)
+            rec["accepted"] = [int(s_[2]) for s_ in stats]
+            masks[kind] = accept_mask(Z, R, eids, mb.gen_combs(pred.get_avail_entities(cids, models[1].comp_ids)), models[1], cell)
+    finally:
+        ctx.set_culling("auto")
+    rec["accept_masks_equal"] = bool(np.array_equal(masks["full"], masks["pairlist"]))
+    rec["accepted_in_mask"] = int((masks["pairlist"] == 1).sum())
+    return rec
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -587,6 +627,10 @@ def run_gpu_arm(args):
         }
         parity["ok"] = bool(parity["accept_mask_equal"] and parity["max_rel_err_E"] <= 1e-9 and parity["max_rel_err_F"] <= 1e-9)
 
+    cand_gen = None
+    if world == 1 and not args.no_cull_record:
+        cand_gen = candidate_generation_record(ctx)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -600,7 +644,7 @@ def run_gpu_arm(args):
             "l2": "flushed between steps (256 MiB fill, untimed); model tables are L2-resident by design within a step",
         },
         "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "multi_gpu_check": mg_check,
-        "strong": strong, "graph": graph,
+        "strong": strong, "graph": graph, "candidate_generation": cand_gen,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(R_host.nbytes), "d2h_bytes_per_step": int(8 * n_frames * (1 + 3 * n_atoms))},
         "gpu_launches": int(nl.item()), "clocks": clocks,
@@ -628,6 +672,7 @@ def main():
                     help="weak: --frames per GPU (default); strong: --frames in total, fragments sharded over the GPUs")
     ap.add_argument("--n-train", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cull-record", action="store_true", help="skip the candidate-generation sub-record (1000-H2O frame)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (one 64-H2O structure)")
     ap.add_argument("--contraction", default="auto", choices=["auto", "fma", "dmma", "dmma_wave"],
                     help="contraction kernel: FP64 tensor pipe, persistent per-warp workers (dmma, default), the same "
