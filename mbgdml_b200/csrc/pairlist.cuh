@@ -31,7 +31,16 @@ struct PairListDev {
   long long* row_cnt;       // [n_frames * n_set]: reduced candidates of a row: C(deg, 2) (order 3) or deg (order 2)
   long long* row_off;       // [n_frames * n_set + 1]: exclusive prefix sum of row_cnt; the last entry is the total
   int W;                    // 64-bit words per row
-  int n_rows;               // n_frames * n_set
+  int n_rows;               // n_frames * n0
+  int n0;                   // rows per frame: entities of slot 0 (== n_set for a homogeneous job)
+  // Heterogeneous product spaces ([h2o, h2o, meoh], ...): a row (frame, i0) has one bit set per slot -- `adj` over the
+  // entities of slot 1, `adj2` over those of slot 2 -- with bit p set <=> entity p of that slot is above the row's
+  // entity (the ascending filter of utils.gen_combs, utils.py:479-488) and the pair may pass; the row's reduced
+  // candidates are the deg x deg2 combinations in product order.
+  int hetero;
+  unsigned long long* adj2;  // [n_rows][W2]
+  int* deg2;                 // [n_rows]
+  int W2;
   int mode;                 // 0: periodic cut-off, 1: cluster centre-of-mass distance, 2: cluster first-atom distance
   double thr;               // modes 1, 2: the criterion's upper bound; mode 0: its bound if max_atom_pair_dist, else +inf
 };
@@ -76,11 +85,39 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_pair_bits(const SysDev sys,
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kPairWarps + (threadIdx.x >> 5);
   if (row >= nl.n_rows) return;
-  const int n = job.n_set;
+  const int n = nl.n0;
   const long long frame = row / n;
   const int a = (int)(row - frame * n);
   const double* Rf = R + frame * 3ll * sys.n_atoms;
   const int ea = job.set_ent[a];
+  if (nl.hetero) {
+    int degs[2] = {0, 0};
+    for (int s = 1; s < job.order; ++s) {
+      const int* set = job.set_ent + job.set_off[s];
+      const int ns = job.set_off[s + 1] - job.set_off[s], Ws = s == 1 ? nl.W : nl.W2;
+      unsigned long long* out = s == 1 ? nl.adj + row * nl.W : nl.adj2 + row * nl.W2;
+      int d = 0;
+      for (int w = lane; w < Ws; w += 32) {
+        unsigned long long bits = 0;
+        const int p_hi = min(w * 64 + 64, ns);
+        for (int p = w * 64; p < p_hi; ++p) {
+          const int eb = set[p];
+          if (eb > ea && pair_may_pass(sys, nl, frame, Rf, ea, eb)) bits |= 1ull << (p & 63);
+        }
+        out[w] = bits;
+        d += __popcll(bits);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      degs[s - 1] = d;
+    }
+    if (lane == 0) {
+      nl.deg[row] = degs[0];
+      if (job.order == 3) nl.deg2[row] = degs[1];
+      nl.row_cnt[row] = job.order == 3 ? (long long)degs[0] * degs[1] : degs[0];
+    }
+    return;
+  }
   int deg = 0;
   for (int w = lane; w < nl.W; w += 32) {
     unsigned long long bits = 0;
@@ -163,20 +200,37 @@ __device__ __forceinline__ int select_bit(const unsigned long long* __restrict__
   return -1;
 }
 
-// Reduced candidate g -> (frame, positions in the set, entity tuple).  Returns false when the tuple's last pair is not
-// in the pair list (order 3: c is not a neighbour of b), i.e. the tuple cannot be accepted.
-__device__ __forceinline__ bool decode_reduced(const PairListDev& nl, const JobDev& j, long long g, long long* frame,
-                                               int pos[kMaxOrder], int ent[kMaxOrder]) {
+// Reduced candidate g -> (frame, positions in the slots' sets, entity tuple).  Returns 1 when the tuple goes to the full
+// evaluation, 2 when its last pair is not admissible (order 3: (b, c) fails the pair test), i.e. the tuple cannot be
+// accepted, 0 when it is not ascending (heterogeneous jobs only: utils.gen_combs never yields it).
+__device__ __forceinline__ int decode_reduced(const SysDev& sys, const double* __restrict__ R, const PairListDev& nl,
+                                              const JobDev& j, long long g, long long* frame, int pos[kMaxOrder],
+                                              int ent[kMaxOrder]) {
   int lo = 0, hi = nl.n_rows - 1;  // last row with row_off[row] <= g
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (nl.row_off[mid] <= g) lo = mid; else hi = mid - 1;
   }
   const long long row = lo, local = g - nl.row_off[row];
-  const int n = j.n_set;
+  const int n = nl.n0;
   *frame = row / n;
   pos[0] = (int)(row - *frame * n);
   const unsigned long long* bits = nl.adj + row * nl.W;
+  if (nl.hetero) {
+    ent[0] = j.set_ent[pos[0]];
+    if (j.order == 2) {
+      pos[1] = select_bit(bits, nl.W, (int)local);
+      ent[1] = j.set_ent[j.set_off[1] + pos[1]];
+      return 1;
+    }
+    const long long d2 = nl.deg2[row];
+    pos[1] = select_bit(bits, nl.W, (int)(local / d2));
+    pos[2] = select_bit(nl.adj2 + row * nl.W2, nl.W2, (int)(local % d2));
+    ent[1] = j.set_ent[j.set_off[1] + pos[1]];
+    ent[2] = j.set_ent[j.set_off[2] + pos[2]];
+    if (!(ent[1] < ent[2])) return 0;
+    return pair_may_pass(sys, nl, *frame, R + *frame * 3ll * sys.n_atoms, ent[1], ent[2]) ? 1 : 2;
+  }
   bool ok = true;
   if (j.order == 2) {
     pos[1] = select_bit(bits, nl.W, (int)local);
@@ -195,12 +249,17 @@ __device__ __forceinline__ bool decode_reduced(const PairListDev& nl, const JobD
     ok = (bits_b[pos[2] >> 6] >> (pos[2] & 63)) & 1ull;
   }
   for (int s = 0; s < j.order; ++s) ent[s] = j.set_ent[pos[s]];
-  return ok;
+  return ok ? 1 : 2;
 }
 
 // Lexicographic rank of the combination pos[0] < pos[1] < ... among the C(n_set, order) (inverse of decode_tuple's
 // unranking): the candidate index within the frame, i.e. the row of the decomposed outputs.
 __device__ __forceinline__ long long rank_combination(const JobDev& j, const int pos[kMaxOrder]) {
+  if (!j.homogeneous) {  // product order of the slots' sets, last slot fastest (decode_tuple)
+    long long idx = 0;
+    for (int s = 0; s < j.order; ++s) idx = idx * (j.set_off[s + 1] - j.set_off[s]) + pos[s];
+    return idx;
+  }
   const int n = j.n_set, w = j.order + 1;
   long long rank = 0;
   int prev = -1;
@@ -223,8 +282,9 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_nl(const __grid_constant_
   if (g < nl.row_off[nl.n_rows]) {
     long long frame;
     int pos[kMaxOrder], ent[kMaxOrder];
-    flag = 2;
-    if (decode_reduced(nl, a.job, g, &frame, pos, ent)) {
+    flag = decode_reduced(a.sys, a.R, nl, a.job, g, &frame, pos, ent);
+    if (flag == 1) {
+      flag = 2;
       const double* Rf = a.R + frame * 3ll * a.sys.n_atoms;
       if (first_atoms_may_pass(a.sys, frame, a.job, Rf, ent)) {
         int atoms[kMaxFragAtoms];
@@ -238,7 +298,7 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_nl(const __grid_constant_
   const int n_acc = __syncthreads_count(flag == 1);
   if (threadIdx.x == 0) {
     a.block_accept[blockIdx.x] = n_acc;
-    a.block_enum[blockIdx.x] = 0;  // the enumerated count of a homogeneous job is its candidate count (k_add_total)
+    a.block_enum[blockIdx.x] = 0;  // the enumerated count comes from k_add_total / k_count_ascending
   }
 }
 
@@ -258,7 +318,7 @@ __global__ void __launch_bounds__(kCullThreads) k_compact_nl(const __grid_consta
   const long long g = global_candidate(ca, blockIdx.x, tid);
   long long frame;
   int pos[kMaxOrder], ent[kMaxOrder], atoms[kMaxFragAtoms];
-  decode_reduced(nl, a.job, g, &frame, pos, ent);
+  decode_reduced(a.sys, nullptr, nl, a.job, g, &frame, pos, ent);
   const int na = gather_atoms(a.sys, a.job, ent, atoms);
   a.rec_frame[pos_out] = (int)frame;
   a.rec_slot[pos_out] = rank_combination(a.job, pos);
@@ -273,11 +333,53 @@ __global__ void __launch_bounds__(kCullThreads) k_mask_nl(const __grid_constant_
   const long long g = global_candidate(a, blockIdx.x, threadIdx.x);
   long long frame;
   int pos[kMaxOrder], ent[kMaxOrder];
-  decode_reduced(nl, a.job, g, &frame, pos, ent);
+  decode_reduced(a.sys, nullptr, nl, a.job, g, &frame, pos, ent);
   const long long idx = frame * a.job.cand_per_frame + rank_combination(a.job, pos) - mask_lo;
   if (idx >= 0 && idx < mask_n) mask[idx] = 1;
 }
 
 __global__ void k_add_total(long long* p, long long v) { *p += v; }
+
+// Enumerated count of a heterogeneous job (the ascending tuples of its product space, per frame): one thread per
+// (i0, i1) with ent0 < ent1 adds the entities of slot 2 above ent1 (sets are ascending: binary search).
+__global__ void __launch_bounds__(256) k_count_ascending(const JobDev job, unsigned long long* __restrict__ count) {
+  const int n0 = job.set_off[1] - job.set_off[0], n1 = job.set_off[2] - job.set_off[1];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c = 0;
+  if (t < (long long)n0 * n1) {
+    const int e0 = job.set_ent[t / n1], e1 = job.set_ent[job.set_off[1] + t % n1];
+    if (e0 < e1) {
+      if (job.order == 2) {
+        c = 1;
+      } else {
+        const int* s2 = job.set_ent + job.set_off[2];
+        int lo = 0, hi = job.set_off[3] - job.set_off[2];  // first position with s2[p] > e1
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s2[mid] > e1) hi = mid; else lo = mid + 1;
+        }
+        c = (unsigned long long)(job.set_off[3] - job.set_off[2] - lo);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+// ... times the frames, this shard's share (the pair list shards the reduced space, so the enumerated tuples are
+// attributed evenly: the sum over the shards is the job's count).
+__global__ void k_add_share(long long* p, const unsigned long long* per_frame, long long n_frames, int rank, int count) {
+  const long long total = (long long)*per_frame * n_frames;
+  *p += total / count + (rank < total % count ? 1 : 0);
+}
+
+// mbg_accept_mask through the pair list, heterogeneous jobs: 2 where the tuple is ascending, else 0.
+__global__ void __launch_bounds__(kCullThreads) k_mask_init(const JobDev job, long long n_total, unsigned char* __restrict__ mask) {
+  const long long g = (long long)blockIdx.x * kCullThreads + threadIdx.x;
+  if (g >= n_total) return;
+  int ent[kMaxOrder];
+  mask[g] = decode_tuple(job, g % job.cand_per_frame, ent) ? 2 : 0;
+}
 
 }  // namespace mbg
