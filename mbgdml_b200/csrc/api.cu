@@ -850,6 +850,7 @@ static int build_job(mbg_context_t ctx, Tables& tb, const mbg_system_desc* sys, 
           return fail(MBG_ERR_ARG, "entities of slot %d have different atom counts", s);
       }
       na += slot_atoms < 0 ? 0 : slot_atoms;
+      j.slot_atoms[s] = slot_atoms < 0 ? 0 : slot_atoms;
       const long long n_s = hi - lo;
       if (n_s == 0) prod = 0;
       else if (prod > (1ll << 60) / n_s) return fail(MBG_ERR_UNSUPPORTED, "candidate space overflows");
@@ -951,9 +952,13 @@ constexpr long long kPairListMinCand = 1ll << 23;  // MBG_CULL_AUTO: candidates 
 static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, int n_frames,
                               long long n_cand_total, int* mode, double* thr) {
   if (ctx->culling == MBG_CULL_FULL) return false;
-  if (!j.homogeneous || j.explicit_combs || (j.order != 2 && j.order != 3)) return false;
+  if (j.explicit_combs || (j.order != 2 && j.order != 3)) return false;
   if (ctx->culling == MBG_CULL_AUTO && n_cand_total < kPairListMinCand) return false;
-  if ((long long)n_frames * j.n_set >= (1ll << 30)) return false;
+  const int n0 = j.homogeneous ? j.n_set : j.set_off[1] - j.set_off[0];
+  if ((long long)n_frames * n0 >= (1ll << 30)) return false;
+  if (!j.homogeneous)  // a row's reduced candidates are addressed with 32-bit neighbour indices
+    for (int s = 1; s < j.order; ++s)
+      if (j.set_off[s + 1] - j.set_off[s] > (1 << 24)) return false;
   const CritDev& c = m->crit;
   const bool upper = c.kind != MBG_CRIT_NONE && (c.bound == MBG_BOUND_UPPER || c.bound == MBG_BOUND_RANGE);
   *thr = std::numeric_limits<double>::infinity();
@@ -969,13 +974,16 @@ static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& 
     return true;
   }
   // com_distance_sum: the criterion's groups must be the fragment's entities (one group per slot)
-  if (c.n_groups != j.order || j.n_frag_atoms % j.order) return false;
-  const int per = j.n_frag_atoms / j.order;
-  for (int a = 0; a < j.n_frag_atoms; ++a)
-    if (c.group[a] != c.group[a / per * per]) return false;
+  if (c.n_groups != j.order) return false;
+  int first[kMaxOrder + 1] = {0};
+  for (int p = 0; p < j.order; ++p) first[p + 1] = first[p] + j.slot_atoms[p];
+  if (first[j.order] != j.n_frag_atoms) return false;
+  for (int p = 0; p < j.order; ++p)
+    for (int a = first[p]; a < first[p + 1]; ++a)
+      if (c.group[a] != c.group[first[p]]) return false;
   for (int p = 0; p < j.order; ++p)
     for (int q = p + 1; q < j.order; ++q)
-      if (c.group[p * per] == c.group[q * per]) return false;
+      if (c.group[first[p]] == c.group[first[q]]) return false;
   *mode = 1;
   return true;
 }
@@ -986,14 +994,18 @@ static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& 
 // keep the full space as their bound.
 static int build_pair_list(mbg_context_t ctx, Scratch& sc, const SysDev& s, const JobDev& j, const double* dR, int n_frames,
                            int mode, double thr, PairListDev& nl, long long* n_reduced) {
-  nl.W = (j.n_set + 63) / 64;
-  nl.n_rows = n_frames * j.n_set;
+  nl.hetero = j.homogeneous ? 0 : 1;
+  nl.n0 = j.homogeneous ? j.n_set : j.set_off[1] - j.set_off[0];
+  nl.W = ((j.homogeneous ? j.n_set : j.set_off[2] - j.set_off[1]) + 63) / 64;
+  nl.W2 = (nl.hetero && j.order == 3) ? (j.set_off[3] - j.set_off[2] + 63) / 64 : 0;
+  nl.n_rows = n_frames * nl.n0;
   nl.mode = mode, nl.thr = thr;
-  TRY(sc.nl_adj.ensure((size_t)nl.n_rows * nl.W * sizeof(unsigned long long)));
-  TRY(sc.nl_deg.ensure((size_t)nl.n_rows * sizeof(int)));
+  TRY(sc.nl_adj.ensure((size_t)nl.n_rows * (nl.W + nl.W2) * sizeof(unsigned long long)));
+  TRY(sc.nl_deg.ensure((size_t)nl.n_rows * 2 * sizeof(int)));
   TRY(sc.nl_cnt.ensure((size_t)nl.n_rows * sizeof(long long)));
   TRY(sc.nl_off.ensure(((size_t)nl.n_rows + 1) * sizeof(long long)));
   nl.adj = sc.nl_adj.as<unsigned long long>(), nl.deg = sc.nl_deg.as<int>();
+  nl.adj2 = nl.adj + (size_t)nl.n_rows * nl.W, nl.deg2 = nl.deg + nl.n_rows;
   nl.row_cnt = sc.nl_cnt.as<long long>(), nl.row_off = sc.nl_off.as<long long>();
   k_pair_bits<<<(nl.n_rows + kPairWarps - 1) / kPairWarps, kPairWarps * 32, 0, ctx->stream>>>(s, j, nl, dR);
   k_scan_rows<<<1, 1024, 0, ctx->stream>>>(nl.row_cnt, nl.n_rows, nl.row_off);
@@ -1027,11 +1039,20 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
   double nl_thr = 0;
   const bool use_nl = !decomp && pair_list_applies(ctx, s, j, m, n_frames, n_cand_total, &nl_mode, &nl_thr);
   if (use_nl) {
-    const long long n_enum_shard = *n_cand_shard_out;  // every tuple of a homogeneous job is ascending
     long long n_reduced = 0;
     TRY(build_pair_list(ctx, sc, s, j, dR, n_frames, nl_mode, nl_thr, nl, &n_reduced));
-    k_add_total<<<1, 1, 0, ctx->stream>>>(sc.job_totals.as<long long>() + 2 * (size_t)job_slot + 1, n_enum_shard);
-    ctx->launches++;
+    long long* enum_tot = sc.job_totals.as<long long>() + 2 * (size_t)job_slot + 1;
+    if (j.homogeneous) {  // every tuple is ascending: the enumerated count is this shard's candidate count
+      k_add_total<<<1, 1, 0, ctx->stream>>>(enum_tot, *n_cand_shard_out);
+      ctx->launches++;
+    } else {  // the ascending tuples of the product space, counted on the device; this shard's share of them
+      unsigned long long* cnt = reinterpret_cast<unsigned long long*>(nl.row_cnt);  // row counts are consumed by now
+      const long long pairs = (long long)(j.set_off[1] - j.set_off[0]) * (j.set_off[2] - j.set_off[1]);
+      CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+      k_count_ascending<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(j, cnt);
+      k_add_share<<<1, 1, 0, ctx->stream>>>(enum_tot, cnt, n_frames, shard_rank, shard_count);
+      ctx->launches += 2;
+    }
     if (n_reduced >= 0) {
       n_cand_total = n_reduced;
       my_granules = shard_blocks(n_cand_total, shard_rank, shard_count);
@@ -2103,7 +2124,13 @@ int mbg_accept_mask(mbg_context_t ctx, const mbg_system_desc* sys, const double*
     long long n_reduced = 0;
     TRY(build_pair_list(ctx, ctx->scr, s, j, dR, n_frames, nl_mode, nl_thr, nl, &n_reduced));
     TRY(ctx->mask_buf.ensure((size_t)n_cand_total));
-    CUDA_TRY(cudaMemsetAsync(ctx->mask_buf.p, 2, (size_t)n_cand_total, ctx->stream));
+    if (j.homogeneous) {
+      CUDA_TRY(cudaMemsetAsync(ctx->mask_buf.p, 2, (size_t)n_cand_total, ctx->stream));
+    } else {
+      k_mask_init<<<(unsigned)((n_cand_total + kCullThreads - 1) / kCullThreads), kCullThreads, 0, ctx->stream>>>(
+          j, n_cand_total, ctx->mask_buf.as<unsigned char>());
+      ctx->launches++;
+    }
     const long long n_blocks = (n_reduced + kCullThreads - 1) / kCullThreads;
     for (long long g0 = 0; g0 < n_blocks; g0 += kChunk) {
       const int blocks = (int)std::min(kChunk, n_blocks - g0);

@@ -229,6 +229,7 @@ __device__ __forceinline__ int decode_reduced(const SysDev& sys, const double* _
     ent[1] = j.set_ent[j.set_off[1] + pos[1]];
     ent[2] = j.set_ent[j.set_off[2] + pos[2]];
     if (!(ent[1] < ent[2])) return 0;
+    if (R == nullptr) return 1;  // compaction / mask of an accepted candidate: only the tuple is wanted
     return pair_may_pass(sys, nl, *frame, R + *frame * 3ll * sys.n_atoms, ent[1], ent[2]) ? 1 : 2;
   }
   bool ok = true;

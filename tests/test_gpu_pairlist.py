@@ -142,3 +142,80 @@ def test_predictions_equal_plain_sharded_and_step(ctx):
         Ek, Fk, Vk, stk = _predict(ctx, "full", Z, Rk, eids, cids, models, cell, al)
         assert [s[2] for s in sts] == [s[2] for s in stk]
         assert relerr(Es, Ek) <= 1e-12 and relerr(Fs, Fk) <= 1e-12 and relerr(Vs, Vk) <= 1e-12
+
+
+# ---- heterogeneous product spaces ([h2o, meoh], [h2o, h2o, meoh], ...): one bit row per slot ------------------------
+MIX_FAMILIES = [["h2o", "meoh"], ["h2o", "h2o", "meoh"], ["h2o", "meoh", "meoh"], ["meoh", "meoh", "meoh"]]
+MIX_COMP = ["h2o", "meoh"] * 30 + ["h2o"] * 50 + ["meoh"] * 10  # interleaved ids: the product spaces hold non-ascending tuples
+
+
+def _mix_dicts(n_train=4):
+    return [synthetic.make_model(f, n_train=n_train, sig=100.0 + 50 * k, seed=k + 11) for k, f in enumerate(MIX_FAMILIES)]
+
+
+def test_mixed_box_masks_equal(ctx):
+    """Water-methanol box (config 5's kind of system), entity ids interleaved: 0 (not ascending) / 1 / 2 of every
+    tuple of every product space, two frames."""
+    Z, R, eids, cids, cell_v = synthetic.make_periodic_box(n_mol=len(MIX_COMP), box=17.8, n_frames=2, seed=0, comp=MIX_COMP,
+                                                           frame_sigma=0.1)
+    masks = _masks(ctx, Z, R, eids, cids, b200_models(_mix_dicts(), [6.5, 10.5, 11.0, 11.5]), mb.Cell(cell_v, cutoff=7.5, pbc=True))
+    _assert_same(masks)
+    assert all(int((m == 0).sum()) > 0 for m in masks["pairlist"][:3])
+
+
+@pytest.mark.parametrize("desc,cut", [("com", [6.0, 9.5, 10.0, 10.5]), ("pair", [6.5, 8.0, 8.5, 9.0])])
+def test_mixed_cluster_masks_equal(ctx, desc, cut):
+    Z, R, eids, cids = synthetic.make_cluster(len(MIX_COMP), seed=4, spacing=3.6, comp=MIX_COMP)
+    masks = _masks(ctx, Z, R, eids, cids, b200_models(_mix_dicts(), cut, desc=desc), None)
+    _assert_same(masks)
+
+
+def test_mixed_predictions_equal_plain_sharded_and_step(ctx):
+    dicts = _mix_dicts(n_train=24)
+    Z, R, eids, cids, cell_v = synthetic.make_periodic_box(n_mol=len(MIX_COMP), box=17.8, n_frames=2, seed=2, comp=MIX_COMP,
+                                                           frame_sigma=0.1)
+    cell = mb.Cell(cell_v, pbc=True)
+    models = b200_models(dicts, [6.5, 10.5, 11.0, 11.5])
+    al = [mb.mbeAlchemyScale(1, 3, mb.linear_switching, {"factor": 0.5})]
+    E0, F0, V0, st0 = _predict(ctx, "full", Z, R, eids, cids, models, cell, al)
+    E1, F1, V1, st1 = _predict(ctx, "pairlist", Z, R, eids, cids, models, cell, al)
+    assert st0 == st1 and all(s[2] > 0 for s in st1)
+    assert relerr(E1, E0) <= 1e-12 and relerr(F1, F0) <= 1e-12 and relerr(V1, V0) <= 1e-12
+    parts = [_predict(ctx, "pairlist", Z, R, eids, cids, models, cell, al, shard=(r, 3)) for r in range(3)]
+    for k in range(len(models)):
+        assert [sum(p[3][k][i] for p in parts) for i in range(3)] == list(st0[k])
+    assert relerr(sum(p[0] for p in parts), E0) <= 1e-12 and relerr(sum(p[1] for p in parts), F0) <= 1e-12
+    pred = mb.mbePredict(models, mb.predict_gdml, alchemy_scalers=al, periodic_cell=cell)
+    srcs = [mb.gen_combs(pred.get_avail_entities(cids, m.comp_ids)) for m in models]
+    step = _engine.make_step(ctx, Z, eids, models, srcs, [pred._scalers_for(m) for m in models], cell, 2, compute_virial=True)
+    cells, cutoff = cell.native_cell()
+    Es, Fs, Vs, sts = step.run(R, cells, np.array([cutoff]))
+    assert [tuple(s) for s in sts] == [tuple(s) for s in st0]
+    assert relerr(Es, E0) <= 1e-12 and relerr(Fs, F0) <= 1e-12 and relerr(Vs, V0) <= 1e-12
+
+
+def test_public_api_512_h2o_auto_switch():
+    """MBG_CULL_AUTO through the public API: a 512-H2O frame has 22.2 M trimer candidates (> 2^23), so the plain call
+    (first `predict`) and the prepared step (second `predict`: graph replay, reduced count on the device) both go
+    through the pair list; the same prediction with the full enumeration forced is the reference point."""
+    ctx = _native.get_context()
+    box = 16.12 * (512 / 140) ** (1 / 3)
+    Z, R, eids, cids, cell_v = synthetic.make_periodic_box(n_mol=512, box=box, n_frames=1, seed=9, frame_sigma=0.1)
+    dicts = [synthetic.make_model(["h2o"] * k, n_train=16, sig=s, seed=k) for k, s in ((1, 10.0), (2, 100.0), (3, 400.0))]
+    models = b200_models(dicts, [None, 6.0, 10.0])
+    cell = mb.Cell(cell_v, cutoff=8.0, pbc=True)
+    try:
+        ctx.set_culling("full")
+        ref = mb.mbePredict(models, mb.predict_gdml, periodic_cell=cell)
+        ref.use_graph = False
+        E0, F0 = ref.predict(Z, R, eids, cids)
+        st0 = list(ref.last_stats)
+        ctx.set_culling("auto")
+        pred = mb.mbePredict(models, mb.predict_gdml, periodic_cell=cell)
+        for _ in range(3):
+            E, F = pred.predict(Z, R, eids, cids)
+            assert [tuple(s) for s in pred.last_stats] == [tuple(s) for s in st0]
+            assert relerr(E, E0) <= 1e-12 and relerr(F, F0) <= 1e-12
+    finally:
+        ctx.set_culling("auto")
+    assert st0[2][0] == 22238720 and 50000 < st0[2][2] < 100000
