@@ -30,6 +30,8 @@ class GDMLTorchPredict(nn.Module):
         self.dim_d, self.n_train = model["R_desc"].shape[:2]
         self.n_perms, self.n_atoms = model["perms"].shape
         self.dim_i = 3 * self.n_atoms
+        self._model_dict = model
+        self.R_d_desc = None  # training mode: Jacobians of the training geometries (torchtools.py:702-732)
         self._model = gdmlModel(model, comp_ids=np.array(["mol"]))
         self._std = float(self._model.stdev)
         self._c = float(self._model.integ_c)
@@ -42,12 +44,40 @@ class GDMLTorchPredict(nn.Module):
     def set_n_perm_batches(self, n_perm_batches):  # pylint: disable=unused-argument
         return None
 
+    @staticmethod
+    def _host(x):
+        return np.asarray(x.detach().cpu().numpy() if hasattr(x, "detach") else x, dtype=np.float64)
+
+    def set_R_d_desc(self, R_d_desc):  # pylint: disable=invalid-name
+        """Descriptor Jacobians (n_train, D, 3) of the training geometries (torchtools.py:702-732): with them the
+        training points can be evaluated by index and ``set_alphas`` can reconfigure the model."""
+        self.R_d_desc = self._host(R_d_desc)
+
+    def set_alphas(self, alphas, alphas_E=None):  # pylint: disable=invalid-name
+        """New regression parameters (torchtools.py:734-849): ``R_d_desc_alpha = d_desc_dot_vec(R_d_desc, alphas)``."""
+        assert self.R_d_desc is not None
+        a = self._host(alphas).reshape(-1, self.n_atoms, 3)
+        i, j = np.tril_indices(self.n_atoms, k=-1)
+        model = dict(self._model_dict)
+        model["R_d_desc_alpha"] = np.einsum("tkc,tkc->tk", self.R_d_desc, a[:, j, :] - a[:, i, :])
+        if alphas_E is not None:
+            model["alphas_E"] = self._host(alphas_E)
+        self._model_dict = model
+        self._model = gdmlModel(model, comp_ids=np.array(["mol"]))
+
     def forward(self, Rs_or_train_idxs, return_E=True):
         """(M, N, 3) coordinates -> ``(Es (M,), Fs (M, N, 3))``, or ``(Fs,)`` when ``return_E`` is False
-        (torchtools.py:999-1063).  Evaluating training points by index (a 1-D tensor) is training-side."""
+        (torchtools.py:999-1063).  A 1-D tensor selects training points by index (torchtools.py:861-877; needs
+        ``set_R_d_desc``): their geometries are rebuilt from the model's descriptors and the Jacobians."""
         Rs = Rs_or_train_idxs
         if Rs.dim() == 1:
-            raise NotImplementedError("prediction by training index needs set_R_d_desc(), which is training-side")
+            if self.R_d_desc is None:
+                raise ValueError("set_R_d_desc() must be called before training points can be evaluated by index")
+            from ..gdml_predict import geometries_from_desc
+
+            idx = Rs.detach().cpu().numpy().astype(np.int64)
+            R_desc = np.asarray(self._model_dict["R_desc"], dtype=np.float64).T[idx]
+            Rs = torch.from_numpy(geometries_from_desc(R_desc, self.R_d_desc[idx])).to(Rs.device)
         if Rs.dim() != 3 or Rs.shape[1] != self.n_atoms or Rs.shape[2] != 3:
             raise ValueError(f"Rs must be (M, {self.n_atoms}, 3)")
         M = int(Rs.shape[0])

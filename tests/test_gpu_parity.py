@@ -536,5 +536,48 @@ def test_sgdml_torch_predictor():
     assert not Fc.is_cuda and relerr(Fc.numpy(), F_o) <= TOL
     E_b, F_b = GDMLPredict(md).predict(R.reshape(9, -1))
     assert relerr(E_b, E_o) <= TOL and relerr(F_b.reshape(9, 6, 3), F_o) <= TOL
-    with pytest.raises(NotImplementedError):
-        net(torch.arange(3))
+    with pytest.raises(ValueError):
+        net(torch.arange(3))  # by training index: needs set_R_d_desc (torchtools.py:861-877)
+
+
+def test_sgdml_predictors_training_mode():
+    """The training-side entry points of the bulk predictors (predict.py:485-575, 1108-1120; torchtools.py:702-877):
+    ``predict()`` without R evaluates the cached training descriptors / Jacobians, ``set_alphas`` reconfigures the model,
+    ``forward(train_idxs)`` selects training points.  Checks: (a) against the oracle worker fed with the SAME
+    descriptors and Jacobians; (b) the closed form the iterative solver relies on, F_train = std * K alpha, with K from
+    the kernel-matrix assembly."""
+    import torch
+
+    from mbgdml_b200._gdml.torchtools import GDMLTorchPredict
+    from mbgdml_b200._gdml.train import assemble_kernel_mat
+    from mbgdml_b200.gdml_predict import GDMLPredict, geometries_from_desc
+
+    comp, T, n = ["h2o", "h2o"], 30, 6
+    md = synthetic.make_model(comp, n_train=T, sig=25.0, seed=21, c=-1.5, std=1.3)
+    Rt = synthetic.fragment_geometries(np.random.default_rng(21), comp, T)  # what make_model derived R_desc from
+    X, G = np.zeros((T, 15)), np.zeros((T, 15, 3))
+    for t in range(T):
+        X[t], G[t] = orc.from_r(Rt[t].reshape(-1))
+    assert relerr(X, md["R_desc"].T) <= 1e-14
+    assert relerr(geometries_from_desc(X, G), Rt - Rt[:, :1]) <= 1e-13
+    gp = GDMLPredict(dict(md))
+    with pytest.raises(ValueError):
+        gp.predict()
+    gp.set_R_desc(X), gp.set_R_d_desc(G)
+    E, F = gp.predict()
+    om = orc.Model(dict(md))
+    for t in range(T):
+        out = orc.predict_gdml_wkr(X[t], G[t], n, om.sig, om.n_perms, om.R_desc_perms, om.R_d_desc_alpha_perms)
+        assert abs(E[t] - (out[0] * md["std"] + md["c"])) <= TOL * abs(E[t]) and relerr(F[t], out[1:] * md["std"]) <= TOL
+    # (b) new alphas: forces on the training points are std * K alpha
+    alpha = np.random.default_rng(22).normal(size=T * 3 * n)
+    K = assemble_kernel_mat(X, G, md["tril_perms_lin"], md["sig"])
+    gp.set_alphas(alpha)
+    (F2,) = gp.predict(return_E=False)
+    assert relerr(F2, md["std"] * (K @ alpha).reshape(T, -1)) <= 1e-9
+    net = GDMLTorchPredict(dict(md))
+    net.set_R_d_desc(torch.from_numpy(G))
+    net.set_alphas(torch.from_numpy(alpha))
+    idx = torch.tensor([4, 0, 17], device="cuda")
+    Es, Fs = net(idx)
+    assert Fs.is_cuda and relerr(Fs.cpu().numpy().reshape(3, -1), F2[[4, 0, 17]]) <= 1e-12
