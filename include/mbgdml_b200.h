@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MBG_ABI_VERSION 2
+#define MBG_ABI_VERSION 3
 
 #define MBG_OK 0
 #define MBG_ERR_ARG (-1)         /* invalid argument (the Python mirror raises ValueError/AssertionError) */
@@ -105,6 +105,8 @@ typedef struct mbg_system_desc {
    * of the finite-difference virial (stress.py:75-152) evaluated as ONE 18-frame call.                     */
   const double *frame_cells;     /* [n_frames][9] or NULL                                                  */
   const double *frame_cutoffs;   /* [n_frames] Cell.cutoff of each frame's cell (required with frame_cells) */
+  const int32_t *pbc;            /* [3] Cell.pbc (periodic.py:40-59): 0 = not periodic along that cell vector, or NULL =
+                                    periodic in all three (find_mic(d, cell_v, pbc), periodic.py:78)            */
 } mbg_system_desc;
 
 /* One model applied to the system: the fragments it predicts and its alchemical scalers. */
@@ -238,13 +240,13 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
 /* Cell.r_mic (periodic.py:86-107) on device for one fragment: r[n][3] -> out[n][3];
  * *accepted = 0 when any pair distance >= cutoff (the reference returns None). */
 int mbg_r_mic(mbg_context_t ctx, const double *cell, double cutoff, const double *r, int32_t n,
-              double *out, int32_t *accepted);
+              double *out, int32_t *accepted, const int32_t *pbc /* [3] or NULL = all periodic */);
 
 /* Cell.d_mic (periodic.py:61-84) on device: minimum image of n displacement vectors d[n][3] -> out[n][3]; with
  * check_cutoff, *accepted = 0 when any pair distance among the imaged vectors is >= cutoff (the reference returns
  * None); without it *accepted = 1. */
 int mbg_d_mic(mbg_context_t ctx, const double *cell, double cutoff, const double *d, int32_t n, int32_t check_cutoff,
-              double *out, int32_t *accepted);
+              double *out, int32_t *accepted, const int32_t *pbc /* [3] or NULL = all periodic */);
 
 /* mbe_worker + the add/remove step of mbe_contrib (mbe.py:73-197, 381-427), used by decomp_to_total
  * (mbe.py:432-508): for each selected reference structure i (row ref_rows[i] of E[n_total] /

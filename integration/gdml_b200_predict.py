@@ -33,7 +33,7 @@ class _ModelDesc(C.Structure):  # struct mbg_model_desc (include/mbgdml_b200.h),
 
 class _SystemDesc(C.Structure):  # struct mbg_system_desc
     _fields_ = [("n_atoms", C.c_int32), ("n_entities", C.c_int32), ("entity_offsets", _ip), ("entity_atoms", _ip),
-                ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double), ("frame_cells", _dp), ("frame_cutoffs", _dp)]
+                ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double), ("frame_cells", _dp), ("frame_cutoffs", _dp), ("pbc", _ip)]
 
 
 class _Job(C.Structure):  # struct mbg_job
@@ -128,16 +128,15 @@ def _system(Z, entity_ids, periodic_cell, keep):
     offs = np.zeros(int(entity_ids.max()) + 2, dtype=np.int32)
     offs[1:] = np.cumsum(np.bincount(entity_ids))
     masses = np.array([to_mass(int(z)) for z in Z], dtype=np.float64)
-    cell, cutoff = None, 0.0
+    cell, cutoff, pbc = None, 0.0, None
     if periodic_cell:
-        if not np.all(periodic_cell.pbc):
-            raise NotImplementedError("only pbc=True in all directions")
         cell = np.ascontiguousarray(periodic_cell.cell_v, dtype=np.float64).reshape(9)
         cutoff = float(periodic_cell.cutoff)
-    keep += [order, offs, masses, cell]
+        pbc = np.ascontiguousarray(np.broadcast_to(np.asarray(periodic_cell.pbc, dtype=bool), (3,)), dtype=np.int32)
+    keep += [order, offs, masses, cell, pbc]
     return _SystemDesc(len(Z), len(offs) - 1, offs.ctypes.data_as(_ip), order.ctypes.data_as(_ip),
                        masses.ctypes.data_as(_dp), cell.ctypes.data_as(_dp) if cell is not None else _dp(), cutoff,
-                       _dp(), _dp())
+                       _dp(), _dp(), pbc.ctypes.data_as(_ip) if pbc is not None else _ip())
 
 
 def _job(model, entity_combs, scalers, keep):

@@ -34,15 +34,19 @@ class System:
         np.cumsum(counts, out=self.entity_offsets[1:])
         self.masses = _native.as_f64(masses_of(Z, strict=need_masses))
         self.cell = None
+        self.pbc = None  # int32[3] when a direction is not periodic (Cell.pbc)
         cutoff = 0.0
         if periodic_cell is not None:
             self.cell, cutoff = periodic_cell.native_cell()
+            self.pbc = periodic_cell.native_pbc()
         self.frame_cells = self.frame_cutoffs = None
-        if frame_cells is not None:  # one cell per frame: (cells (n, 3, 3), cutoffs (n,))
+        if frame_cells is not None:  # one cell per frame: (cells (n, 3, 3), cutoffs (n,)[, pbc int32[3]])
             self.frame_cells = _native.as_f64(frame_cells[0]).reshape(-1, 9)
             self.frame_cutoffs = _native.as_f64(frame_cells[1]).reshape(-1)
             if len(self.frame_cells) != len(self.frame_cutoffs):
                 raise ValueError("one cutoff per frame cell")
+            if len(frame_cells) > 2 and frame_cells[2] is not None:  # Cell.pbc shared by all frames
+                self.pbc = _native.as_i32(frame_cells[2])
         self.desc = _native.SystemDesc(
             n_atoms=self.n_atoms, n_entities=self.n_entities,
             entity_offsets=_native.ptr(self.entity_offsets, _native._ip),
@@ -50,6 +54,7 @@ class System:
             masses=_native.ptr(self.masses, _native._dp),
             cell=_native.ptr(self.cell, _native._dp), cell_cutoff=cutoff,
             frame_cells=_native.ptr(self.frame_cells, _native._dp), frame_cutoffs=_native.ptr(self.frame_cutoffs, _native._dp),
+            pbc=_native.ptr(self.pbc, _native._ip),
         )
 
 
@@ -66,7 +71,8 @@ def cached_system(Z, entity_ids, periodic_cell, need_masses):
     cell_key = None
     if periodic_cell is not None:
         cell, cutoff = periodic_cell.native_cell()
-        cell_key = (cell.tobytes(), float(cutoff))
+        pbc = periodic_cell.native_pbc()
+        cell_key = (cell.tobytes(), float(cutoff), None if pbc is None else pbc.tobytes())
     hit = _last_system
     if (hit is not None and hit[2] == cell_key and hit[3] == bool(need_masses) and hit[0].shape == Z.shape
             and hit[1].shape == entity_ids.shape and np.array_equal(hit[0], Z) and np.array_equal(hit[1], entity_ids)):
@@ -145,6 +151,8 @@ class StepCache:
     @staticmethod
     def small_key(models, scalers_per_model, n_frames, periodic_cell, frame_cells, compute_virial):
         cell_kind = "frames" if frame_cells is not None else ("cell" if periodic_cell is not None else None)
+        if cell_kind == "cell" and periodic_cell.native_pbc() is not None:  # the step keeps Cell.pbc from its creation
+            cell_kind = ("cell", periodic_cell.native_pbc().tobytes())
         return (tuple((m._uid, m._criteria_key()) for m in models),
                 tuple(tuple((s.entity_id, s.order, s.native_factor()) for s in (sc or [])) for sc in scalers_per_model),
                 int(n_frames), cell_kind, bool(compute_virial))

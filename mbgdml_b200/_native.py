@@ -57,6 +57,7 @@ class SystemDesc(C.Structure):
     _fields_ = [
         ("n_atoms", C.c_int32), ("n_entities", C.c_int32), ("entity_offsets", _ip), ("entity_atoms", _ip),
         ("masses", _dp), ("cell", _dp), ("cell_cutoff", C.c_double), ("frame_cells", _dp), ("frame_cutoffs", _dp),
+        ("pbc", _ip),
     ]
 
 
@@ -118,8 +119,8 @@ def load_library():
         lib.mbg_enumerate.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, _lp]
         lib.mbg_from_r.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp]
         lib.mbg_criteria_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _ip, _dp, C.c_int64, _dp]
-        lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip]
-        lib.mbg_d_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, C.c_int32, _dp, _ip]
+        lib.mbg_r_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, _dp, _ip, _ip]
+        lib.mbg_d_mic.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int32, C.c_int32, _dp, _ip, _ip]
         lib.mbg_mbe_accumulate.argtypes = [C.c_void_p, C.c_int64, _lp, _lp, _lp, _ip, C.c_int32, C.c_int32, _ip, _ip,
                                            C.c_int32, _ip, _ip, _dp, _dp, C.c_int64, C.c_double, _dp, _dp, C.c_int64]
         lib.mbg_kernel_mat.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _lp, C.c_double, C.c_int32,
@@ -386,22 +387,22 @@ class Context:
                                       rows.shape[0], ptr(out, _dp)))
         return out
 
-    def d_mic(self, cell, cutoff, d, check_cutoff=True):
+    def d_mic(self, cell, cutoff, d, check_cutoff=True, pbc=None):
         d = as_f64(d)
         cell = as_f64(cell).reshape(9)
         out = np.zeros_like(d)
         acc = C.c_int32(0)
         check(self.lib.mbg_d_mic(self.handle, ptr(cell, _dp), float(cutoff), ptr(d, _dp), d.shape[0], int(bool(check_cutoff)),
-                                 ptr(out, _dp), C.byref(acc)))
+                                 ptr(out, _dp), C.byref(acc), ptr(pbc, _ip)))
         return out, bool(acc.value)
 
-    def r_mic(self, cell, cutoff, r):
+    def r_mic(self, cell, cutoff, r, pbc=None):
         r = as_f64(r)
         cell = as_f64(cell).reshape(9)
         out = np.zeros_like(r)
         acc = C.c_int32(0)
         check(self.lib.mbg_r_mic(self.handle, ptr(cell, _dp), float(cutoff), ptr(r, _dp), r.shape[0], ptr(out, _dp),
-                                 C.byref(acc)))
+                                 C.byref(acc), ptr(pbc, _ip)))
         return out, bool(acc.value)
 
 

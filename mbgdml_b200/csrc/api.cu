@@ -722,9 +722,11 @@ __global__ void k_r_mic(CellDev s, const double* r, int n, double* out, int* acc
 // ------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------
-static int fill_cell(CellDev& s, const double* cell, double cutoff) {
+static int fill_cell(CellDev& s, const double* cell, double cutoff, const int32_t* pbc = nullptr) {
   memset(&s, 0, sizeof(s));
   s.cutoff = cutoff;
+  for (int i = 0; i < 3; ++i) s.pbc[i] = (!pbc || pbc[i]) ? 1 : 0;
+  const bool full = s.pbc[0] && s.pbc[1] && s.pbc[2];
   memcpy(s.cell, cell, 9 * sizeof(double));
   if (!hostmath::inverse3(s.cell, s.cell_inv)) return fail(MBG_ERR_ARG, "cell is singular");
   double mn = std::numeric_limits<double>::infinity();
@@ -732,12 +734,13 @@ static int fill_cell(CellDev& s, const double* cell, double cutoff) {
     const double* v = cell + 3 * i;
     mn = std::min(mn, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
   }
-  s.half_min_len = 0.5 * mn;
-  if (!hostmath::minkowski_reduce(s.cell, s.rcell)) return fail(MBG_ERR_ARG, "Minkowski reduction of the cell failed");
+  // find_mic tries the naive image only when all three directions are periodic (dim == 3)
+  s.half_min_len = full ? 0.5 * mn : -1.0;
+  if (!hostmath::minkowski_reduce_pbc(s.cell, s.pbc, s.rcell)) return fail(MBG_ERR_ARG, "Minkowski reduction of the cell failed");
   if (!hostmath::inverse3(s.rcell, s.rcell_inv)) return fail(MBG_ERR_ARG, "reduced cell is singular");
   const bool ortho = cell[1] == 0 && cell[2] == 0 && cell[3] == 0 && cell[5] == 0 && cell[6] == 0 && cell[7] == 0;
-  s.fast_reject = (ortho && cutoff <= s.half_min_len) ? 1 : 0;
-  s.ortho = ortho ? 1 : 0;
+  s.fast_reject = (full && ortho && cutoff <= s.half_min_len) ? 1 : 0;
+  s.ortho = (full && ortho) ? 1 : 0;
   return MBG_OK;
 }
 
@@ -748,11 +751,11 @@ static int build_cells(const mbg_system_desc* sys, int n_frames, std::vector<Cel
   if (sys->frame_cells) {
     if (!sys->frame_cutoffs) return fail(MBG_ERR_ARG, "frame_cells without frame_cutoffs");
     cells.resize(std::max(n_frames, 0));
-    for (int f = 0; f < n_frames; ++f) TRY(fill_cell(cells[f], sys->frame_cells + 9 * (size_t)f, sys->frame_cutoffs[f]));
+    for (int f = 0; f < n_frames; ++f) TRY(fill_cell(cells[f], sys->frame_cells + 9 * (size_t)f, sys->frame_cutoffs[f], sys->pbc));
     *stride = 1;
   } else if (sys->cell) {
     cells.resize(1);
-    TRY(fill_cell(cells[0], sys->cell, sys->cell_cutoff));
+    TRY(fill_cell(cells[0], sys->cell, sys->cell_cutoff, sys->pbc));
   }
   return MBG_OK;
 }
@@ -1414,6 +1417,7 @@ struct mbg_step_s {
   long long* h_tot = nullptr;  // [n_jobs][2]
   size_t n_out = 0;
   int shard_rank = 0, shard_count = 1;
+  int32_t pbc[3] = {1, 1, 1};  // Cell.pbc of the system the step was created for (new cells keep it)
   cudaGraph_t graph = nullptr, graph_dev = nullptr;  // with / without the host <-> device copies
   cudaGraphExec_t exec = nullptr, exec_dev = nullptr;
 };
@@ -1491,6 +1495,8 @@ extern "C" int mbg_step_create(mbg_context_t ctx, const mbg_system_desc* sys, in
   memset(&st->sys, 0, sizeof(st->sys));
   if ((rc = upload_system(ctx, st->tab, sys, n_frames, st->sys)) != MBG_OK) return bail(rc);
   st->n_cells = (int)st->tab.h_cells.size();
+  if (sys->pbc)
+    for (int i = 0; i < 3; ++i) st->pbc[i] = sys->pbc[i] ? 1 : 0;
   size_t total = 0;
   for (int q = 0; q < n_jobs; ++q) {
     const mbg_job& jq = jobs[q];
@@ -1557,7 +1563,7 @@ extern "C" int mbg_step_run(mbg_step_t st, const double* R, const double* cells,
     if (!cutoffs) return fail(MBG_ERR_ARG, "cells without cutoffs");
     for (int c = 0; c < st->n_cells; ++c)
       if (memcmp(st->h_cells[c].cell, cells + 9 * (size_t)c, 9 * sizeof(double)) != 0 || st->h_cells[c].cutoff != cutoffs[c])
-        TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c]));
+        TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c], st->pbc));
   }
   if (direct) {
     const double* o = st->dOut.as<double>();
@@ -1598,7 +1604,7 @@ extern "C" int mbg_step_run_device(mbg_step_t st, const double* dR, const double
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the pinned cell table may still be read by the previous replay
     for (int c = 0; c < st->n_cells; ++c)
       if (memcmp(st->h_cells[c].cell, cells + 9 * (size_t)c, 9 * sizeof(double)) != 0 || st->h_cells[c].cutoff != cutoffs[c])
-        TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c]));
+        TRY(fill_cell(st->h_cells[c], cells + 9 * (size_t)c, cutoffs[c], st->pbc));
   }
   CUDA_TRY(cudaMemcpyAsync(st->dR.p, dR, nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CUDA_TRY(cudaGraphLaunch(st->exec_dev, ctx->stream));
@@ -2271,12 +2277,12 @@ int mbg_criteria_eval(mbg_context_t ctx, int32_t kind, int32_t n_atoms, const do
 }
 
 int mbg_d_mic(mbg_context_t ctx, const double* cell, double cutoff, const double* d, int32_t n, int32_t check_cutoff,
-              double* out, int32_t* accepted) {
+              double* out, int32_t* accepted, const int32_t* pbc) {
   if (!ctx || !cell || !d || !out || !accepted) return fail(MBG_ERR_ARG, "NULL argument");
   if (n < 1) return fail(MBG_ERR_ARG, "n < 1");
   CUDA_TRY(cudaSetDevice(ctx->device));
   CellDev s;
-  TRY(fill_cell(s, cell, cutoff));
+  TRY(fill_cell(s, cell, cutoff, pbc));
   TRY(ctx->R.ensure((size_t)n * 3 * sizeof(double)));
   TRY(ctx->outF.ensure((size_t)n * 3 * sizeof(double)));
   TRY(ctx->totals.ensure(2 * sizeof(long long)));
@@ -2319,12 +2325,12 @@ int mbg_from_r(mbg_context_t ctx, int32_t n_atoms, const double* lattice, const 
 }
 
 int mbg_r_mic(mbg_context_t ctx, const double* cell, double cutoff, const double* r, int32_t n, double* out,
-              int32_t* accepted) {
+              int32_t* accepted, const int32_t* pbc) {
   if (!ctx || !cell || !r || !out || !accepted) return fail(MBG_ERR_ARG, "NULL argument");
   if (n < 1) return fail(MBG_ERR_ARG, "n < 1");
   CUDA_TRY(cudaSetDevice(ctx->device));
   CellDev s;
-  TRY(fill_cell(s, cell, cutoff));
+  TRY(fill_cell(s, cell, cutoff, pbc));
   s.fast_reject = 0;  // the caller wants the coordinates even when the fragment is rejected
   TRY(ctx->R.ensure((size_t)n * 3 * sizeof(double)));
   TRY(ctx->outF.ensure((size_t)n * 3 * sizeof(double)));

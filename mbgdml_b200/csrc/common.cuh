@@ -23,7 +23,10 @@ struct CellDev {
   double half_min_len;            // 0.5 * min |cell vector|
   double cutoff;                  // Cell.cutoff
   int fast_reject;                // orthorhombic cell and cutoff <= half_min_len: a naive image beyond L_min/2 implies rejection
-  int ortho;                      // orthorhombic cell: the naive image is the exact minimum image (pairlist.cuh)
+  int ortho;                      // orthorhombic, fully periodic cell: the naive image is the exact minimum image (pairlist.cuh)
+  int pbc[3];                     // 1: periodic along this cell vector (Cell.pbc, periodic.py:40-59).  With a 0 entry find_mic
+                                  // always takes the general branch: half_min_len = -1 makes every "naive image is safe" test fail
+  int pad;
 };
 
 // The supersystem on device.

@@ -38,22 +38,29 @@ __device__ __forceinline__ double mic_naive(const CellDev& s, const double v[3],
   return norm3_rn(out[0], out[1], out[2]);
 }
 
-// ase.geometry.general_find_mic on the Minkowski-reduced cell: wrap into [0,1)^3, then the
-// shortest of (0,0,0) followed by itertools.product([-1,0,1], repeat=3); first minimum wins.
+// ase.geometry.general_find_mic on the Minkowski-reduced cell: wrap the periodic fractional coordinates into [0,1),
+// then the shortest of (0,0,0) followed by itertools.product of [-1,0,1] over the periodic directions ([0] over the
+// others); first minimum wins.  No periodic direction at all: the vector itself (find_mic copies it).
 __device__ __noinline__ void mic_general(const CellDev& s, const double v[3], double out[3]) {
+  const int l0 = s.pbc[0], l1 = s.pbc[1], l2 = s.pbc[2];
+  if (!(l0 | l1 | l2)) {
+    out[0] = v[0], out[1] = v[1], out[2] = v[2];
+    return;
+  }
   double f[3], pos[3];
   vec_mat_rn(v, s.rcell_inv, f);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) f[i] = __dsub_rn(f[i], floor(f[i]));
+  for (int i = 0; i < 3; ++i)
+    if (s.pbc[i]) f[i] = __dsub_rn(f[i], floor(f[i]));
   vec_mat_rn(f, s.rcell, pos);
   double best = norm3_rn(pos[0], pos[1], pos[2]);
   out[0] = pos[0], out[1] = pos[1], out[2] = pos[2];
 #pragma unroll 1
-  for (int h = -1; h <= 1; ++h)
+  for (int h = -l0; h <= l0; ++h)
 #pragma unroll 1
-    for (int k = -1; k <= 1; ++k)
+    for (int k = -l1; k <= l1; ++k)
 #pragma unroll 1
-      for (int l = -1; l <= 1; ++l) {
+      for (int l = -l2; l <= l2; ++l) {
         const double hkl[3] = {(double)h, (double)k, (double)l};
         double sh[3], x[3];
         vec_mat_rn(hkl, s.rcell, sh);

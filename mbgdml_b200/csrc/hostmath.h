@@ -137,5 +137,53 @@ inline bool minkowski_reduce(const double* B, double* rcell) {
   return true;
 }
 
+// ase.geometry.minkowski_reduce(cell, pbc) with a non-periodic direction: two periodic directions are Gauss-reduced
+// (periodic vectors permuted to the front, shorter first, reduced, permutation undone, handedness kept -- judged with
+// the plane normal in place of the non-periodic vector); one or none: the cell is left alone.
+inline bool minkowski_reduce_pbc(const double* B, const int pbc[3], double* rcell) {
+  const int dim = (pbc[0] != 0) + (pbc[1] != 0) + (pbc[2] != 0);
+  if (dim == 3) return minkowski_reduce(B, rcell);
+  long long op[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  if (dim == 2) {
+    int asc[3] = {0, 1, 2};
+    std::stable_sort(asc, asc + 3, [&](int x, int y) { return (pbc[x] != 0) < (pbc[y] != 0); });
+    const int perm[3] = {asc[2], asc[1], asc[0]};  // np.argsort(pbc, kind='merge')[::-1]
+    double P[9];
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) P[3 * i + k] = B[3 * perm[i] + perm[k]];
+    const double n0 = std::sqrt(P[0] * P[0] + P[1] * P[1] + P[2] * P[2]), n1 = std::sqrt(P[3] * P[3] + P[4] * P[4] + P[5] * P[5]);
+    I3 hu = {1, 0, 0}, hv = {0, 1, 0};
+    if (n1 < n0) std::swap(hu, hv);  // op = eye[argsort(norms)], the non-periodic vector last
+    gauss_reduce(P, hu, hv);
+    const long long opP[3][3] = {{hu[0], hu[1], hu[2]}, {hv[0], hv[1], hv[2]}, {0, 0, 1}};
+    int inv[3];
+    for (int i = 0; i < 3; ++i) inv[perm[i]] = i;
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) op[i][k] = opP[inv[i]][inv[k]];
+    const int index = pbc[0] ? (pbc[1] ? 2 : 1) : 0;  // np.argmin(pbc)
+    const int ia = (index + 1) % 3, ib = (index + 2) % 3;  // cell[index - 2], cell[index - 1]
+    auto rowof = [&](const long long h[3], double out[3]) {
+      for (int k = 0; k < 3; ++k) out[k] = (double)h[0] * B[k] + (double)h[1] * B[3 + k] + (double)h[2] * B[6 + k];
+    };
+    const double* a = B + 3 * ia;
+    const double* b = B + 3 * ib;
+    const double nrm[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    auto det_with_normal = [&](const double M[9]) {
+      double C[9];
+      for (int k = 0; k < 9; ++k) C[k] = M[k];
+      for (int k = 0; k < 3; ++k) C[3 * index + k] = nrm[k];
+      return C[0] * (C[4] * C[8] - C[5] * C[7]) - C[1] * (C[3] * C[8] - C[5] * C[6]) + C[2] * (C[3] * C[7] - C[4] * C[6]);
+    };
+    double R1[9];
+    for (int i = 0; i < 3; ++i) rowof(op[i], R1 + 3 * i);
+    if ((det_with_normal(B) > 0) != (det_with_normal(R1) > 0))
+      for (int k = 0; k < 3; ++k) op[ib][k] = -op[ib][k];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k)
+      rcell[3 * i + k] = (double)op[i][0] * B[k] + (double)op[i][1] * B[3 + k] + (double)op[i][2] * B[6 + k];
+  return true;
+}
+
 }  // namespace hostmath
 }  // namespace mbg

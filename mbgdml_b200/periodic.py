@@ -32,12 +32,13 @@ class Cell:
         vec = self.cell_v
         return np.dot(vec[2], np.cross(vec[0], vec[1]))
 
-    def _check_pbc(self):
-        if not np.all(np.broadcast_to(np.asarray(self.pbc, dtype=bool), (3,))):
-            raise NotImplementedError("only pbc=True in all three directions is implemented on device")
+    def native_pbc(self):
+        """``pbc`` as the three flags ``find_mic(d, cell_v, pbc=self.pbc)`` sees (periodic.py:78; ASE's ``pbc2pbc``
+        broadcasts a scalar), int32[3]; ``None`` when all three directions are periodic."""
+        flags = np.ascontiguousarray(np.broadcast_to(np.asarray(self.pbc, dtype=bool), (3,)), dtype=np.int32)
+        return None if flags.all() else flags
 
     def native_cell(self):
-        self._check_pbc()
         return np.ascontiguousarray(self.cell_v, dtype=np.float64).reshape(9), float(self.cutoff)
 
     def r_mic(self, r):
@@ -45,7 +46,7 @@ class Cell:
         or ``None`` if any pair distance is >= cutoff."""
         assert np.ndim(r) == 2
         cell, cutoff = self.native_cell()
-        out, ok = _native.get_context().r_mic(cell, cutoff, r)
+        out, ok = _native.get_context().r_mic(cell, cutoff, r, pbc=self.native_pbc())
         return out if ok else None
 
     def d_mic(self, d, check_cutoff=True):
@@ -54,7 +55,7 @@ class Cell:
         d = np.asarray(d, dtype=np.float64)
         assert d.ndim == 2
         cell, cutoff = self.native_cell()
-        out, ok = _native.get_context().d_mic(cell, cutoff, d, check_cutoff=check_cutoff)
+        out, ok = _native.get_context().d_mic(cell, cutoff, d, check_cutoff=check_cutoff, pbc=self.native_pbc())
         if check_cutoff and not ok:
             return None
         return out

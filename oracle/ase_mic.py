@@ -21,7 +21,12 @@ after Nguyen & Stehle 2009):
 PARITY UNPINNED: there is no real ASE here and the reference has no test of
 its periodic path, so this restatement is checked only
 against a brute-force image search (tests/test_oracle_mic.py).
-Partial periodicity (a False entry in pbc) is not restated.
+Partial periodicity (a False entry in pbc): find_mic then always takes the general
+branch; minkowski_reduce Gauss-reduces the two periodic vectors when two directions
+are periodic (permute periodic first, reduce, undo the permutation, keep the
+handedness) and leaves the cell alone when one is; wrap_positions wraps the periodic
+fractional coordinates only and the image search runs over the periodic directions
+only.  Checked against a brute-force search over the periodic images.
 """
 import itertools
 
@@ -108,12 +113,33 @@ def _reduction_full(B):
     raise RuntimeError("Reduced basis not found")
 
 
-def minkowski_reduce(cell):
-    """Return (reduced_cell, op) with reduced_cell = op @ cell (fully periodic 3-D)."""
+def minkowski_reduce(cell, pbc=True):
+    """Return (reduced_cell, op) with reduced_cell = op @ cell; only the periodic directions are reduced."""
     cell = np.asarray(cell, dtype=float)
-    _, op = _reduction_full(cell)
-    if np.sign(np.linalg.det(cell)) != np.sign(np.linalg.det(op @ cell)):
-        op = -op
+    pbc = _pbc3(pbc)
+    dim = int(pbc.sum())
+    op = np.eye(3, dtype=int)
+    if dim == 2:
+        perm = np.argsort(pbc, kind="merge")[::-1]  # periodic directions first
+        pcell = cell[perm][:, perm]
+        norms = np.linalg.norm(pcell, axis=1)
+        norms[2] = float("inf")
+        op = op[np.argsort(norms)]
+        hu, hv = _reduction_gauss(pcell, op[0], op[1])
+        op[0], op[1] = hu, hv
+        invperm = np.argsort(perm)
+        op = op[invperm][:, invperm]
+        index = int(np.argmin(pbc))  # the non-periodic direction: handedness judged with the plane normal in its place
+        normal = np.cross(cell[index - 2], cell[index - 1])
+        normal /= np.linalg.norm(normal)
+        c0, c1 = cell.copy(), op @ cell
+        c0[index], c1[index] = normal, normal
+        if np.sign(np.linalg.det(c0)) != np.sign(np.linalg.det(c1)):
+            op[index - 1] *= -1
+    elif dim == 3:
+        _, op = _reduction_full(cell)
+        if np.sign(np.linalg.det(cell)) != np.sign(np.linalg.det(op @ cell)):
+            op = -op
     norms1 = np.sort(np.linalg.norm(cell, axis=1))
     norms2 = np.sort(np.linalg.norm(op @ cell, axis=1))
     if (norms2 > norms1 + 1e-12).any():
@@ -127,11 +153,13 @@ def _pbc3(pbc):
     return out
 
 
-def wrap_positions_eps0(positions, cell):
-    """ase.geometry.wrap_positions(positions, cell, pbc=True, eps=0): map into [0,1)."""
+def wrap_positions_eps0(positions, cell, pbc=True):
+    """ase.geometry.wrap_positions(positions, cell, pbc, eps=0): periodic fractional coordinates into [0,1)."""
+    pbc = _pbc3(pbc)
     fractional = np.linalg.solve(cell.T, np.asarray(positions).T).T
     for i in range(3):
-        fractional[:, i] %= 1.0
+        if pbc[i]:
+            fractional[:, i] %= 1.0
     return np.dot(fractional, cell)
 
 
@@ -145,11 +173,9 @@ def naive_find_mic(v, cell):
 
 def general_find_mic(v, cell, pbc=True):
     pbc = _pbc3(pbc)
-    if not pbc.all():
-        raise NotImplementedError("find_mic restatement: only pbc=True in all directions")
-    rcell, _ = minkowski_reduce(cell)
-    positions = wrap_positions_eps0(v, rcell)
-    ranges = [np.arange(-1, 2) for _ in range(3)]
+    rcell, _ = minkowski_reduce(cell, pbc)
+    positions = wrap_positions_eps0(v, rcell, pbc)
+    ranges = [np.arange(-1 * p, p + 1) for p in pbc.astype(int)]
     hkls = np.array([(0, 0, 0)] + list(itertools.product(*ranges)))
     vrvecs = hkls @ rcell
     x = positions + vrvecs[:, None]

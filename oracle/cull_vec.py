@@ -54,27 +54,35 @@ def _pdist_max_ge(r, cutoff):
     return bad
 
 
-def find_mic_batch(d, cell):
-    """ase.geometry.find_mic (oracle/ase_mic.py:find_mic, pbc all True) applied independently to each fragment's
-    vector set d[k] (n, NA, 3).  Returns the minimum-image vectors (n, NA, 3)."""
+def find_mic_batch(d, cell, pbc=True):
+    """ase.geometry.find_mic (oracle/ase_mic.py:find_mic) applied independently to each fragment's vector set d[k]
+    (n, NA, 3).  Returns the minimum-image vectors (n, NA, 3).  With a non-periodic direction the naive form is
+    never tried (find_mic: dim < 3) and the image search runs over the periodic directions only."""
     cell = np.asarray(cell, dtype=float)
+    pbc = np.broadcast_to(np.asarray(pbc, dtype=bool), (3,))
     n, na, _ = d.shape
-    flat = d.reshape(-1, 3)
-    f = np.linalg.solve(cell.T, flat.T).T
-    f -= np.floor(f + 0.5)
-    vmin = (f @ cell).reshape(n, na, 3)
-    vlen = _norm_rows(vmin)
-    half = 0.5 * min(np.linalg.norm(cell, axis=1))
-    naive_ok = (vlen < half).all(axis=1)
+    if not pbc.any():
+        return d.copy()
+    if pbc.all():
+        flat = d.reshape(-1, 3)
+        f = np.linalg.solve(cell.T, flat.T).T
+        f -= np.floor(f + 0.5)
+        vmin = (f @ cell).reshape(n, na, 3)
+        vlen = _norm_rows(vmin)
+        half = 0.5 * min(np.linalg.norm(cell, axis=1))
+        naive_ok = (vlen < half).all(axis=1)
+    else:
+        vmin = np.zeros_like(d)
+        naive_ok = np.zeros(n, dtype=bool)
     redo = np.where(~naive_ok)[0]
     if redo.size:
-        rcell, _ = ase_mic.minkowski_reduce(cell)
-        hkls = np.array([(0, 0, 0)] + list(itertools.product(*[np.arange(-1, 2)] * 3)))
+        rcell, _ = ase_mic.minkowski_reduce(cell, pbc)
+        hkls = np.array([(0, 0, 0)] + list(itertools.product(*[np.arange(-1 * p, p + 1) for p in pbc.astype(int)])))
         vrvecs = hkls @ rcell
         for lo in range(0, redo.size, 20000):  # 28 images x 20000 x NA x 3 doubles per chunk
             sel = redo[lo:lo + 20000]
             v = d[sel].reshape(-1, 3)
-            pos = ase_mic.wrap_positions_eps0(v, rcell)
+            pos = ase_mic.wrap_positions_eps0(v, rcell, pbc)
             x = pos[None, :, :] + vrvecs[:, None, :]
             lengths = _norm_rows(x)
             idx = np.argmin(lengths, axis=0)
@@ -113,9 +121,7 @@ def accept_mask(Z, R, entity_ids, combs, model, periodic_cell=None, return_coord
     r = R[atoms]  # (n, NA, 3)
     ok = np.ones(len(combs), dtype=bool)
     if periodic_cell is not None:
-        if not np.all(periodic_cell.pbc):
-            raise NotImplementedError("vectorised culling: pbc=True only")
-        r = find_mic_batch(r - r[:, :1, :], periodic_cell.cell_v)
+        r = find_mic_batch(r - r[:, :1, :], periodic_cell.cell_v, periodic_cell.pbc)
         ok &= ~_pdist_max_ge(r, periodic_cell.cutoff)
     crit = model.criteria
     if crit is not None and crit.cutoff is not None and len(combs):

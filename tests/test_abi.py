@@ -27,13 +27,13 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/mbgdml_b200.h but not exported"
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
-    assert _native.load_library().mbg_abi_version() == 2
+    assert _native.load_library().mbg_abi_version() == 3
 
 
 def test_struct_layouts_match_header_sizes():
     # sizes implied by the header on LP64
     assert ctypes.sizeof(_native.ModelDesc) == 16 + 24 + 32 + 8 + 16 + 8 + 8
-    assert ctypes.sizeof(_native.SystemDesc) == 8 + 32 + 8 + 16
+    assert ctypes.sizeof(_native.SystemDesc) == 8 + 32 + 8 + 16 + 8
     assert ctypes.sizeof(_native.Job) == 8 + 24 + 8 + 8 + 16
     assert ctypes.sizeof(_native.JobStats) == 24
 

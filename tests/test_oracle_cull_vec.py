@@ -39,3 +39,22 @@ def test_non_periodic_and_range_criteria():
             vec = cull_vec.accept_mask(Z, R, eids, combs, m, None)
             scalar = np.array([orc._fragment(Z, R, eids, c, m, None) is not None for c in combs])
             assert np.array_equal(vec, scalar)
+
+
+@pytest.mark.parametrize("pbc", [(True, True, False), (False, True, True), (True, False, False)])
+def test_vectorised_mask_equals_scalar_oracle_partial_pbc(pbc):
+    """Cell(pbc=...) with a non-periodic direction (periodic.py:40-59 -> find_mic(..., pbc)): slab / wire geometries."""
+    g = load("periodic_40h2o.npz")
+    oms = oracle_models(unpack_models(g), cutoffs_from(g["crit_cutoffs"]))
+    Z, eids, cids = g["cub_Z"], g["cub_eids"], g["cub_cids"]
+    rng = np.random.default_rng(1)
+    for tag in ("cub", "tri"):
+        R = g[tag + "_R"][0]
+        cell = orc.Cell(g[tag + "_cell"], pbc=pbc)
+        for m in oms[1:]:
+            combs = orc.gen_combs_array(orc.get_avail_entities(cids, m.comp_ids))
+            vec = cull_vec.accept_mask(Z, R, eids, combs, m, cell)
+            sel = rng.choice(len(combs), min(len(combs), 400), replace=False)
+            scalar = np.array([orc._fragment(Z, R, eids, combs[i], m, cell) is not None for i in sel])
+            assert np.array_equal(vec[sel], scalar)
+            assert 0 < vec.sum() < len(combs)
