@@ -151,9 +151,9 @@ int mbg_context_synchronize(mbg_context_t ctx);
 /* Choose the kernel that evaluates _predict_gdml_wkr (gdml_predict.py:94-142): MBG_CONTRACT_*.  Both give the
  * same results to rounding; the choice exists so that the benchmark can time one against the other. */
 int mbg_context_set_contraction(mbg_context_t ctx, int kind);
-/* Choose how mbg_predict / mbg_accept_mask generate the candidates of a 2- or 3-body job given as entity sets (the tuples of
- * utils.gen_combs, utils.py:449-489, that the reference feeds to the slice -> r_mic -> criteria loop,
- * gdml_predict.py:210-235): MBG_CULL_*.  The accepted fragments and their order do not depend on the choice.  In a
+/* Choose how mbg_predict / mbg_accept_mask generate the candidates of a job given as entity sets (2- and 3-body jobs;
+ * 4- to 6-body jobs over one homogeneous set), i.e. the tuples of utils.gen_combs, utils.py:449-489, that the
+ * reference feeds to the slice -> r_mic -> criteria loop, gdml_predict.py:210-235: MBG_CULL_*.  The accepted fragments and their order do not depend on the choice.  In a
  * plain call the pair list costs one device -> host read of a count per job; a prepared step (mbg_step_*) takes the
  * choice in force when it is created and keeps the count on the device. */
 int mbg_context_set_culling(mbg_context_t ctx, int kind);

@@ -955,7 +955,8 @@ constexpr long long kPairListMinCand = 1ll << 23;  // MBG_CULL_AUTO: candidates 
 static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, int n_frames,
                               long long n_cand_total, int* mode, double* thr) {
   if (ctx->culling == MBG_CULL_FULL) return false;
-  if (j.explicit_combs || (j.order != 2 && j.order != 3)) return false;
+  // 2- and 3-body jobs over entity sets; homogeneous sets up to 6-body (C(deg, order - 1) stays far below 2^61)
+  if (j.explicit_combs || j.order < 2 || (j.order > 3 && !(j.homogeneous && j.order <= 6 && j.n_set <= 4096))) return false;
   if (ctx->culling == MBG_CULL_AUTO && n_cand_total < kPairListMinCand) return false;
   const int n0 = j.homogeneous ? j.n_set : j.set_off[1] - j.set_off[0];
   if ((long long)n_frames * n0 >= (1ll << 30)) return false;

@@ -28,7 +28,7 @@ constexpr int kPairWarps = 8;  // rows (frame, a) per block of k_pair_bits
 struct PairListDev {
   unsigned long long* adj;  // [n_frames][n_set][W]: bit b of row a set <=> b > a and the pair may pass
   int* deg;                 // [n_frames * n_set]: set bits of a row
-  long long* row_cnt;       // [n_frames * n_set]: reduced candidates of a row: C(deg, 2) (order 3) or deg (order 2)
+  long long* row_cnt;       // [n_frames * n_set]: reduced candidates of a row: C(deg, order - 1)
   long long* row_off;       // [n_frames * n_set + 1]: exclusive prefix sum of row_cnt; the last entry is the total
   int W;                    // 64-bit words per row
   int n_rows;               // n_frames * n0
@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_pair_bits(const SysDev sys,
   for (int o = 16; o; o >>= 1) deg += __shfl_xor_sync(0xffffffffu, deg, o);
   if (lane == 0) {
     nl.deg[row] = deg;
-    nl.row_cnt[row] = job.order == 3 ? (long long)deg * (deg - 1) / 2 : deg;
+    // C(deg, order - 1) combinations of the row's neighbours (orders above 3: from the job's binomial table)
+    nl.row_cnt[row] = job.order == 2 ? deg : job.order == 3 ? (long long)deg * (deg - 1) / 2
+                                                            : job.binom[(long long)deg * (job.order + 1) + (job.order - 1)];
   }
 }
 
@@ -235,6 +237,35 @@ __device__ __forceinline__ int decode_reduced(const SysDev& sys, const double* _
   bool ok = true;
   if (j.order == 2) {
     pos[1] = select_bit(bits, nl.W, (int)local);
+  } else if (j.order > 3) {
+    // (order - 1)-subsets of the row's deg neighbours in lexicographic order: decode_tuple's unranking with n = deg
+    // (the job's binomial table covers every m <= n_set), then all pairs among them must be in the list
+    const int n_nb = nl.deg[row], m = j.order - 1, w = j.order + 1;
+    long long rem = local;
+    int prev = -1;
+    for (int s = 0; s < m; ++s) {
+      const int r = m - s - 1;
+      int p;
+      if (r == 0) {
+        p = prev + 1 + (int)rem;
+      } else {
+        const long long top = j.binom[(long long)(n_nb - prev - 1) * w + (r + 1)];
+        const long long target = top - rem;
+        int lo2 = r, hi2 = n_nb - prev - 2;
+        while (lo2 < hi2) {
+          const int mid = (lo2 + hi2 + 1) >> 1;
+          if (j.binom[(long long)mid * w + (r + 1)] < target) lo2 = mid; else hi2 = mid - 1;
+        }
+        p = n_nb - 1 - lo2;
+        rem -= top - j.binom[(long long)(n_nb - p) * w + (r + 1)];
+      }
+      pos[s + 1] = select_bit(bits, nl.W, p);
+      prev = p;
+    }
+    for (int s = 1; s < j.order && ok; ++s) {
+      const unsigned long long* bits_s = nl.adj + (*frame * n + pos[s]) * nl.W;
+      for (int t = s + 1; t < j.order; ++t) ok = ok && ((bits_s[pos[t] >> 6] >> (pos[t] & 63)) & 1ull);
+    }
   } else {
     // pairs (i < k) of the row's deg neighbours in lexicographic order: S(i) = i deg - i (i + 1) / 2 pairs start below i
     const long long deg = nl.deg[row];

@@ -219,3 +219,21 @@ def test_public_api_512_h2o_auto_switch():
     finally:
         ctx.set_culling("auto")
     assert st0[2][0] == 22238720 and 50000 < st0[2][2] < 100000
+
+
+def test_four_body_masks_equal_and_match_the_oracle(ctx):
+    """Homogeneous 4-body job (12-atom water tetramers): a row's reduced candidates are the C(deg, 3) triples of its
+    neighbours, unranked with the job's binomial table; periodic box (vs the oracle culling too) and cluster."""
+    md = synthetic.make_model(["h2o"] * 4, n_train=4, sig=500.0, seed=31)
+    Z, R, eids, cids, cell_v = synthetic.make_periodic_box(n_mol=48, box=11.3, n_frames=2, seed=6, frame_sigma=0.1)
+    cell = mb.Cell(cell_v, pbc=True)
+    masks = _masks(ctx, Z, R, eids, cids, b200_models([md], [13.0]), cell)
+    _assert_same(masks)
+    assert masks["full"][0].shape == (2, 194580)
+    om = oracle_models([md], [13.0])[0]
+    combs = orc.gen_combs_array([list(range(48))] * 4)
+    want = cull_vec.accept_mask(Z, R[1], eids, combs, om, orc.Cell(cell_v))
+    assert np.array_equal(masks["pairlist"][0][1] == 1, want) and 0 < want.sum() < len(combs)
+    Zc, Rc, ec, cc = synthetic.make_cluster(40, seed=8)
+    for desc, cut in (("com", 11.0), ("pair", 7.0)):
+        _assert_same(_masks(ctx, Zc, Rc, ec, cc, b200_models([md], [cut], desc=desc), None))
