@@ -43,7 +43,7 @@ extern "C" {
 #define MBG_CONTRACT_DMMA_WAVE 3 /* the same arithmetic, wave-launched one CTA per query batch   (csrc/matern_mma.cuh) */
 
 /* Candidate generation (mbg_context_set_culling). */
-#define MBG_CULL_AUTO 0     /* MBG_CULL_PAIRLIST from 2^23 candidates per job on (where it applies), else MBG_CULL_FULL */
+#define MBG_CULL_AUTO 0     /* MBG_CULL_PAIRLIST from 2^21 candidates per job on (where it applies), else MBG_CULL_FULL */
 #define MBG_CULL_FULL 1     /* every tuple of utils.gen_combs is unranked and tested, as the reference does (csrc/enumerate.cuh) */
 #define MBG_CULL_PAIRLIST 2 /* per-frame pair list first, only tuples of mutually admissible pairs are tested: same accepted
                                set, same order, cost ~ accepted fragments instead of C(n, order)          (csrc/pairlist.cuh) */

@@ -951,7 +951,7 @@ static long long shard_candidates(long long b0, long long blocks, int shard_rank
 }
 
 // Pair-list candidate generation (pairlist.cuh): does it apply to this job, and with which pair condition?
-constexpr long long kPairListMinCand = 1ll << 23;  // MBG_CULL_AUTO: candidates per job (all frames) from which it is used
+constexpr long long kPairListMinCand = 1ll << 21;  // MBG_CULL_AUTO: candidates per job (all frames) from which it is used
 static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& j, const mbg_model_t m, int n_frames,
                               long long n_cand_total, int* mode, double* thr) {
   if (ctx->culling == MBG_CULL_FULL) return false;
@@ -1131,17 +1131,22 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
       TRY(launch_matern_small(ctx, NA, m->use_E, q, slot));
       continue;
     }
-    // CTA-cooperative persistent kernel (MBG_MMA_CFG=9: off): always for wide fragments (13-18 atoms), and for 9-12
+    // CTA-cooperative persistent kernel (MBG_MMA_CFG=9: off): always for fragments of 10-18 atoms, and for 9
     // atoms when the launch can only be mid-size -- at most kCtaMaxCandidates candidates (a frame or two of an MD
     // box), at least four rounds of batches if all were accepted: there its device-side tail splitting is worth 2.7 %
     // (one 140-H2O frame 11.03 -> 10.73 ms), while large launches (-1.7 %) and small ones stay on the per-warp kernel.
     // Without a criteria and without a cell nothing is culled (heterogeneous product spaces aside) and the candidates
     // ARE the count: the window is then 8 .. 96 rounds of batches.
+    // 10- to 12-atom fragments (two m-tiles per warp, 8 warps) behave like the wide ones: the CTA form is quicker at
+    // every size measured (29 000 / 116 200 [h2o, h2o, meoh] fragments: 12.80 -> 12.43 ms / 50.53 -> 49.44 ms, 0.92 of
+    // the DMMA peak; water trimers of the same runs: 44.15 per-warp vs 44.91 ms).  When the pair list sized this
+    // chunk, n_up counts reduced candidates, of which ~5 x more are accepted than of all tuples.
     const long long bound_batches = n_up * m->P / (NA == 9 ? 288 : 128);
     const bool culled = m->crit.kind != 0 || s.periodic || !(j.homogeneous || j.explicit_combs);
-    const bool mid_size = NA >= 9 && (culled ? n_up <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count
+    const long long cand_equiv = (use_nl && !ctx->capturing) ? 5 * n_up : n_up;
+    const bool mid_size = NA >= 9 && (culled ? cand_equiv <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count
                                              : bound_batches >= 8ll * ctx->sm_count && bound_batches <= 96ll * ctx->sm_count);
-    if ((NA >= 13 || mid_size || (NA >= 9 && ctx->mma_cfg == 10)) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {  // 10 (developer): always from 9 atoms on
+    if ((NA >= 10 || mid_size || (NA >= 9 && ctx->mma_cfg == 10)) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {  // 10 (developer): always from 9 atoms on
       MaternMmaArgs w;
       memset(&w, 0, sizeof(w));
       w.sys = s, w.R = dR;

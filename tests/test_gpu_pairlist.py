@@ -195,7 +195,7 @@ def test_mixed_predictions_equal_plain_sharded_and_step(ctx):
 
 
 def test_public_api_512_h2o_auto_switch():
-    """MBG_CULL_AUTO through the public API: a 512-H2O frame has 22.2 M trimer candidates (> 2^23), so the plain call
+    """MBG_CULL_AUTO through the public API: a 512-H2O frame has 22.2 M trimer candidates (> 2^21), so the plain call
     (first `predict`) and the prepared step (second `predict`: graph replay, reduced count on the device) both go
     through the pair list; the same prediction with the full enumeration forced is the reference point."""
     ctx = _native.get_context()
