@@ -154,8 +154,9 @@ int mbg_context_set_contraction(mbg_context_t ctx, int kind);
 /* Choose how mbg_predict / mbg_accept_mask generate the candidates of a job given as entity sets (2- and 3-body jobs;
  * 4- to 6-body jobs over one homogeneous set), i.e. the tuples of utils.gen_combs, utils.py:449-489, that the
  * reference feeds to the slice -> r_mic -> criteria loop, gdml_predict.py:210-235: MBG_CULL_*.  The accepted fragments and their order do not depend on the choice.  In a
- * plain call the pair list costs one device -> host read of a count per job; a prepared step (mbg_step_*) takes the
- * choice in force when it is created and keeps the count on the device. */
+ * plain call a job of 2^23 candidates or more reads one count back from the device (it sizes the launches that
+ * follow); smaller jobs and prepared steps (mbg_step_*, which take the choice in force when they are created) keep the
+ * count on the device. */
 int mbg_context_set_culling(mbg_context_t ctx, int kind);
 /* Launch counters since context creation: number of kernels this library launched. */
 int mbg_context_launch_count(mbg_context_t ctx, int64_t *n_launches);

@@ -992,12 +992,14 @@ static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& 
   return true;
 }
 
-// Build the pair list of a job on the context's stream.  A plain call brings the reduced candidate count to the host
-// (the one synchronisation of this path: it sizes the cull launches and the record buffers by what can be accepted);
-// inside a prepared step (captured graph) the count stays on the device, *n_reduced = -1, and the launches that follow
-// keep the full space as their bound.
+// Build the pair list of a job on the context's stream.  With want_count a plain call brings the reduced candidate
+// count to the host (the one synchronisation of this path: it sizes the cull launches and the record buffers by what
+// can be accepted -- worth it from kPairListSyncCand candidates on, where launches over the full space would cost more
+// than the round trip); otherwise, and always inside a prepared step (captured graph), the count stays on the device,
+// *n_reduced = -1, and the launches that follow keep the full space as their bound.
+constexpr long long kPairListSyncCand = 1ll << 23;  // 512 H2O (22 M): 0.47 ms with the count, 0.78 ms without; box140 x 8 (3.6 M): equal
 static int build_pair_list(mbg_context_t ctx, Scratch& sc, const SysDev& s, const JobDev& j, const double* dR, int n_frames,
-                           int mode, double thr, PairListDev& nl, long long* n_reduced) {
+                           int mode, double thr, PairListDev& nl, long long* n_reduced, bool want_count = true) {
   nl.hetero = j.homogeneous ? 0 : 1;
   nl.n0 = j.homogeneous ? j.n_set : j.set_off[1] - j.set_off[0];
   nl.W = ((j.homogeneous ? j.n_set : j.set_off[2] - j.set_off[1]) + 63) / 64;
@@ -1016,7 +1018,7 @@ static int build_pair_list(mbg_context_t ctx, Scratch& sc, const SysDev& s, cons
   ctx->launches += 2;
   CUDA_TRY(cudaGetLastError());
   *n_reduced = -1;
-  if (ctx->capturing) return MBG_OK;
+  if (ctx->capturing || !want_count) return MBG_OK;
   CUDA_TRY(cudaMemcpyAsync(ctx->h_totals, nl.row_off + nl.n_rows, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   *n_reduced = ctx->h_totals[0];
@@ -1042,9 +1044,11 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
   int nl_mode = 0;
   double nl_thr = 0;
   const bool use_nl = !decomp && pair_list_applies(ctx, s, j, m, n_frames, n_cand_total, &nl_mode, &nl_thr);
+  bool reduced_known = false;  // the chunks below are sized by the pair list's count instead of the full space
   if (use_nl) {
     long long n_reduced = 0;
-    TRY(build_pair_list(ctx, sc, s, j, dR, n_frames, nl_mode, nl_thr, nl, &n_reduced));
+    TRY(build_pair_list(ctx, sc, s, j, dR, n_frames, nl_mode, nl_thr, nl, &n_reduced, *n_cand_shard_out >= kPairListSyncCand));
+    reduced_known = n_reduced >= 0;
     long long* enum_tot = sc.job_totals.as<long long>() + 2 * (size_t)job_slot + 1;
     if (j.homogeneous) {  // every tuple is ascending: the enumerated count is this shard's candidate count
       k_add_total<<<1, 1, 0, ctx->stream>>>(enum_tot, *n_cand_shard_out);
@@ -1143,7 +1147,7 @@ static int run_job_pw(mbg_context_t ctx, Scratch& sc, const SysDev& s, const Job
     // chunk, n_up counts reduced candidates, of which ~5 x more are accepted than of all tuples.
     const long long bound_batches = n_up * m->P / (NA == 9 ? 288 : 128);
     const bool culled = m->crit.kind != 0 || s.periodic || !(j.homogeneous || j.explicit_combs);
-    const long long cand_equiv = (use_nl && !ctx->capturing) ? 5 * n_up : n_up;
+    const long long cand_equiv = reduced_known ? 5 * n_up : n_up;
     const bool mid_size = NA >= 9 && (culled ? cand_equiv <= kCtaMaxCandidates && bound_batches >= 4ll * ctx->sm_count
                                              : bound_batches >= 8ll * ctx->sm_count && bound_batches <= 96ll * ctx->sm_count);
     if ((NA >= 10 || mid_size || (NA >= 9 && ctx->mma_cfg == 10)) && !m->use_lat && ctx->mma_cfg != 9 && ctx->mma_cfg != 1) {  // 10 (developer): always from 9 atoms on
