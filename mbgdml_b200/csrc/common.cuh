@@ -12,7 +12,7 @@ constexpr int kMaxOrder = MBG_MAX_ORDER;
 constexpr int kMaxFragAtoms = MBG_MAX_FRAG_ATOMS;
 constexpr int kMaxAlchemy = MBG_MAX_ALCHEMY;
 constexpr int kCullThreads = 256;  // candidates per cull/compact block
-constexpr int kShardGranule = 64;  // sharding granule: consecutive candidates that stay on one rank (divides kCullThreads)
+constexpr int kShardGranule = 16;  // sharding granule: consecutive candidates that stay on one rank (divides kCullThreads); 64 until r2: 8 ranks of box140 x 64 frames were 0.56 % apart
 
 // One periodic cell on device (mbgdml/periodic.py:32-140): lives in device memory so that every frame of a batch can
 // have its own (NPT trajectories, the strained boxes of the finite-difference virial, stress.py:75-152) and so that

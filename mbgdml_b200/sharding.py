@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-GRANULE = 64  # csrc/common.cuh: kShardGranule
+GRANULE = 16  # csrc/common.cuh: kShardGranule
 
 
 def owner_of(candidate_index, world):
