@@ -45,3 +45,37 @@ def test_attributes_equal_the_reference_objects():
     lat = dict(unpack_models(load("lattice_model.npz"), prefix="tri_m")[0])
     m, rm = mb.gdmlModel(dict(lat)), ref.gdmlModel(dict(lat))
     assert np.array_equal(m.lat_and_inv[0], rm.lat_and_inv[0]) and np.array_equal(m.lat_and_inv[1], rm.lat_and_inv[1])
+
+
+def test_training_mode_helpers_on_the_host():
+    """Host logic of the predictors' training mode (no GPU): geometries rebuilt from descriptor + compressed Jacobian
+    (what ``GDMLPredict.predict()`` without R sends to the device) equal the geometries the descriptors came from, up to
+    the translation; ``GDMLTorchAssemble`` maps the entries of ``J`` to columns like the reference's ``_forward``
+    (torchtools.py:119-153)."""
+    import torch
+
+    from mbgdml_b200 import synthetic
+    from mbgdml_b200._gdml.torchtools import GDMLTorchAssemble
+    from mbgdml_b200.gdml_predict import geometries_from_desc
+
+    for comp in (["h2o"], ["h2o", "meoh"], ["h2o", "h2o", "h2o"]):
+        R = synthetic.fragment_geometries(np.random.default_rng(7), comp, 11)
+        n = R.shape[1]
+        X, G = np.zeros((11, n * (n - 1) // 2)), np.zeros((11, n * (n - 1) // 2, 3))
+        for t in range(11):
+            X[t], G[t] = orc.from_r(R[t].reshape(-1))
+        got = geometries_from_desc(X, G)
+        assert np.abs(got - (R - R[:, :1])).max() <= 1e-13
+        x2, g2 = orc.from_r(got[3].reshape(-1))  # same descriptor and Jacobian again
+        assert np.abs(x2 - X[3]).max() <= 1e-13 and np.abs(g2 - G[3]).max() <= 1e-12
+    with pytest.raises(ValueError):
+        geometries_from_desc(X, G[:, :-1])
+    T, n, dim_i = 5, 3, 9
+    asm = GDMLTorchAssemble([0, 3, 7, (4, 2, [1, 8]), (6, T * dim_i + 4, [0])], np.arange(6), 10.0, True,
+                            torch.zeros(T, 3), torch.zeros(T, 3, 3), out=None)
+    assert asm.n_atoms == n and asm.dim_i == dim_i and asm.n_perms == 2
+    dst, src = asm._columns(asm.J[1])
+    assert list(dst) == list(range(27, 36)) and list(src) == list(range(27, 36))
+    assert [list(c) for c in asm._columns(asm.J[2])] == [[T * dim_i + 2], [T * dim_i + 2]]  # energy column j % n_train
+    assert [list(c) for c in asm._columns(asm.J[3])] == [[4, 5], [19, 26]]
+    assert [list(c) for c in asm._columns(asm.J[4])] == [[6], [T * dim_i + 4]]
