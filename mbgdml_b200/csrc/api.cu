@@ -840,6 +840,7 @@ static int build_job(mbg_context_t ctx, Tables& tb, const mbg_system_desc* sys, 
     if (job->set_offsets[0] != 0) return fail(MBG_ERR_ARG, "set_offsets[0] must be 0");
     long long prod = 1;
     int na = 0;
+    j.sets_ascending = 1;
     for (int s = 0; s < m->order; ++s) {
       const int lo = job->set_offsets[s], hi = job->set_offsets[s + 1];
       if (hi < lo) return fail(MBG_ERR_ARG, "set_offsets not monotone");
@@ -847,6 +848,7 @@ static int build_job(mbg_context_t ctx, Tables& tb, const mbg_system_desc* sys, 
       int slot_atoms = -1;
       for (int k = lo; k < hi; ++k) {
         const int e = job->set_entities[k];
+        if (k > lo && e <= job->set_entities[k - 1]) j.sets_ascending = 0;
         if (e < 0 || e >= sys->n_entities) return fail(MBG_ERR_ARG, "set entity id %d out of range", e);
         if (slot_atoms < 0) slot_atoms = ent_size(e);
         if (ent_size(e) != slot_atoms)
@@ -960,9 +962,11 @@ static bool pair_list_applies(mbg_context_t ctx, const SysDev& s, const JobDev& 
   if (ctx->culling == MBG_CULL_AUTO && n_cand_total < kPairListMinCand) return false;
   const int n0 = j.homogeneous ? j.n_set : j.set_off[1] - j.set_off[0];
   if ((long long)n_frames * n0 >= (1ll << 30)) return false;
-  if (!j.homogeneous)  // a row's reduced candidates are addressed with 32-bit neighbour indices
+  if (!j.homogeneous) {  // a row's reduced candidates are addressed with 32-bit neighbour indices
+    if (!j.sets_ascending) return false;  // k_count_ascending searches the sets
     for (int s = 1; s < j.order; ++s)
       if (j.set_off[s + 1] - j.set_off[s] > (1 << 24)) return false;
+  }
   const CritDev& c = m->crit;
   const bool upper = c.kind != MBG_CRIT_NONE && (c.bound == MBG_BOUND_UPPER || c.bound == MBG_BOUND_RANGE);
   *thr = std::numeric_limits<double>::infinity();

@@ -62,6 +62,7 @@ struct JobDev {
   const long long* binom;   // [(n_set + 1) x (order + 1)] binomial table, binom[m * (order + 1) + r] = C(m, r)
   int set_off[kMaxOrder + 1];
   int slot_atoms[kMaxOrder]; // atoms per entity of each slot (sets only)
+  int sets_ascending;        // every slot's set lists its entities in ascending order (what get_avail_entities yields)
   const int* set_ent;       // concatenated per-slot entity ids (device)
   const int* combs;         // [n][order] (device) when explicit
   long long cand_per_frame; // product size, C(n_set, order), or n_combs
