@@ -563,8 +563,36 @@ def case_train_kernel_cols():
     np.savez_compressed(os.path.join(GOLD, "train_kernel_cols.npz"), **out)
 
 
+def case_slab():
+    """Partial periodicity (Cell(pbc=...) with a non-periodic direction, periodic.py:40-59 -> find_mic(d, cell_v, pbc)):
+    the 40-H2O box of case_periodic as a slab and as a wire, cubic and triclinic, through the live reference."""
+    out = {}
+    mds = synth_water_models(32, seed=40)
+    out.update(pack_models("m", mds))
+    cuts = [None, 5.0, 8.5]
+    out["crit_cutoffs"] = np.array([np.nan, 5.0, 8.5])
+    Z, R, eids, cids, cell = syn.make_periodic_box(n_mol=40, box=12.4, n_frames=2, seed=8, frame_sigma=0.08)
+    tri = np.array([[12.6, 0.0, 0.0], [2.8, 12.1, 0.0], [-1.9, 3.1, 11.8]])
+    Rt = np.linalg.solve(cell.T, R.reshape(-1, 3).T).T.reshape(R.shape) @ tri
+    out.update(Z=Z, eids=eids, cids=cids, cub_R=R, cub_cell=cell, tri_R=Rt, tri_cell=tri)
+    pbcs = [(True, True, False), (False, True, True), (True, False, False)]
+    out["pbcs"] = np.array(pbcs)
+    for tag, cv, Rk in (("cub", cell, R), ("tri", tri, Rt)):
+        for k, pbc in enumerate(pbcs):
+            ref = mbePredict(ref_models(mds, cuts), predict_gdml, periodic_cell=Cell(cv, pbc=pbc)).predict(Z, Rk, eids, cids)
+            got = orc.mbe_predict(orc_models(mds, cuts), Z, Rk, eids, cids, periodic_cell=orc.Cell(cv, pbc=pbc))
+            check(f"slab {tag} {pbc} E", got[0], ref[0]); check(f"slab {tag} {pbc} F", got[1], ref[1])
+            full = mbePredict(ref_models(mds, cuts), predict_gdml, periodic_cell=Cell(cv, pbc=True)).predict(Z, Rk, eids, cids)
+            assert relerr(full[0], ref[0]) > 1e-6  # the flags matter
+            out[f"{tag}_E{k}"], out[f"{tag}_F{k}"] = ref[0], ref[1]
+    np.savez_compressed(os.path.join(GOLD, "slab_40h2o.npz"), **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="raise", under="ignore")
+    if "--only-slab" in sys.argv:
+        print("slab / wire"); case_slab()
+        sys.exit(0)
     if "--only-lattice" in sys.argv:
         print("lattice models"); case_lattice()
         sys.exit(0)
@@ -581,5 +609,6 @@ if __name__ == "__main__":
     print("train kernel"); case_train_kernel()
     print("lattice models"); case_lattice()
     print("train kernel, column subsets"); case_train_kernel_cols()
+    print("slab / wire"); case_slab()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden fixtures written: %.1f KB" % (total / 1024))

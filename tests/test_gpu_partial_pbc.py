@@ -88,3 +88,17 @@ def test_slab_accept_masks_and_prediction(pbc, tag):
     # the fully periodic box gives something else: the flags are not ignored
     E_full, _ = mb.mbePredict(models, mb.predict_gdml, periodic_cell=mb.Cell(g[tag + "_cell"], pbc=True)).predict(Z, R, eids, cids)
     assert abs(E_full[0] - E_o) > 1e-6 * abs(E_o)
+
+
+def test_slab_and_wire_golden_from_the_live_reference():
+    """Energies and forces of the UNMODIFIED reference (`mbePredict` + `predict_gdml` + `Cell(pbc=...)`, its find_mic
+    the restated one) for the 40-H2O box as slab / wire, cubic and triclinic: tests/golden/slab_40h2o.npz."""
+    g = load("slab_40h2o.npz")
+    mds = unpack_models(g)
+    models = b200_models(mds, cutoffs_from(g["crit_cutoffs"]))
+    for tag in ("cub", "tri"):
+        for k in range(len(g["pbcs"])):
+            pbc = tuple(bool(x) for x in g["pbcs"][k])
+            pred = mb.mbePredict(models, mb.predict_gdml, periodic_cell=mb.Cell(g[tag + "_cell"], pbc=pbc))
+            E, F = pred.predict(g["Z"], g[tag + "_R"][:1], g["eids"], g["cids"])
+            assert relerr(E, g[f"{tag}_E{k}"][:1]) <= TOL and relerr(F, g[f"{tag}_F{k}"][:1]) <= TOL, (tag, pbc)
