@@ -58,3 +58,18 @@ def test_vectorised_mask_equals_scalar_oracle_partial_pbc(pbc):
             scalar = np.array([orc._fragment(Z, R, eids, combs[i], m, cell) is not None for i in sel])
             assert np.array_equal(vec[sel], scalar)
             assert 0 < vec.sum() < len(combs)
+
+
+def test_vectorised_mask_equals_scalar_oracle_four_body():
+    """4-body fragments (the reference point of tests/test_gpu_pairlist.py::test_four_body_...): periodic box."""
+    from mbgdml_b200 import synthetic
+
+    md = synthetic.make_model(["h2o"] * 4, n_train=4, sig=500.0, seed=31)
+    Z, R, eids, cids, cell_v = synthetic.make_periodic_box(n_mol=24, box=9.0, n_frames=1, seed=6, frame_sigma=0.1)
+    om = oracle_models([md], [13.0])[0]
+    cell = orc.Cell(cell_v, cutoff=6.5)  # above L/2: the general branch of find_mic decides
+    combs = orc.gen_combs_array([list(range(24))] * 4)
+    vec = cull_vec.accept_mask(Z, R[0], eids, combs, om, cell)
+    sel = np.random.default_rng(2).choice(len(combs), 500, replace=False)
+    scalar = np.array([orc._fragment(Z, R[0], eids, combs[i], om, cell) is not None for i in sel])
+    assert np.array_equal(vec[sel], scalar) and 0 < vec.sum() < len(combs)
