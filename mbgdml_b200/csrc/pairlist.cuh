@@ -9,6 +9,12 @@
 // (first_atoms_may_pass / fragment_accept, unchanged) still takes every decision that counts and the accepted set,
 // its order (frame, then lexicographic tuple == candidate rank) and the fragment records are identical to k_cull's.
 //
+// Job shapes: one homogeneous entity set, 2- to 6-body (a row's reduced candidates are the C(deg, order - 1)
+// combinations of its neighbours, every pair among them checked against the bits), and heterogeneous product spaces of
+// 2- and 3-body jobs ([h2o, meoh], [h2o, h2o, meoh], ...: one bit row per later slot, the ascending filter of
+// utils.gen_combs folded into the bits).  A plain call reads the reduced total back once when the job is large
+// (api.cu: kPairListSyncCand); otherwise, and inside captured steps, every kernel reads it on the device.
+//
 // Pair conditions (p_x = first atom of entity x, r = the fragment's final coordinates):
 //   * periodic cell (periodic.py:61-107): every r_i - r_j is p_i - p_j plus a lattice vector, so
 //     |r_i - r_j| >= the minimum-image length of p_i - p_j, and periodic.py:80-83 rejects when any pair distance
