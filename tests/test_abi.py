@@ -122,3 +122,16 @@ def test_cached_system_reuse_and_invalidation():
     assert s3 is not s2 and _engine.cached_system(Z, eids, Cell(np.eye(3) * 10.0, pbc=True), True) is s3
     assert _engine.cached_system(Z, eids, Cell(np.eye(3) * 11.0, pbc=True), True) is not s3
     assert list(s3.entity_offsets) == [0, 3, 6]
+
+
+def test_constants_of_the_python_mirror_match_the_header():
+    """#define values of include/mbgdml_b200.h against the constants _native.py passes through ctypes."""
+    text = open(os.path.join(ROOT, "include", "mbgdml_b200.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(MBG_[A-Z0-9_]+)\s+\(?(-?(?:0x)?[0-9a-fA-F]+)\)?", text)}
+    enums = dict(re.findall(r"\b(MBG_[A-Z0-9_]+)\s*=\s*(\d+)", text))
+    for name in ("CONTRACT_AUTO", "CONTRACT_FMA", "CONTRACT_DMMA", "CONTRACT_DMMA_WAVE", "CULL_AUTO", "CULL_FULL",
+                 "CULL_PAIRLIST"):
+        assert defs["MBG_" + name] == getattr(_native, name), name
+    for name in ("CRIT_NONE", "CRIT_COM_DISTANCE_SUM", "CRIT_MAX_ATOM_PAIR_DIST", "BOUND_UPPER", "BOUND_LOWER", "BOUND_RANGE"):
+        assert int(enums["MBG_" + name]) == getattr(_native, name), name
+    assert defs["MBG_ABI_VERSION"] == 3
